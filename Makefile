@@ -1,0 +1,49 @@
+# Builds libwebradio_b200.so (hand-written sm_100a CUDA behind the C ABI of include/webradio_b200.h)
+# and the test harness that drives the DspBlock drop-in classes.  nvcc cross-compiles without a GPU.
+#
+#   make            -> webradio_b200/libwebradio_b200.so
+#   make harness    -> tests/harness/libwr_blocks_harness.so  (C++ drop-in blocks + graph driver)
+#   make oracle     -> oracle/libwr_oracle.so and, where /root/reference is mounted, oracle/_ref/
+NVCC     ?= nvcc
+CXX      ?= g++
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS  := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude -Iwebradio_b200/csrc
+# sample path: every product/sum is an explicit _rn intrinsic; -fmad=false is belt and braces
+PARITY   := -fmad=false
+CSRC     := webradio_b200/csrc
+OBJ      := build/wr_bank.o build/wr_stage.o build/wr_spectrum.o build/wr_host.o
+LIB      := webradio_b200/libwebradio_b200.so
+HARNESS  := tests/harness/libwr_blocks_harness.so
+BLOCKSRC := webradio_b200/dsp/dspblock.cxx webradio_b200/dsp/downconverter.cxx webradio_b200/dsp/lowpass.cxx \
+            webradio_b200/dsp/demodulator.cxx webradio_b200/io/spectrumsink.cxx webradio_b200/dsp/gpubank.cxx
+
+.PHONY: all lib harness oracle clean
+all: lib
+lib: $(LIB)
+
+build/wr_bank.o: $(CSRC)/wr_bank.cu $(wildcard $(CSRC)/*.cuh) $(CSRC)/wr_common.h include/webradio_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) $(PARITY) -c $< -o $@
+build/wr_stage.o: $(CSRC)/wr_stage.cu $(wildcard $(CSRC)/*.cuh) $(CSRC)/wr_common.h include/webradio_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) $(PARITY) -c $< -o $@
+build/wr_spectrum.o: $(CSRC)/wr_spectrum.cu $(wildcard $(CSRC)/*.cuh) $(CSRC)/wr_common.h include/webradio_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+build/wr_host.o: $(CSRC)/wr_host.cpp $(CSRC)/wr_common.h include/webradio_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -Xcompiler -ffp-contract=off -x cu -c $< -o $@
+
+$(LIB): $(OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart_static -lpthread -ldl -lrt
+
+harness: $(HARNESS)
+$(HARNESS): tests/harness/graph_harness.cxx $(BLOCKSRC) $(wildcard webradio_b200/dsp/*.h webradio_b200/io/*.h) $(LIB)
+	$(CXX) -std=c++11 -O2 -fPIC -Wall -shared -Iinclude -Iwebradio_b200 -Iwebradio_b200/dsp -Iwebradio_b200/io \
+	  -o $@ tests/harness/graph_harness.cxx $(BLOCKSRC) -Lwebradio_b200 -lwebradio_b200 -Wl,-rpath,'$$ORIGIN/../../webradio_b200' -lpthread
+
+oracle:
+	$(MAKE) -C oracle port ref
+
+clean:
+	rm -rf build $(LIB) $(HARNESS)

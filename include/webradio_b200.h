@@ -1,0 +1,211 @@
+/*
+ * webradio_b200.h -- C ABI of libwebradio_b200.so, the B200 (sm_100a) implementation of
+ * WebRadio's per-receiver DSP hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types, no
+ * exceptions.  Every entry point names the reference interface it replaces
+ * (mikestir/webradio @ 6500296d, paths relative to the reference root).  The C++ classes in
+ * webradio_b200/dsp and webradio_b200/io (same names and methods as the reference's DspBlock
+ * subclasses) are thin callers of these functions; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - samples are float; IQ is interleaved [I0,Q0,I1,Q1,...] (reference src/dsp/dspblock.h:45)
+ *   - every function returns 0 on success and a negative WR_E* code on failure; the message is
+ *     available from wr_last_error() (thread-local).  A CUDA error never throws or aborts:
+ *     it maps to WR_ECUDA, as DspBlock::process() maps failure to `false`
+ *     (reference src/dsp/dspblock.cxx:192-195).
+ *   - there is NO CPU fallback: without a CUDA device every create call fails with WR_ENODEV.
+ *   - one caller thread per handle for the process calls; the per-receiver setters may be
+ *     called from any thread and take effect at the next block boundary (the reference applies
+ *     them unlocked from HTTP threads: src/web/receiverhandler.cxx:125-140).
+ */
+#ifndef WEBRADIO_B200_H
+#define WEBRADIO_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WR_OK        0
+#define WR_EINVAL   (-1)  /* bad argument */
+#define WR_ENODEV   (-2)  /* no usable CUDA device */
+#define WR_ECUDA    (-3)  /* CUDA runtime error (see wr_last_error) */
+#define WR_ENOMEM   (-4)
+#define WR_ESTATE   (-5)  /* call not valid in the handle's current state */
+
+/* Demodulator::Mode, same numbering (reference src/dsp/demodulator.h:41-47) */
+#define WR_MODE_AM   0
+#define WR_MODE_FM   1
+#define WR_MODE_USB  2
+#define WR_MODE_LSB  3
+
+#define WR_SINTABLE_SIZE 65536u  /* 1 << LOOKUP_BITS, reference src/dsp/downconverter.cxx:36 */
+
+/* wr_rx_reset flags */
+#define WR_RESET_PHASE     1u  /* NCO phase          (reference downconverter.h:58) */
+#define WR_RESET_CHANNEL   2u  /* channel FIR history (reference lowpass.h:64)      */
+#define WR_RESET_DEMOD     4u  /* prev_i / prev_q    (reference demodulator.h:60-61) */
+#define WR_RESET_AUDIO     8u  /* audio FIR history                                  */
+
+/* stage ids for wr_bank_read_stage / the strict stage blocks */
+#define WR_STAGE_CHANNEL 1     /* channel-filtered IQ, float[2*M1] */
+#define WR_STAGE_DEMOD   2     /* demodulated,         float[M1]   */
+
+/* ---------------------------------------------------------------- misc ---- */
+const char *wr_version(void);
+const char *wr_last_error(void);
+int wr_device_count(void);
+
+/* phaseStep for an IF: replaces the expression in DownConverter::setIF / ::init
+ * (reference src/dsp/downconverter.cxx:65,80). */
+int32_t wr_phase_step(int if_hz, unsigned sample_rate);
+
+/* The NCO table exactly as DownConverter's constructor builds it, with the host libm
+ * (reference src/dsp/downconverter.cxx:49-51).  out has WR_SINTABLE_SIZE entries. */
+void wr_build_sintable(float *out);
+
+/* Frequency-sampling low-pass design: replaces LowPass::init (window) + LowPass::recalculate
+ * (reference src/dsp/lowpass.cxx:102-110,164-189).  Host code (cold path, K0 in SURVEY.md 2a).
+ * ntaps a power of two reproduces the reference; other lengths use the same formulas mod ntaps. */
+int wr_lowpass_design(unsigned ntaps, unsigned passband_hz, unsigned sample_rate, float *coeff);
+
+/* ------------------------------------------------- receiver bank (fused) ---- */
+/*
+ * A bank is the batched form of N `Receiver` chains (reference src/radio.cxx:62-90):
+ *   DownConverter::process -> LowPass::process (IQ) -> Demodulator::process -> LowPass::process
+ *   (reference src/dsp/downconverter.cxx:91-114, lowpass.cxx:131-162, demodulator.cxx:77-115)
+ * for n_receivers receivers fed by n_streams tuner streams on one GPU, with all carried state
+ * (NCO phase, both FIR histories, prev I/Q) resident in HBM between calls.
+ * All receivers of a bank share the filter geometry (n1,d1,n2,d2); taps, IF, mode and the
+ * stream each receiver listens to are per receiver.
+ */
+typedef struct wr_bank wr_bank;
+
+wr_bank *wr_bank_create(int device, unsigned n_streams, unsigned n_receivers, unsigned max_frames,
+		unsigned n1, unsigned d1, unsigned n2, unsigned d2);
+void wr_bank_destroy(wr_bank *b);
+
+/* Replace the NCO table (default: wr_build_sintable at create). */
+int wr_bank_set_sintable(wr_bank *b, const float *table);
+
+/* Receiver::setFrontEnd analogue: which stream feeds receiver rx (default rx % n_streams). */
+int wr_rx_set_stream(wr_bank *b, unsigned rx, unsigned stream);
+/* DownConverter::setIF (reference downconverter.cxx:59-67) with the step precomputed. */
+int wr_rx_set_phase_step(wr_bank *b, unsigned rx, int32_t step);
+/* Coefficients as LowPass::recalculate leaves them in `coeff` (reference lowpass.cxx:182-189),
+ * i.e. coeff[0] multiplies the NEWEST sample.  stage 0 = channel filter, 1 = audio filter;
+ * ntaps must equal the bank geometry. */
+int wr_rx_set_taps(wr_bank *b, unsigned rx, int stage, const float *coeff, unsigned ntaps);
+/* Demodulator::setMode (reference demodulator.h:49). */
+int wr_rx_set_mode(wr_bank *b, unsigned rx, int mode);
+/* Clear carried state (OR of WR_RESET_*); mirrors what ctor/deinit do in the reference. */
+int wr_rx_reset(wr_bank *b, unsigned rx, unsigned flags);
+/* Read back NCO phase (reference downconverter.h:58) as of the last completed block. */
+int wr_rx_get_phase(wr_bank *b, unsigned rx, uint32_t *phase);
+
+/* One block through every receiver, HOST buffers (the DspBlock::process data convention,
+ * reference src/dsp/dspblock.cxx:177-195: synchronous, results host-visible on return).
+ *   iq_host    : [n_streams][nframes][2] float
+ *   audio_host : receiver r's floor(floor(nframes/d1)/d2) output frames start at r*audio_stride
+ * Keeps the tuner block in HBM for wr_bank_read_stage. */
+int wr_bank_process(wr_bank *b, const float *iq_host, unsigned nframes,
+		float *audio_host, size_t audio_stride);
+
+/* Same, with input and output already in HBM on the bank's device; asynchronous on
+ * cuda_stream (a cudaStream_t; NULL = the bank's own stream). */
+int wr_bank_process_device(wr_bank *b, const float *iq_dev, size_t stream_stride_frames,
+		unsigned nframes, float *audio_dev, size_t audio_stride, void *cuda_stream);
+
+/* Pipelined host path: enqueue one block (H2D copy, kernels, D2H copy all asynchronous, from
+ * / into caller-owned PINNED buffers) and wait for the oldest outstanding one.  Up to
+ * wr_bank_pipeline_depth() blocks may be in flight. */
+int wr_bank_submit(wr_bank *b, const float *iq_pinned, unsigned nframes,
+		float *audio_pinned, size_t audio_stride);
+int wr_bank_wait(wr_bank *b);
+int wr_bank_pipeline_depth(const wr_bank *b);
+
+/* Host-language loop helpers (what a C++ caller would write itself; they keep interpreter
+ * overhead out of bench.py's timed regions).  Step i uses iq[(first + i) % n_iq] and
+ * audio[(first + i) % n_audio].
+ *   wr_bank_run_device_steps: `steps` calls of wr_bank_process_device on the bank's stream;
+ *   wr_bank_run_host_steps  : `steps` blocks through wr_bank_submit / wr_bank_wait with the
+ *                             pipeline kept full (pipelined != 0) or strictly one at a time. */
+int wr_bank_run_device_steps(wr_bank *b, const float *const *iq_dev, unsigned n_iq, size_t stream_stride_frames,
+		unsigned nframes, float *const *audio_dev, unsigned n_audio, size_t audio_stride,
+		unsigned first, unsigned steps);
+int wr_bank_run_host_steps(wr_bank *b, const float *const *iq_pinned, unsigned n_iq, unsigned nframes,
+		float *const *audio_pinned, unsigned n_audio, size_t audio_stride,
+		unsigned first, unsigned steps, int pipelined);
+void *wr_bank_stream(wr_bank *b);   /* cudaStream_t of the bank */
+int wr_bank_sync(wr_bank *b);
+
+/* Keep (1) or drop (0, default) the intermediate channel-IQ stream of the fused kernel so
+ * that wr_bank_read_stage(WR_STAGE_CHANNEL) can return it; the demod stream is always kept. */
+int wr_bank_keep_channel(wr_bank *b, int keep);
+/* Copy an intermediate stream of the LAST block of receiver rx to the host.  Returns the
+ * number of floats written, or a negative error. */
+long wr_bank_read_stage(wr_bank *b, unsigned rx, int stage, float *out_host, size_t cap_floats);
+
+/* Selects the kernel family: 0 = auto (default), 1 = v1 generic kernels (NCO table read from
+ * L2), 2 = v2 kernels (NCO table resident in shared memory).  For tests and profiling. */
+int wr_bank_set_variant(wr_bank *b, int variant);
+/* Kernel launches issued by this bank since creation (for bench.py's gpu_launches). */
+unsigned long long wr_bank_launch_count(const wr_bank *b);
+/* Per-launch device timing with CUDA events on the launch stream.  While enabled every block
+ * records events around [0] the fused mix+FIR+demod kernel and [1] the audio FIR kernel;
+ * wr_bank_kernel_times returns the summed milliseconds and the number of blocks since timing
+ * was enabled.  This is what fills DspBlock's profile counters
+ * (reference src/dsp/dspblock.cxx:186-204) and bench.py's roofline. */
+int wr_bank_set_timing(wr_bank *b, int on);
+int wr_bank_kernel_times(wr_bank *b, double *ms2_total, unsigned long long *nblocks);
+
+/* --------------------------------------------- strict single-stage blocks ---- */
+/* One kernel per process() call on host buffers: what each reference block does on its own.
+ * Used by the DspBlock drop-ins when a chain cannot be fused, and by stage-by-stage parity. */
+typedef struct wr_stage wr_stage;
+
+wr_stage *wr_stage_create(int device);
+void wr_stage_destroy(wr_stage *s);
+/* DownConverter::process (reference downconverter.cxx:91-114). *phase is read and advanced. */
+int wr_stage_mix(wr_stage *s, const float *table_or_null, uint32_t *phase, int32_t step,
+		const float *iq_host, unsigned nframes, float *out_host);
+/* LowPass::process (reference lowpass.cxx:131-162): history lives in the stage handle. */
+int wr_stage_fir_config(wr_stage *s, unsigned channels, const float *coeff, unsigned ntaps);
+int wr_stage_fir(wr_stage *s, const float *in_host, unsigned nframes, unsigned decim, float *out_host);
+int wr_stage_fir_reset(wr_stage *s);
+/* Demodulator::process (reference demodulator.cxx:77-115). prev[2] read and updated. */
+int wr_stage_demod(wr_stage *s, int mode, float *prev, const float *iq_host, unsigned nframes,
+		float *out_host);
+
+/* ----------------------------------------------------------- spectrum ---- */
+/* SpectrumSink (reference src/io/spectrumsink.cxx:60-142): Hamming window, forward complex
+ * FFT, 10*log10(re^2+im^2) - 20*log10(N), fft-shifted.  n_streams independent streams are
+ * transformed in one launch; hop == fft_size is the reference behaviour, hop < fft_size is
+ * the overlapped waterfall of BASELINE config 4. */
+typedef struct wr_spectrum wr_spectrum;
+
+wr_spectrum *wr_spectrum_create(int device, unsigned fft_size, unsigned hop, unsigned n_streams,
+		unsigned max_frames);
+void wr_spectrum_destroy(wr_spectrum *s);
+/* SpectrumSink::process: feed nframes per stream ([n_streams][nframes][2] host floats).
+ * If rows_host is non-NULL every completed FFT frame's dB row is returned:
+ * stream t's rows start at rows_host + t*row_stride_floats, fft_size floats each.
+ * Returns the number of rows completed per stream by this call (>= 0) or a negative error. */
+long wr_spectrum_process(wr_spectrum *s, const float *iq_host, unsigned nframes,
+		float *rows_host, size_t row_stride_floats);
+/* Device-resident variant (asynchronous on cuda_stream). */
+long wr_spectrum_process_device(wr_spectrum *s, const float *iq_dev, size_t stream_stride_frames,
+		unsigned nframes, float *rows_dev, size_t row_stride_floats, void *cuda_stream);
+/* SpectrumSink::getSpectrum (reference spectrumsink.cxx:125-142): dB of the most recent
+ * transform of one stream; fft_size floats. */
+int wr_spectrum_get(wr_spectrum *s, unsigned stream, float *db_host);
+unsigned long long wr_spectrum_launch_count(const wr_spectrum *s);
+int wr_spectrum_sync(wr_spectrum *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WEBRADIO_B200_H */

@@ -1,0 +1,359 @@
+"""ctypes binding of libwebradio_b200.so (include/webradio_b200.h).
+
+This is plumbing for tests and bench.py: every call goes straight through the C ABI, which is
+the drop-in boundary.  There is no Python or CPU implementation behind it -- if the shared
+library is missing, importing fails loudly; if there is no CUDA device, the create calls fail.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libwebradio_b200.so")
+
+AM, FM, USB, LSB = 0, 1, 2, 3
+MODES = {"AM": AM, "FM": FM, "USB": USB, "LSB": LSB}
+RESET_PHASE, RESET_CHANNEL, RESET_DEMOD, RESET_AUDIO = 1, 2, 4, 8
+STAGE_CHANNEL, STAGE_DEMOD = 1, 2
+
+_fp = C.POINTER(C.c_float)
+
+# every symbol include/webradio_b200.h declares (tests/test_abi.py checks the export list)
+SYMBOLS = [
+    "wr_version", "wr_last_error", "wr_device_count", "wr_phase_step", "wr_build_sintable",
+    "wr_lowpass_design",
+    "wr_bank_create", "wr_bank_destroy", "wr_bank_set_sintable", "wr_rx_set_stream",
+    "wr_rx_set_phase_step", "wr_rx_set_taps", "wr_rx_set_mode", "wr_rx_reset", "wr_rx_get_phase",
+    "wr_bank_process", "wr_bank_process_device", "wr_bank_submit", "wr_bank_wait",
+    "wr_bank_pipeline_depth", "wr_bank_run_device_steps", "wr_bank_run_host_steps", "wr_bank_stream", "wr_bank_sync", "wr_bank_keep_channel",
+    "wr_bank_read_stage", "wr_bank_set_variant", "wr_bank_launch_count", "wr_bank_set_timing",
+    "wr_bank_kernel_times",
+    "wr_stage_create", "wr_stage_destroy", "wr_stage_mix", "wr_stage_fir_config", "wr_stage_fir",
+    "wr_stage_fir_reset", "wr_stage_demod",
+    "wr_spectrum_create", "wr_spectrum_destroy", "wr_spectrum_process", "wr_spectrum_process_device",
+    "wr_spectrum_get", "wr_spectrum_launch_count", "wr_spectrum_sync",
+]
+
+_lib = None
+
+
+class WrError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()); "
+                          "webradio_b200 has no fallback implementation")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, u, i, sz = C.c_void_p, C.c_uint, C.c_int, C.c_size_t
+    L.wr_version.restype = C.c_char_p
+    L.wr_last_error.restype = C.c_char_p
+    L.wr_phase_step.restype = C.c_int32
+    L.wr_phase_step.argtypes = [i, u]
+    L.wr_build_sintable.argtypes = [_fp]
+    L.wr_lowpass_design.argtypes = [u, u, u, _fp]
+    L.wr_bank_create.restype = vp
+    L.wr_bank_create.argtypes = [i, u, u, u, u, u, u, u]
+    L.wr_bank_destroy.argtypes = [vp]
+    L.wr_bank_set_sintable.argtypes = [vp, _fp]
+    L.wr_rx_set_stream.argtypes = [vp, u, u]
+    L.wr_rx_set_phase_step.argtypes = [vp, u, C.c_int32]
+    L.wr_rx_set_taps.argtypes = [vp, u, i, _fp, u]
+    L.wr_rx_set_mode.argtypes = [vp, u, i]
+    L.wr_rx_reset.argtypes = [vp, u, u]
+    L.wr_rx_get_phase.argtypes = [vp, u, C.POINTER(C.c_uint32)]
+    L.wr_bank_process.argtypes = [vp, vp, u, vp, sz]
+    L.wr_bank_process_device.argtypes = [vp, vp, sz, u, vp, sz, vp]
+    L.wr_bank_submit.argtypes = [vp, vp, u, vp, sz]
+    L.wr_bank_wait.argtypes = [vp]
+    L.wr_bank_pipeline_depth.argtypes = [vp]
+    pp = C.POINTER(C.c_void_p)
+    L.wr_bank_run_device_steps.argtypes = [vp, pp, u, sz, u, pp, u, sz, u, u]
+    L.wr_bank_run_host_steps.argtypes = [vp, pp, u, u, pp, u, sz, u, u, i]
+    L.wr_bank_stream.restype = vp
+    L.wr_bank_stream.argtypes = [vp]
+    L.wr_bank_sync.argtypes = [vp]
+    L.wr_bank_keep_channel.argtypes = [vp, i]
+    L.wr_bank_read_stage.restype = C.c_long
+    L.wr_bank_read_stage.argtypes = [vp, u, i, _fp, sz]
+    L.wr_bank_set_variant.argtypes = [vp, i]
+    L.wr_bank_launch_count.restype = C.c_ulonglong
+    L.wr_bank_launch_count.argtypes = [vp]
+    L.wr_bank_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]
+    L.wr_bank_set_timing.argtypes = [vp, i]
+    L.wr_stage_create.restype = vp
+    L.wr_stage_create.argtypes = [i]
+    L.wr_stage_destroy.argtypes = [vp]
+    L.wr_stage_mix.argtypes = [vp, _fp, C.POINTER(C.c_uint32), C.c_int32, _fp, u, _fp]
+    L.wr_stage_fir_config.argtypes = [vp, u, _fp, u]
+    L.wr_stage_fir.argtypes = [vp, _fp, u, u, _fp]
+    L.wr_stage_fir_reset.argtypes = [vp]
+    L.wr_stage_demod.argtypes = [vp, i, _fp, _fp, u, _fp]
+    L.wr_spectrum_create.restype = vp
+    L.wr_spectrum_create.argtypes = [i, u, u, u, u]
+    L.wr_spectrum_destroy.argtypes = [vp]
+    L.wr_spectrum_process.restype = C.c_long
+    L.wr_spectrum_process.argtypes = [vp, vp, u, vp, sz]
+    L.wr_spectrum_process_device.restype = C.c_long
+    L.wr_spectrum_process_device.argtypes = [vp, vp, sz, u, vp, sz, vp]
+    L.wr_spectrum_get.argtypes = [vp, u, _fp]
+    L.wr_spectrum_launch_count.restype = C.c_ulonglong
+    L.wr_spectrum_launch_count.argtypes = [vp]
+    L.wr_spectrum_sync.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def last_error():
+    return lib().wr_last_error().decode(errors="replace")
+
+
+def _check(rc, what):
+    if rc < 0:
+        raise WrError(f"{what} failed ({rc}): {last_error()}")
+    return rc
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(_fp)
+
+
+def phase_step(if_hz, fs):
+    return int(lib().wr_phase_step(int(if_hz), int(fs)))
+
+
+def build_sintable():
+    out = np.empty(65536, np.float32)
+    lib().wr_build_sintable(out.ctypes.data_as(_fp))
+    return out
+
+
+def lowpass_design(n, passband, fs):
+    out = np.empty(n, np.float32)
+    _check(lib().wr_lowpass_design(n, passband, fs, out.ctypes.data_as(_fp)), "wr_lowpass_design")
+    return out
+
+
+class Bank:
+    """n_receivers fused receiver chains fed by n_streams tuner streams on one GPU."""
+
+    def __init__(self, n_streams, n_receivers, max_frames, n1, d1, n2, d2, device=0):
+        self.L = lib()
+        self.T, self.R, self.max_frames = n_streams, n_receivers, max_frames
+        self.n1, self.d1, self.n2, self.d2 = n1, d1, n2, d2
+        self.h = self.L.wr_bank_create(device, n_streams, n_receivers, max_frames, n1, d1, n2, d2)
+        if not self.h:
+            raise WrError("wr_bank_create failed: " + last_error())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.wr_bank_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_sintable(self, table):
+        t, p = _f32(table)
+        _check(self.L.wr_bank_set_sintable(self.h, p), "wr_bank_set_sintable")
+
+    def set_stream(self, rx, stream):
+        _check(self.L.wr_rx_set_stream(self.h, rx, stream), "wr_rx_set_stream")
+
+    def set_phase_step(self, rx, step):
+        _check(self.L.wr_rx_set_phase_step(self.h, rx, step), "wr_rx_set_phase_step")
+
+    def set_if(self, rx, if_hz, fs):
+        self.set_phase_step(rx, phase_step(if_hz, fs))
+
+    def set_taps(self, rx, stage, coeff):
+        c, p = _f32(coeff)
+        _check(self.L.wr_rx_set_taps(self.h, rx, stage, p, c.size), "wr_rx_set_taps")
+
+    def set_mode(self, rx, mode):
+        _check(self.L.wr_rx_set_mode(self.h, rx, MODES.get(mode, mode)), "wr_rx_set_mode")
+
+    def reset(self, rx, flags):
+        _check(self.L.wr_rx_reset(self.h, rx, flags), "wr_rx_reset")
+
+    def get_phase(self, rx):
+        v = C.c_uint32(0)
+        _check(self.L.wr_rx_get_phase(self.h, rx, C.byref(v)), "wr_rx_get_phase")
+        return v.value
+
+    def out_frames(self, nframes):
+        return nframes // self.d1 // self.d2
+
+    def process(self, iq, nframes=None):
+        """iq: float32 [n_streams, nframes, 2] (or flat).  Returns audio [n_receivers, M2]."""
+        a, _ = _f32(iq)
+        if nframes is None:
+            nframes = a.size // (2 * self.T)
+        assert a.size == 2 * self.T * nframes
+        m2 = self.out_frames(nframes)
+        out = np.zeros((self.R, max(m2, 1)), np.float32)
+        _check(self.L.wr_bank_process(self.h, a.ctypes.data, nframes, out.ctypes.data, out.shape[1]),
+               "wr_bank_process")
+        return out[:, :m2]
+
+    def process_device(self, iq_ptr, stream_stride, nframes, audio_ptr, audio_stride, cuda_stream=None):
+        _check(self.L.wr_bank_process_device(self.h, iq_ptr, stream_stride, nframes, audio_ptr,
+                                             audio_stride, cuda_stream), "wr_bank_process_device")
+
+    def submit(self, iq_ptr, nframes, audio_ptr, audio_stride):
+        _check(self.L.wr_bank_submit(self.h, iq_ptr, nframes, audio_ptr, audio_stride), "wr_bank_submit")
+
+    def wait(self):
+        _check(self.L.wr_bank_wait(self.h), "wr_bank_wait")
+
+    def run_device_steps(self, iq_ptrs, stride, nframes, audio_ptrs, audio_stride, first, steps):
+        a = (C.c_void_p * len(iq_ptrs))(*iq_ptrs)
+        o = (C.c_void_p * len(audio_ptrs))(*audio_ptrs)
+        _check(self.L.wr_bank_run_device_steps(self.h, a, len(iq_ptrs), stride, nframes, o, len(audio_ptrs),
+                                               audio_stride, first, steps), "wr_bank_run_device_steps")
+
+    def run_host_steps(self, iq_ptrs, nframes, audio_ptrs, audio_stride, first, steps, pipelined=True):
+        a = (C.c_void_p * len(iq_ptrs))(*iq_ptrs)
+        o = (C.c_void_p * len(audio_ptrs))(*audio_ptrs)
+        _check(self.L.wr_bank_run_host_steps(self.h, a, len(iq_ptrs), nframes, o, len(audio_ptrs), audio_stride,
+                                             first, steps, int(pipelined)), "wr_bank_run_host_steps")
+
+    def pipeline_depth(self):
+        return self.L.wr_bank_pipeline_depth(self.h)
+
+    def stream(self):
+        return self.L.wr_bank_stream(self.h)
+
+    def sync(self):
+        _check(self.L.wr_bank_sync(self.h), "wr_bank_sync")
+
+    def keep_channel(self, keep=True):
+        _check(self.L.wr_bank_keep_channel(self.h, int(keep)), "wr_bank_keep_channel")
+
+    def read_stage(self, rx, stage, nframes):
+        m1 = nframes // self.d1
+        n = 2 * m1 if stage == STAGE_CHANNEL else m1
+        out = np.empty(max(n, 1), np.float32)
+        got = _check(self.L.wr_bank_read_stage(self.h, rx, stage, out.ctypes.data_as(_fp), n), "wr_bank_read_stage")
+        return out[:got]
+
+    def set_variant(self, v):
+        _check(self.L.wr_bank_set_variant(self.h, v), "wr_bank_set_variant")
+
+    def launch_count(self):
+        return int(self.L.wr_bank_launch_count(self.h))
+
+    def set_timing(self, on=True):
+        _check(self.L.wr_bank_set_timing(self.h, int(on)), "wr_bank_set_timing")
+
+    def kernel_times(self):
+        """(total ms in the fused channel kernel, total ms in the audio kernel, blocks timed)."""
+        ms = (C.c_double * 2)()
+        n = C.c_ulonglong(0)
+        _check(self.L.wr_bank_kernel_times(self.h, ms, C.byref(n)), "wr_bank_kernel_times")
+        return float(ms[0]), float(ms[1]), int(n.value)
+
+
+class Stage:
+    """Strict single-stage blocks (one kernel per call, host buffers)."""
+
+    def __init__(self, device=0):
+        self.L = lib()
+        self.h = self.L.wr_stage_create(device)
+        if not self.h:
+            raise WrError("wr_stage_create failed: " + last_error())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.wr_stage_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def mix(self, phase, step, iq, table=None):
+        a, ap = _f32(iq)
+        out = np.empty_like(a)
+        ph = C.c_uint32(phase)
+        tp = None
+        if table is not None:
+            t, tp = _f32(table)
+        _check(self.L.wr_stage_mix(self.h, tp, C.byref(ph), step, ap, a.size // 2, out.ctypes.data_as(_fp)),
+               "wr_stage_mix")
+        return out, ph.value
+
+    def fir_config(self, channels, coeff):
+        c, p = _f32(coeff)
+        self.ch = channels
+        _check(self.L.wr_stage_fir_config(self.h, channels, p, c.size), "wr_stage_fir_config")
+
+    def fir(self, x, decim):
+        a, ap = _f32(x)
+        nframes = a.size // self.ch
+        out = np.empty(max(1, (nframes // decim) * self.ch), np.float32)
+        _check(self.L.wr_stage_fir(self.h, ap, nframes, decim, out.ctypes.data_as(_fp)), "wr_stage_fir")
+        return out[:(nframes // decim) * self.ch]
+
+    def fir_reset(self):
+        _check(self.L.wr_stage_fir_reset(self.h), "wr_stage_fir_reset")
+
+    def demod(self, mode, prev, iq):
+        a, ap = _f32(iq)
+        out = np.empty(max(1, a.size // 2), np.float32)
+        assert prev.dtype == np.float32 and prev.size == 2
+        _check(self.L.wr_stage_demod(self.h, MODES.get(mode, mode), prev.ctypes.data_as(_fp), ap, a.size // 2,
+                                     out.ctypes.data_as(_fp)), "wr_stage_demod")
+        return out[:a.size // 2]
+
+
+class Spectrum:
+    def __init__(self, fft_size, hop=None, n_streams=1, max_frames=None, device=0):
+        self.L = lib()
+        self.N, self.hop, self.T = fft_size, hop or fft_size, n_streams
+        self.max_frames = max_frames or 64 * fft_size
+        self.h = self.L.wr_spectrum_create(device, fft_size, self.hop, n_streams, self.max_frames)
+        if not self.h:
+            raise WrError("wr_spectrum_create failed: " + last_error())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.wr_spectrum_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def process(self, iq, rows=True):
+        """iq: [n_streams, nframes, 2].  Returns rows [n_streams, nrows, N] (or nrows if rows=False)."""
+        a, _ = _f32(iq)
+        nframes = a.size // (2 * self.T)
+        max_rows = (nframes + self.N) // self.hop + 1
+        out = np.empty((self.T, max_rows, self.N), np.float32) if rows else None
+        n = _check(self.L.wr_spectrum_process(self.h, a.ctypes.data, nframes,
+                                              out.ctypes.data if rows else None, max_rows * self.N),
+                   "wr_spectrum_process")
+        return out[:, :n, :] if rows else n
+
+    def process_device(self, iq_ptr, stride, nframes, rows_ptr, row_stride, cuda_stream=None):
+        return _check(self.L.wr_spectrum_process_device(self.h, iq_ptr, stride, nframes, rows_ptr, row_stride,
+                                                        cuda_stream), "wr_spectrum_process_device")
+
+    def get(self, stream=0):
+        out = np.empty(self.N, np.float32)
+        _check(self.L.wr_spectrum_get(self.h, stream, out.ctypes.data_as(_fp)), "wr_spectrum_get")
+        return out
+
+    def launch_count(self):
+        return int(self.L.wr_spectrum_launch_count(self.h))
+
+    def sync(self):
+        _check(self.L.wr_spectrum_sync(self.h), "wr_spectrum_sync")

@@ -1,0 +1,670 @@
+// wr_bank.cu -- the receiver bank: host-side state machine + kernel launches behind the
+// wr_bank_* / wr_rx_* entry points of include/webradio_b200.h.
+#include "wr_common.h"
+#include "wr_bank.cuh"
+#include "wr_kernels_v1.cuh"
+#include "wr_kernels_v2.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+using wrd::RxConf;
+using wrd::RxState;
+
+namespace {
+
+constexpr int kSlots = 3;        // pipeline depth of the submit/wait path
+constexpr int kThreadsV1 = 128;
+
+__global__ void reset_kernel(RxState *st, float2 *hist1, float *demod_hist, unsigned rx,
+		unsigned n1m1, unsigned n2m1, size_t dstride, unsigned flags)
+{
+	const unsigned tid = threadIdx.x;
+	if (tid == 0) {
+		if (flags & WR_RESET_PHASE)
+			st[rx].phase = 0;
+		if (flags & WR_RESET_DEMOD) {
+			st[rx].prev_i = 0.0f;
+			st[rx].prev_q = 0.0f;
+		}
+	}
+	if (flags & WR_RESET_CHANNEL)
+		for (unsigned i = tid; i < n1m1; i += blockDim.x)
+			hist1[(size_t)rx * n1m1 + i] = make_float2(0.0f, 0.0f);
+	if (flags & WR_RESET_AUDIO)
+		for (unsigned i = tid; i < n2m1; i += blockDim.x)
+			demod_hist[(size_t)rx * dstride + i] = 0.0f;
+}
+
+struct Slot {
+	float *d_iq = nullptr;      // [T][maxF][2]
+	float *d_audio = nullptr;   // [R][maxM2]
+	cudaEvent_t in_ready = nullptr, done = nullptr, out_ready = nullptr;
+	bool busy = false;
+	bool used = false;
+};
+
+} // namespace
+
+struct wr_bank {
+	int device = 0;
+	unsigned T = 0, R = 0, maxF = 0, n1 = 0, d1 = 0, n2 = 0, d2 = 0;
+	unsigned maxM1 = 0, maxM2 = 0;
+	size_t dstride = 0;
+	cudaStream_t compute = nullptr, h2d = nullptr, d2h = nullptr;
+
+	float *d_table = nullptr;
+	float *d_taps1 = nullptr, *d_taps2 = nullptr;
+	RxConf *d_conf = nullptr;
+	RxState *d_state[2] = { nullptr, nullptr };
+	float2 *d_hist1[2] = { nullptr, nullptr };
+	float *d_demod[2] = { nullptr, nullptr };
+	float2 *d_chan = nullptr;
+	int cur = 0;
+	unsigned lastM1 = 0, lastM2 = 0;
+	bool keepChan = false;
+
+	// host shadows of the per-receiver configuration; setters touch only these (any thread)
+	std::mutex mu;
+	std::vector<RxConf> h_conf;
+	std::vector<float> h_taps1, h_taps2;   // reversed, as the kernels read them
+	std::vector<unsigned> h_reset;         // pending WR_RESET_* per receiver
+	bool confDirty = true, taps1Dirty = true, taps2Dirty = true, resetDirty = false;
+	bool tableDirty = false;
+	std::vector<float> h_table;
+	// pinned staging for the uploads
+	RxConf *p_conf = nullptr;
+	float *p_taps1 = nullptr, *p_taps2 = nullptr, *p_table = nullptr;
+	cudaEvent_t stagingFree = nullptr;
+
+	Slot slot[kSlots];
+	int head = 0, tail = 0, inflight = 0;
+
+	int variant = 0;
+	wrd::V2Plan v2;
+	unsigned long long launches = 0;
+	// optional per-launch device timing: a ring of event triples drained into accumulators
+	bool timing = false;
+	static constexpr int kTimeRing = 128;
+	cudaEvent_t tev[kTimeRing][3] = {};
+	int tHead = 0, tCount = 0;
+	double accMs[2] = { 0.0, 0.0 };
+	unsigned long long accBlocks = 0;
+};
+
+namespace {
+
+// fold the oldest timed block into the accumulators (blocks until its events completed)
+int drain_one(wr_bank *b)
+{
+	const int idx = (b->tHead - b->tCount + wr_bank::kTimeRing) % wr_bank::kTimeRing;
+	float a = 0.0f, c = 0.0f;
+	WR_CUDA(cudaEventSynchronize(b->tev[idx][2]));
+	WR_CUDA(cudaEventElapsedTime(&a, b->tev[idx][0], b->tev[idx][1]));
+	WR_CUDA(cudaEventElapsedTime(&c, b->tev[idx][1], b->tev[idx][2]));
+	b->accMs[0] += a;
+	b->accMs[1] += c;
+	b->accBlocks++;
+	b->tCount--;
+	return WR_OK;
+}
+
+int apply_pending(wr_bank *b, cudaStream_t st)
+{
+	std::lock_guard<std::mutex> lk(b->mu);
+	if (!(b->confDirty || b->taps1Dirty || b->taps2Dirty || b->resetDirty || b->tableDirty))
+		return WR_OK;
+	// the pinned staging buffers may still be the source of an earlier async upload
+	WR_CUDA(cudaEventSynchronize(b->stagingFree));
+	if (b->tableDirty) {
+		memcpy(b->p_table, b->h_table.data(), sizeof(float) * WR_SINTABLE_SIZE);
+		WR_CUDA(cudaMemcpyAsync(b->d_table, b->p_table, sizeof(float) * WR_SINTABLE_SIZE,
+				cudaMemcpyHostToDevice, st));
+		b->tableDirty = false;
+		b->v2.tableStale = true;
+	}
+	if (b->confDirty) {
+		memcpy(b->p_conf, b->h_conf.data(), sizeof(RxConf) * b->R);
+		WR_CUDA(cudaMemcpyAsync(b->d_conf, b->p_conf, sizeof(RxConf) * b->R, cudaMemcpyHostToDevice, st));
+		b->confDirty = false;
+	}
+	if (b->taps1Dirty) {
+		memcpy(b->p_taps1, b->h_taps1.data(), sizeof(float) * b->h_taps1.size());
+		WR_CUDA(cudaMemcpyAsync(b->d_taps1, b->p_taps1, sizeof(float) * b->h_taps1.size(),
+				cudaMemcpyHostToDevice, st));
+		b->taps1Dirty = false;
+	}
+	if (b->taps2Dirty) {
+		memcpy(b->p_taps2, b->h_taps2.data(), sizeof(float) * b->h_taps2.size());
+		WR_CUDA(cudaMemcpyAsync(b->d_taps2, b->p_taps2, sizeof(float) * b->h_taps2.size(),
+				cudaMemcpyHostToDevice, st));
+		b->taps2Dirty = false;
+	}
+	WR_CUDA(cudaEventRecord(b->stagingFree, st));
+	if (b->resetDirty) {
+		for (unsigned r = 0; r < b->R; r++) {
+			if (!b->h_reset[r])
+				continue;
+			reset_kernel<<<1, 128, 0, st>>>(b->d_state[b->cur], b->d_hist1[b->cur], b->d_demod[b->cur],
+					r, b->n1 - 1, b->n2 - 1, b->dstride, b->h_reset[r]);
+			b->launches++;
+			b->h_reset[r] = 0;
+		}
+		WR_CUDA(cudaGetLastError());
+		b->resetDirty = false;
+	}
+	return WR_OK;
+}
+
+// Tile sizes of the v1 kernels: as many outputs per CTA as keep the mixed tile under ~40 KiB.
+unsigned pick_tk_v1(unsigned n1, unsigned d1)
+{
+	const unsigned budgetFrames = 40 * 1024 / 8;
+	unsigned tk = 128;
+	while (tk > 8 && (size_t)tk * d1 + n1 > budgetFrames)
+		tk /= 2;
+	return tk;
+}
+
+int launch_block(wr_bank *b, const float *iq_dev, size_t stream_stride, unsigned F,
+		float *audio_dev, size_t audio_stride, cudaStream_t st)
+{
+	int rc = apply_pending(b, st);
+	if (rc != WR_OK)
+		return rc;
+	const unsigned M1 = F / b->d1;
+	const unsigned M2 = M1 / b->d2;
+	const int cur = b->cur, nxt = cur ^ 1;
+
+	cudaEvent_t *tev = nullptr;
+	if (b->timing) {
+		if (b->tCount == wr_bank::kTimeRing && (rc = drain_one(b)) != WR_OK)
+			return rc;
+		tev = b->tev[b->tHead];
+		WR_CUDA(cudaEventRecord(tev[0], st));
+	}
+
+	bool useV2 = (b->variant == 2) || (b->variant == 0 && wrd::v2_supported(b->v2));
+	if (b->variant == 2 && !wrd::v2_supported(b->v2)) {
+		wr::set_error("v2 kernels do not support this geometry (n1=%u d1=%u)", b->n1, b->d1);
+		return WR_EINVAL;
+	}
+
+	wrd::ChanArgs ca;
+	ca.iq = reinterpret_cast<const float2*>(iq_dev);
+	ca.stream_stride = stream_stride;
+	ca.table = b->d_table;
+	ca.taps1 = b->d_taps1;
+	ca.conf = b->d_conf;
+	ca.st_in = b->d_state[cur];
+	ca.st_out = b->d_state[nxt];
+	ca.hist_in = b->d_hist1[cur];
+	ca.hist_out = b->d_hist1[nxt];
+	ca.demod = b->d_demod[cur];
+	ca.dstride = b->dstride;
+	ca.demod_off = b->n2 - 1;
+	ca.chan = b->keepChan ? b->d_chan : nullptr;
+	ca.chan_stride = b->maxM1;
+	ca.F = F;
+	ca.M1 = M1;
+	ca.n1 = b->n1;
+	ca.d1 = b->d1;
+
+	if (useV2) {
+		rc = wrd::v2_launch_chan(b->v2, ca, b->R, st, &b->launches);
+		if (rc != WR_OK)
+			return rc;
+	} else {
+		ca.TK = pick_tk_v1(b->n1, b->d1);
+		ca.ntiles = (M1 + ca.TK - 1) / ca.TK;
+		size_t smem = sizeof(float2) * ((size_t)ca.TK * b->d1 + b->n1)
+				+ sizeof(float) * ((b->n1 + 3) & ~3u) + sizeof(float2) * (ca.TK + 1);
+		dim3 grid(ca.ntiles + 1, b->R);
+		wrd::chan_kernel_v1<kThreadsV1><<<grid, kThreadsV1, smem, st>>>(ca);
+		b->launches++;
+	}
+	WR_CUDA(cudaGetLastError());
+	if (tev)
+		WR_CUDA(cudaEventRecord(tev[1], st));
+
+	wrd::AudioArgs aa;
+	aa.x = b->d_demod[cur];
+	aa.x_next = b->d_demod[nxt];
+	aa.dstride = b->dstride;
+	aa.taps2 = b->d_taps2;
+	aa.audio = audio_dev;
+	aa.audio_stride = audio_stride;
+	aa.M1 = M1;
+	aa.M2 = M2;
+	aa.n2 = b->n2;
+	aa.d2 = b->d2;
+	aa.TK = 128;
+	aa.ntiles = (M2 + aa.TK - 1) / aa.TK;
+	{
+		size_t lmax = (size_t)(aa.TK - 1) * b->d2 + b->n2;
+		size_t smem = sizeof(float) * (((lmax + 3) & ~(size_t)3) + b->n2);
+		dim3 grid(aa.ntiles + 1, b->R);
+		wrd::audio_kernel_v1<kThreadsV1><<<grid, kThreadsV1, smem, st>>>(aa);
+		b->launches++;
+	}
+	WR_CUDA(cudaGetLastError());
+	if (tev) {
+		WR_CUDA(cudaEventRecord(tev[2], st));
+		b->tHead = (b->tHead + 1) % wr_bank::kTimeRing;
+		b->tCount++;
+	}
+
+	b->cur = nxt;
+	b->lastM1 = M1;
+	b->lastM2 = M2;
+	return WR_OK;
+}
+
+void free_bank(wr_bank *b)
+{
+	if (!b)
+		return;
+	cudaSetDevice(b->device);
+	if (b->compute)
+		cudaStreamSynchronize(b->compute);
+	if (b->h2d)
+		cudaStreamSynchronize(b->h2d);
+	if (b->d2h)
+		cudaStreamSynchronize(b->d2h);
+	wrd::v2_destroy(b->v2);
+	cudaFree(b->d_table);
+	cudaFree(b->d_taps1);
+	cudaFree(b->d_taps2);
+	cudaFree(b->d_conf);
+	for (int i = 0; i < 2; i++) {
+		cudaFree(b->d_state[i]);
+		cudaFree(b->d_hist1[i]);
+		cudaFree(b->d_demod[i]);
+	}
+	cudaFree(b->d_chan);
+	cudaFreeHost(b->p_conf);
+	cudaFreeHost(b->p_taps1);
+	cudaFreeHost(b->p_taps2);
+	cudaFreeHost(b->p_table);
+	for (int i = 0; i < kSlots; i++) {
+		cudaFree(b->slot[i].d_iq);
+		cudaFree(b->slot[i].d_audio);
+		if (b->slot[i].in_ready) cudaEventDestroy(b->slot[i].in_ready);
+		if (b->slot[i].done) cudaEventDestroy(b->slot[i].done);
+		if (b->slot[i].out_ready) cudaEventDestroy(b->slot[i].out_ready);
+	}
+	if (b->stagingFree) cudaEventDestroy(b->stagingFree);
+	for (int i = 0; i < wr_bank::kTimeRing; i++)
+		for (int j = 0; j < 3; j++)
+			if (b->tev[i][j]) cudaEventDestroy(b->tev[i][j]);
+	if (b->compute) cudaStreamDestroy(b->compute);
+	if (b->h2d) cudaStreamDestroy(b->h2d);
+	if (b->d2h) cudaStreamDestroy(b->d2h);
+	cudaGetLastError();
+	delete b;
+}
+
+#define WR_BANK_ALLOC(expr)                                                             \
+	do {                                                                                \
+		cudaError_t e_ = (expr);                                                        \
+		if (e_ != cudaSuccess) {                                                        \
+			wr::set_error("%s: %s", #expr, cudaGetErrorString(e_));                     \
+			free_bank(b);                                                               \
+			return nullptr;                                                             \
+		}                                                                               \
+	} while (0)
+
+} // namespace
+
+extern "C" {
+
+wr_bank *wr_bank_create(int device, unsigned n_streams, unsigned n_receivers, unsigned max_frames,
+		unsigned n1, unsigned d1, unsigned n2, unsigned d2)
+{
+	if (n_streams == 0 || n_receivers == 0 || max_frames == 0 || n1 == 0 || n2 == 0 || d1 == 0 || d2 == 0
+			|| n_receivers > 65535 || n1 > 4096 || n2 > 4096) {
+		wr::set_error("wr_bank_create: bad geometry (streams=%u receivers=%u frames=%u n1=%u d1=%u n2=%u d2=%u)",
+				n_streams, n_receivers, max_frames, n1, d1, n2, d2);
+		return nullptr;
+	}
+	if (!wr::check_device(device))
+		return nullptr;
+	wr_bank *b = new wr_bank();
+	b->device = device;
+	b->T = n_streams; b->R = n_receivers; b->maxF = max_frames;
+	b->n1 = n1; b->d1 = d1; b->n2 = n2; b->d2 = d2;
+	b->maxM1 = max_frames / d1;
+	b->maxM2 = b->maxM1 / d2;
+	b->dstride = ((size_t)(n2 - 1) + b->maxM1 + 3) & ~(size_t)3;
+	const unsigned R = n_receivers;
+
+	WR_BANK_ALLOC(cudaStreamCreateWithFlags(&b->compute, cudaStreamNonBlocking));
+	WR_BANK_ALLOC(cudaStreamCreateWithFlags(&b->h2d, cudaStreamNonBlocking));
+	WR_BANK_ALLOC(cudaStreamCreateWithFlags(&b->d2h, cudaStreamNonBlocking));
+	WR_BANK_ALLOC(cudaEventCreateWithFlags(&b->stagingFree, cudaEventDisableTiming));
+
+	WR_BANK_ALLOC(cudaMalloc(&b->d_table, sizeof(float) * WR_SINTABLE_SIZE));
+	WR_BANK_ALLOC(cudaMalloc(&b->d_taps1, sizeof(float) * (size_t)R * n1));
+	WR_BANK_ALLOC(cudaMalloc(&b->d_taps2, sizeof(float) * (size_t)R * n2));
+	WR_BANK_ALLOC(cudaMalloc(&b->d_conf, sizeof(RxConf) * R));
+	const size_t h1 = std::max<size_t>(1, (size_t)R * (n1 - 1));
+	for (int i = 0; i < 2; i++) {
+		WR_BANK_ALLOC(cudaMalloc(&b->d_state[i], sizeof(RxState) * R));
+		WR_BANK_ALLOC(cudaMemset(b->d_state[i], 0, sizeof(RxState) * R));
+		WR_BANK_ALLOC(cudaMalloc(&b->d_hist1[i], sizeof(float2) * h1));
+		WR_BANK_ALLOC(cudaMemset(b->d_hist1[i], 0, sizeof(float2) * h1));
+		WR_BANK_ALLOC(cudaMalloc(&b->d_demod[i], sizeof(float) * (size_t)R * b->dstride));
+		WR_BANK_ALLOC(cudaMemset(b->d_demod[i], 0, sizeof(float) * (size_t)R * b->dstride));
+	}
+	WR_BANK_ALLOC(cudaMallocHost(&b->p_conf, sizeof(RxConf) * R));
+	WR_BANK_ALLOC(cudaMallocHost(&b->p_taps1, sizeof(float) * (size_t)R * n1));
+	WR_BANK_ALLOC(cudaMallocHost(&b->p_taps2, sizeof(float) * (size_t)R * n2));
+	WR_BANK_ALLOC(cudaMallocHost(&b->p_table, sizeof(float) * WR_SINTABLE_SIZE));
+	for (int i = 0; i < kSlots; i++) {
+		WR_BANK_ALLOC(cudaEventCreateWithFlags(&b->slot[i].in_ready, cudaEventDisableTiming));
+		WR_BANK_ALLOC(cudaEventCreateWithFlags(&b->slot[i].done, cudaEventDisableTiming));
+		WR_BANK_ALLOC(cudaEventCreateWithFlags(&b->slot[i].out_ready, cudaEventDisableTiming));
+	}
+
+	b->h_conf.resize(R);
+	for (unsigned r = 0; r < R; r++) {
+		b->h_conf[r].step = 0;
+		b->h_conf[r].mode = WR_MODE_AM;  // Demodulator's constructor default (demodulator.cxx:33)
+		b->h_conf[r].stream = r % n_streams;
+		b->h_conf[r].pad = 0;
+	}
+	b->h_taps1.assign((size_t)R * n1, 0.0f);
+	b->h_taps2.assign((size_t)R * n2, 0.0f);
+	b->h_reset.assign(R, 0);
+	b->h_table.resize(WR_SINTABLE_SIZE);
+	wr_build_sintable(b->h_table.data());
+	b->tableDirty = true;
+
+	if (wrd::v2_init(b->v2, device, n1, d1) != WR_OK) {
+		free_bank(b);
+		return nullptr;
+	}
+	return b;
+}
+
+void wr_bank_destroy(wr_bank *b) { free_bank(b); }
+
+int wr_bank_set_sintable(wr_bank *b, const float *table)
+{
+	WR_REQUIRE(b && table, WR_EINVAL, "wr_bank_set_sintable: null argument");
+	std::lock_guard<std::mutex> lk(b->mu);
+	memcpy(b->h_table.data(), table, sizeof(float) * WR_SINTABLE_SIZE);
+	b->tableDirty = true;
+	return WR_OK;
+}
+
+int wr_rx_set_stream(wr_bank *b, unsigned rx, unsigned stream)
+{
+	WR_REQUIRE(b && rx < b->R && stream < b->T, WR_EINVAL, "wr_rx_set_stream: rx %u / stream %u out of range", rx, stream);
+	std::lock_guard<std::mutex> lk(b->mu);
+	b->h_conf[rx].stream = stream;
+	b->confDirty = true;
+	return WR_OK;
+}
+
+int wr_rx_set_phase_step(wr_bank *b, unsigned rx, int32_t step)
+{
+	WR_REQUIRE(b && rx < b->R, WR_EINVAL, "wr_rx_set_phase_step: rx %u out of range", rx);
+	std::lock_guard<std::mutex> lk(b->mu);
+	b->h_conf[rx].step = step;
+	b->confDirty = true;
+	return WR_OK;
+}
+
+int wr_rx_set_taps(wr_bank *b, unsigned rx, int stage, const float *coeff, unsigned ntaps)
+{
+	WR_REQUIRE(b && coeff && rx < b->R && (stage == 0 || stage == 1), WR_EINVAL, "wr_rx_set_taps: bad argument");
+	const unsigned n = stage ? b->n2 : b->n1;
+	WR_REQUIRE(ntaps == n, WR_EINVAL, "wr_rx_set_taps: %u taps given, bank geometry has %u", ntaps, n);
+	std::lock_guard<std::mutex> lk(b->mu);
+	float *dst = (stage ? b->h_taps2.data() : b->h_taps1.data()) + (size_t)rx * n;
+	for (unsigned j = 0; j < n; j++)
+		dst[j] = coeff[n - 1 - j]; // the kernels walk taps in sample order (lowpass.cxx:152-156)
+	(stage ? b->taps2Dirty : b->taps1Dirty) = true;
+	return WR_OK;
+}
+
+int wr_rx_set_mode(wr_bank *b, unsigned rx, int mode)
+{
+	WR_REQUIRE(b && rx < b->R, WR_EINVAL, "wr_rx_set_mode: rx %u out of range", rx);
+	WR_REQUIRE(mode >= WR_MODE_AM && mode <= WR_MODE_LSB, WR_EINVAL, "wr_rx_set_mode: bad mode %d", mode);
+	std::lock_guard<std::mutex> lk(b->mu);
+	b->h_conf[rx].mode = mode;
+	b->confDirty = true;
+	return WR_OK;
+}
+
+int wr_rx_reset(wr_bank *b, unsigned rx, unsigned flags)
+{
+	WR_REQUIRE(b && rx < b->R, WR_EINVAL, "wr_rx_reset: rx %u out of range", rx);
+	std::lock_guard<std::mutex> lk(b->mu);
+	b->h_reset[rx] |= flags;
+	b->resetDirty = true;
+	return WR_OK;
+}
+
+int wr_rx_get_phase(wr_bank *b, unsigned rx, uint32_t *phase)
+{
+	WR_REQUIRE(b && phase && rx < b->R, WR_EINVAL, "wr_rx_get_phase: bad argument");
+	if (!wr::use_device(b->device))
+		return WR_ENODEV;
+	WR_CUDA(cudaStreamSynchronize(b->compute));
+	RxState st;
+	WR_CUDA(cudaMemcpy(&st, b->d_state[b->cur] + rx, sizeof(st), cudaMemcpyDeviceToHost));
+	*phase = st.phase;
+	return WR_OK;
+}
+
+int wr_bank_process_device(wr_bank *b, const float *iq_dev, size_t stream_stride_frames,
+		unsigned nframes, float *audio_dev, size_t audio_stride, void *cuda_stream)
+{
+	WR_REQUIRE(b && iq_dev && audio_dev, WR_EINVAL, "wr_bank_process_device: null argument");
+	WR_REQUIRE(nframes <= b->maxF, WR_EINVAL, "wr_bank_process_device: %u frames > max_frames %u", nframes, b->maxF);
+	if (!wr::use_device(b->device))
+		return WR_ENODEV;
+	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->compute;
+	return launch_block(b, iq_dev, stream_stride_frames, nframes, audio_dev, audio_stride, st);
+}
+
+int wr_bank_submit(wr_bank *b, const float *iq_host, unsigned nframes, float *audio_host, size_t audio_stride)
+{
+	WR_REQUIRE(b && iq_host && audio_host, WR_EINVAL, "wr_bank_submit: null argument");
+	WR_REQUIRE(nframes <= b->maxF, WR_EINVAL, "wr_bank_submit: %u frames > max_frames %u", nframes, b->maxF);
+	WR_REQUIRE(b->inflight < kSlots, WR_ESTATE, "wr_bank_submit: %d blocks already in flight", b->inflight);
+	if (!wr::use_device(b->device))
+		return WR_ENODEV;
+	Slot &s = b->slot[b->head];
+	if (!s.d_iq) {
+		WR_CUDA(cudaMalloc(&s.d_iq, sizeof(float) * 2 * (size_t)b->T * b->maxF));
+		WR_CUDA(cudaMalloc(&s.d_audio, sizeof(float) * (size_t)b->R * std::max(1u, b->maxM2)));
+	}
+	const unsigned M2 = nframes / b->d1 / b->d2;
+	// H2D: must not overwrite the slot's tuner block before the kernels of its previous use ran
+	if (s.used)
+		WR_CUDA(cudaStreamWaitEvent(b->h2d, s.done, 0));
+	WR_CUDA(cudaMemcpy2DAsync(s.d_iq, sizeof(float) * 2 * (size_t)b->maxF,
+			iq_host, sizeof(float) * 2 * (size_t)nframes,
+			sizeof(float) * 2 * (size_t)nframes, b->T, cudaMemcpyHostToDevice, b->h2d));
+	WR_CUDA(cudaEventRecord(s.in_ready, b->h2d));
+	// compute: after the copy in, and after the previous read-out of this slot's audio buffer
+	WR_CUDA(cudaStreamWaitEvent(b->compute, s.in_ready, 0));
+	if (s.used)
+		WR_CUDA(cudaStreamWaitEvent(b->compute, s.out_ready, 0));
+	int rc = launch_block(b, s.d_iq, b->maxF, nframes, s.d_audio, std::max(1u, b->maxM2), b->compute);
+	if (rc != WR_OK)
+		return rc;
+	WR_CUDA(cudaEventRecord(s.done, b->compute));
+	// D2H
+	WR_CUDA(cudaStreamWaitEvent(b->d2h, s.done, 0));
+	if (M2 > 0)
+		WR_CUDA(cudaMemcpy2DAsync(audio_host, sizeof(float) * audio_stride,
+				s.d_audio, sizeof(float) * std::max(1u, b->maxM2),
+				sizeof(float) * M2, b->R, cudaMemcpyDeviceToHost, b->d2h));
+	WR_CUDA(cudaEventRecord(s.out_ready, b->d2h));
+	s.busy = true;
+	s.used = true;
+	b->head = (b->head + 1) % kSlots;
+	b->inflight++;
+	return WR_OK;
+}
+
+int wr_bank_wait(wr_bank *b)
+{
+	WR_REQUIRE(b, WR_EINVAL, "wr_bank_wait: null bank");
+	WR_REQUIRE(b->inflight > 0, WR_ESTATE, "wr_bank_wait: nothing in flight");
+	if (!wr::use_device(b->device))
+		return WR_ENODEV;
+	Slot &s = b->slot[b->tail];
+	WR_CUDA(cudaEventSynchronize(s.out_ready));
+	s.busy = false;
+	b->tail = (b->tail + 1) % kSlots;
+	b->inflight--;
+	return WR_OK;
+}
+
+int wr_bank_pipeline_depth(const wr_bank *) { return kSlots; }
+
+int wr_bank_process(wr_bank *b, const float *iq_host, unsigned nframes, float *audio_host, size_t audio_stride)
+{
+	WR_REQUIRE(b, WR_EINVAL, "wr_bank_process: null bank");
+	WR_REQUIRE(b->inflight == 0, WR_ESTATE, "wr_bank_process: pipelined blocks still in flight");
+	int rc = wr_bank_submit(b, iq_host, nframes, audio_host, audio_stride);
+	if (rc != WR_OK)
+		return rc;
+	return wr_bank_wait(b);
+}
+
+int wr_bank_run_device_steps(wr_bank *b, const float *const *iq_dev, unsigned n_iq, size_t stream_stride_frames,
+		unsigned nframes, float *const *audio_dev, unsigned n_audio, size_t audio_stride,
+		unsigned first, unsigned steps)
+{
+	WR_REQUIRE(b && iq_dev && audio_dev && n_iq && n_audio, WR_EINVAL, "wr_bank_run_device_steps: bad argument");
+	for (unsigned i = 0; i < steps; i++) {
+		int rc = wr_bank_process_device(b, iq_dev[(first + i) % n_iq], stream_stride_frames, nframes,
+				audio_dev[(first + i) % n_audio], audio_stride, nullptr);
+		if (rc != WR_OK)
+			return rc;
+	}
+	return WR_OK;
+}
+
+int wr_bank_run_host_steps(wr_bank *b, const float *const *iq_pinned, unsigned n_iq, unsigned nframes,
+		float *const *audio_pinned, unsigned n_audio, size_t audio_stride,
+		unsigned first, unsigned steps, int pipelined)
+{
+	WR_REQUIRE(b && iq_pinned && audio_pinned && n_iq && n_audio, WR_EINVAL, "wr_bank_run_host_steps: bad argument");
+	WR_REQUIRE(b->inflight == 0, WR_ESTATE, "wr_bank_run_host_steps: blocks already in flight");
+	const int depth = pipelined ? std::min<int>(kSlots, (int)n_audio) : 1;
+	int rc;
+	for (unsigned i = 0; i < steps; i++) {
+		if (b->inflight == depth && (rc = wr_bank_wait(b)) != WR_OK)
+			return rc;
+		rc = wr_bank_submit(b, iq_pinned[(first + i) % n_iq], nframes, audio_pinned[(first + i) % n_audio], audio_stride);
+		if (rc != WR_OK)
+			return rc;
+	}
+	while (b->inflight > 0)
+		if ((rc = wr_bank_wait(b)) != WR_OK)
+			return rc;
+	return WR_OK;
+}
+
+void *wr_bank_stream(wr_bank *b) { return b ? (void*)b->compute : nullptr; }
+
+int wr_bank_sync(wr_bank *b)
+{
+	WR_REQUIRE(b, WR_EINVAL, "wr_bank_sync: null bank");
+	if (!wr::use_device(b->device))
+		return WR_ENODEV;
+	WR_CUDA(cudaStreamSynchronize(b->h2d));
+	WR_CUDA(cudaStreamSynchronize(b->compute));
+	WR_CUDA(cudaStreamSynchronize(b->d2h));
+	return WR_OK;
+}
+
+int wr_bank_keep_channel(wr_bank *b, int keep)
+{
+	WR_REQUIRE(b, WR_EINVAL, "wr_bank_keep_channel: null bank");
+	if (!wr::use_device(b->device))
+		return WR_ENODEV;
+	if (keep && !b->d_chan)
+		WR_CUDA(cudaMalloc(&b->d_chan, sizeof(float2) * (size_t)b->R * std::max(1u, b->maxM1)));
+	b->keepChan = keep != 0;
+	return WR_OK;
+}
+
+long wr_bank_read_stage(wr_bank *b, unsigned rx, int stage, float *out, size_t cap)
+{
+	WR_REQUIRE(b && out && rx < b->R, WR_EINVAL, "wr_bank_read_stage: bad argument");
+	if (!wr::use_device(b->device))
+		return WR_ENODEV;
+	WR_CUDA(cudaStreamSynchronize(b->compute));
+	if (stage == WR_STAGE_DEMOD) {
+		size_t n = std::min<size_t>(b->lastM1, cap);
+		const float *src = b->d_demod[b->cur ^ 1] + (size_t)rx * b->dstride + (b->n2 - 1);
+		WR_CUDA(cudaMemcpy(out, src, sizeof(float) * n, cudaMemcpyDeviceToHost));
+		return (long)n;
+	}
+	if (stage == WR_STAGE_CHANNEL) {
+		WR_REQUIRE(b->keepChan && b->d_chan, WR_ESTATE, "wr_bank_read_stage: channel stream not kept (wr_bank_keep_channel)");
+		size_t n = std::min<size_t>((size_t)b->lastM1 * 2, cap);
+		WR_CUDA(cudaMemcpy(out, b->d_chan + (size_t)rx * b->maxM1, sizeof(float) * n, cudaMemcpyDeviceToHost));
+		return (long)n;
+	}
+	wr::set_error("wr_bank_read_stage: unknown stage %d", stage);
+	return WR_EINVAL;
+}
+
+int wr_bank_set_variant(wr_bank *b, int variant)
+{
+	WR_REQUIRE(b && variant >= 0 && variant <= 2, WR_EINVAL, "wr_bank_set_variant: bad variant %d", variant);
+	b->variant = variant;
+	return WR_OK;
+}
+
+unsigned long long wr_bank_launch_count(const wr_bank *b) { return b ? b->launches : 0; }
+
+int wr_bank_set_timing(wr_bank *b, int on)
+{
+	WR_REQUIRE(b, WR_EINVAL, "wr_bank_set_timing: null bank");
+	if (!wr::use_device(b->device))
+		return WR_ENODEV;
+	if (on && !b->tev[0][0])
+		for (int i = 0; i < wr_bank::kTimeRing; i++)
+			for (int j = 0; j < 3; j++)
+				WR_CUDA(cudaEventCreate(&b->tev[i][j]));
+	while (b->tCount > 0) {
+		int rc = drain_one(b);
+		if (rc != WR_OK)
+			return rc;
+	}
+	b->timing = on != 0;
+	b->accMs[0] = b->accMs[1] = 0.0;
+	b->accBlocks = 0;
+	return WR_OK;
+}
+
+int wr_bank_kernel_times(wr_bank *b, double *ms2_total, unsigned long long *nblocks)
+{
+	WR_REQUIRE(b && ms2_total && nblocks, WR_EINVAL, "wr_bank_kernel_times: null argument");
+	if (!wr::use_device(b->device))
+		return WR_ENODEV;
+	while (b->tCount > 0) {
+		int rc = drain_one(b);
+		if (rc != WR_OK)
+			return rc;
+	}
+	ms2_total[0] = b->accMs[0];
+	ms2_total[1] = b->accMs[1];
+	*nblocks = b->accBlocks;
+	return WR_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,135 @@
+// wr_host.cpp -- cold-path host code of libwebradio_b200.so: error plumbing, the NCO table,
+// the phase step and the filter design (K0 in SURVEY.md 2a stays on the host, as in the
+// reference).  None of this runs per sample.
+#include "wr_common.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace wr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+const char *get_error() { return g_err; }
+
+bool check_device(int device)
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0) {
+		set_error("no CUDA device available (%s); libwebradio_b200 has no CPU fallback",
+				e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+		cudaGetLastError();
+		return false;
+	}
+	if (device < 0 || device >= n) {
+		set_error("device %d out of range (have %d)", device, n);
+		return false;
+	}
+	return use_device(device);
+}
+
+bool use_device(int device)
+{
+	int cur = -1;
+	if (cudaGetDevice(&cur) == cudaSuccess && cur == device)
+		return true;
+	cudaError_t e = cudaSetDevice(device);
+	if (e != cudaSuccess) {
+		set_error("cudaSetDevice(%d): %s; libwebradio_b200 has no CPU fallback", device, cudaGetErrorString(e));
+		cudaGetLastError();
+		return false;
+	}
+	return true;
+}
+
+} // namespace wr
+
+extern "C" {
+
+const char *wr_version(void) { return "webradio_b200 0.1 (sm_100a)"; }
+
+const char *wr_last_error(void) { return wr::get_error(); }
+
+int wr_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+// Replaces the expression at reference downconverter.cxx:65 and :80: a 64-bit product of the
+// IF and 2^31 divided (truncating toward zero) by the input sample rate.
+int32_t wr_phase_step(int if_hz, unsigned sample_rate)
+{
+	if (sample_rate == 0)
+		return 0;
+	const int64_t full_turn = (int64_t)1 << 31;
+	return (int32_t)((int64_t)if_hz * full_turn / (int64_t)sample_rate);
+}
+
+// Replaces the loop at reference downconverter.cxx:49-51.  The angle is formed in double
+// ((float)n*2 is a float, the product with pi promotes) and narrowed to float by sinf; the
+// table must come from the host libm so that it is bit-identical to the reference's on the
+// same machine -- the GPU only ever gathers from it.
+void wr_build_sintable(float *out)
+{
+	const float scale = (float)WR_SINTABLE_SIZE;
+	for (unsigned n = 0; n < WR_SINTABLE_SIZE; n++) {
+		double angle = (double)((float)n * 2) * M_PI / (double)scale;
+		out[n] = sinf((float)angle);
+	}
+}
+
+// Replaces LowPass::init's window (reference lowpass.cxx:102-110) and LowPass::recalculate
+// (lowpass.cxx:164-189).  The reference runs an n-point inverse FFTW transform of a real,
+// symmetric 0/1 mask; that transform is evaluated here directly in float64 (the mask is real
+// and even, so only the cosine terms survive) and rounded once, which is the correctly
+// rounded version of what the reference's float FFT approximates.
+int wr_lowpass_design(unsigned n, unsigned passband_hz, unsigned sample_rate, float *coeff)
+{
+	WR_REQUIRE(n >= 2 && coeff && sample_rate > 0, WR_EINVAL, "wr_lowpass_design: bad arguments");
+	std::vector<double> mask(n, 0.0);
+	// same unsigned arithmetic as lowpass.cxx:167
+	unsigned maxbin = n * passband_hz / sample_rate / 2;
+	for (unsigned k = 0; k < n / 2 + 1; k++) {
+		double v = (k < maxbin) ? 1.0 : 0.0;
+		mask[k] = v;
+		mask[(n - k) % n] = v;
+	}
+	const double two_pi = 6.283185307179586476925286766559;
+	for (unsigned k = 0; k < n; k++) {
+		unsigned bin = (k + n / 2) % n; // lowpass.cxx:184 re-ordering
+		double re = 0.0;
+		for (unsigned m = 0; m < n; m++) {
+			unsigned long long idx = ((unsigned long long)bin * m) % n;
+			double a = two_pi * (double)idx / (double)n;
+			re += mask[m] * cos(a);
+		}
+		float impulse = (float)re;
+		// lowpass.cxx:108-109: Hamming window, then the 1/N of the unnormalised transform
+		float w = (float)(0.54 - 0.46 * cosf((float)(2 * M_PI * (float)k / (float)(n - 1))));
+		w /= (float)n;
+		coeff[k] = impulse * w;
+	}
+	return WR_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,343 @@
+// wr_spectrum.cu -- SpectrumSink on the GPU (K5 + K6 of SURVEY.md 2a): Hamming window fused
+// into the load, Stockham autosort FFT held entirely in shared memory, and the
+// 10*log10(|X|^2) - 20*log10(N) conversion with the fft-shift fused into the store
+// (reference src/io/spectrumsink.cxx:88-142).
+//
+// One CTA transforms one FFT frame of one stream.  A frame may straddle the carry buffer
+// (frames left over from the previous call) and the new block, so the kernel reads through a
+// two-segment view instead of first concatenating them in HBM.
+#include "wr_common.h"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace {
+
+struct SpecArgs {
+	const float2 *carry;     // [T][carry_stride] frames left from earlier calls
+	size_t carry_stride;
+	unsigned ncarry;         // valid frames in carry (same for every stream)
+	const float2 *in;        // [T][in_stride] this call's frames
+	size_t in_stride;
+	const float *window;     // [N]
+	const float2 *twiddle;   // [N] exp(-2*pi*i*k/N)
+	float *rows;             // may be null
+	size_t row_stride;       // floats between streams
+	float *last;             // [T][N] most recent row per stream
+	unsigned N, logN, hop;
+	unsigned first_row;      // blockIdx.x + first_row = frame index within this call
+	unsigned nrows;          // rows completed by this call
+	float scaledb;
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+	return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+__device__ __forceinline__ float2 view(const SpecArgs &a, unsigned t, size_t pos)
+{
+	if (pos < a.ncarry)
+		return a.carry[(size_t)t * a.carry_stride + pos];
+	return __ldg(a.in + (size_t)t * a.in_stride + (pos - a.ncarry));
+}
+
+// Stockham autosort passes (natural order in, natural order out).  sa/sb ping-pong.
+__global__ void __launch_bounds__(1024) spectrum_kernel_v1(const SpecArgs a)
+{
+	extern __shared__ float2 wr_fft_smem[];
+	const unsigned N = a.N;
+	float2 *sa = wr_fft_smem;
+	float2 *sb = wr_fft_smem + N;
+	const unsigned t = blockIdx.y;
+	const unsigned m = blockIdx.x + a.first_row;
+	const size_t start = (size_t)m * a.hop;
+	const unsigned tid = threadIdx.x, nt = blockDim.x;
+
+	// window fused into the load: inbuf[n] *= window[n] (spectrumsink.cxx:110-113)
+	for (unsigned i = tid; i < N; i += nt) {
+		float2 x = view(a, t, start + i);
+		float w = a.window[i];
+		sa[i] = make_float2(__fmul_rn(x.x, w), __fmul_rn(x.y, w));
+	}
+	__syncthreads();
+
+	unsigned Ns = 1;
+	if (a.logN & 1) { // one radix-2 pass first (Ns = 1: no twiddles)
+		for (unsigned j = tid; j < N / 2; j += nt) {
+			float2 u = sa[j], v = sa[j + N / 2];
+			sb[2 * j] = make_float2(u.x + v.x, u.y + v.y);
+			sb[2 * j + 1] = make_float2(u.x - v.x, u.y - v.y);
+		}
+		__syncthreads();
+		float2 *tmp = sa; sa = sb; sb = tmp;
+		Ns = 2;
+	}
+	const unsigned Q = N / 4;
+	for (; Ns < N; Ns *= 4) {
+		const unsigned tw_stride = N / (Ns * 4);
+		for (unsigned j = tid; j < Q; j += nt) {
+			const unsigned k = j & (Ns - 1);
+			float2 v0 = sa[j], v1 = sa[j + Q], v2 = sa[j + 2 * Q], v3 = sa[j + 3 * Q];
+			if (Ns > 1) {
+				const unsigned q = k * tw_stride;
+				v1 = cmul(v1, __ldg(a.twiddle + q));
+				v2 = cmul(v2, __ldg(a.twiddle + 2 * q));
+				v3 = cmul(v3, __ldg(a.twiddle + 3 * q));
+			}
+			float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y);
+			float2 d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
+			float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y);
+			float2 d13 = make_float2(v1.y - v3.y, v3.x - v1.x); // (v1 - v3) * (-i)
+			const unsigned base = (j - k) * 4 + k;
+			sb[base] = make_float2(s02.x + s13.x, s02.y + s13.y);
+			sb[base + Ns] = make_float2(d02.x + d13.x, d02.y + d13.y);
+			sb[base + 2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
+			sb[base + 3 * Ns] = make_float2(d02.x - d13.x, d02.y - d13.y);
+		}
+		__syncthreads();
+		float2 *tmp = sa; sa = sb; sb = tmp;
+	}
+
+	// dB + fft-shift fused into the store (spectrumsink.cxx:127-140)
+	float *row = a.rows ? a.rows + (size_t)t * a.row_stride + (size_t)m * N : nullptr;
+	float *last = (m == a.nrows - 1) ? a.last + (size_t)t * N : nullptr;
+	const unsigned half = N / 2;
+	for (unsigned o = tid; o < N; o += nt) {
+		const unsigned n = (o + half) & (N - 1); // output slot o holds bin n
+		float2 X = sa[n];
+		float p = __fadd_rn(__fmul_rn(X.x, X.x), __fmul_rn(X.y, X.y));
+		float db = __fsub_rn(__fmul_rn(10.0f, log10f(p)), a.scaledb);
+		if (row) row[o] = db;
+		if (last) last[o] = db;
+	}
+}
+
+// leftover frames of [carry | in] starting at `from` become the next call's carry
+__global__ void spectrum_carry_kernel(const SpecArgs a, float2 *next, size_t from, unsigned count)
+{
+	const unsigned t = blockIdx.y;
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+		next[(size_t)t * a.carry_stride + i] = view(a, t, from + i);
+}
+
+} // namespace
+
+struct wr_spectrum {
+	int device = 0;
+	unsigned N = 0, logN = 0, hop = 0, T = 0, maxF = 0;
+	cudaStream_t st = nullptr;
+	float *d_window = nullptr;
+	float2 *d_twiddle = nullptr;
+	float2 *d_carry[2] = { nullptr, nullptr };
+	int cur = 0;
+	unsigned ncarry = 0;
+	float *d_in = nullptr;     // host-path staging [T][maxF][2]
+	float *d_rows = nullptr;   // host-path staging [T][maxRows][N]
+	unsigned maxRows = 0;
+	float *d_last = nullptr;   // [T][N]
+	bool haveLast = false;
+	cudaStream_t lastStream = nullptr; // stream of the most recent launch
+	unsigned long long launches = 0;
+};
+
+namespace {
+
+void free_spectrum(wr_spectrum *s)
+{
+	if (!s)
+		return;
+	cudaSetDevice(s->device);
+	if (s->st)
+		cudaStreamSynchronize(s->st);
+	cudaFree(s->d_window);
+	cudaFree(s->d_twiddle);
+	cudaFree(s->d_carry[0]);
+	cudaFree(s->d_carry[1]);
+	cudaFree(s->d_in);
+	cudaFree(s->d_rows);
+	cudaFree(s->d_last);
+	if (s->st)
+		cudaStreamDestroy(s->st);
+	cudaGetLastError();
+	delete s;
+}
+
+long run(wr_spectrum *s, const float *iq_dev, size_t in_stride, unsigned nframes,
+		float *rows_dev, size_t row_stride, cudaStream_t st)
+{
+	const size_t avail = (size_t)s->ncarry + nframes;
+	const unsigned nrows = avail >= s->N ? (unsigned)((avail - s->N) / s->hop + 1) : 0;
+	SpecArgs a;
+	a.carry = s->d_carry[s->cur];
+	a.carry_stride = s->N;
+	a.ncarry = s->ncarry;
+	a.in = reinterpret_cast<const float2*>(iq_dev);
+	a.in_stride = in_stride;
+	a.window = s->d_window;
+	a.twiddle = s->d_twiddle;
+	a.rows = rows_dev;
+	a.row_stride = row_stride;
+	a.last = s->d_last;
+	a.N = s->N;
+	a.logN = s->logN;
+	a.hop = s->hop;
+	a.nrows = nrows;
+	// scaledb = 20 * log10f((float)N) with the host libm, as the reference computes it
+	a.scaledb = 20 * log10f((float)s->N);
+	if (nrows) {
+		// without a row buffer only the newest transform is observable (getSpectrum), so only
+		// that one is computed; the reference transforms every frame and discards all but the last
+		a.first_row = rows_dev ? 0 : nrows - 1;
+		dim3 grid(nrows - a.first_row, s->T);
+		unsigned threads = std::min(1024u, std::max(32u, s->N / 4));
+		size_t smem = sizeof(float2) * 2 * (size_t)s->N;
+		spectrum_kernel_v1<<<grid, threads, smem, st>>>(a);
+		s->launches++;
+		WR_CUDA(cudaGetLastError());
+		s->haveLast = true;
+		s->lastStream = st;
+	}
+	const size_t consumed = (size_t)nrows * s->hop;
+	const unsigned left = (unsigned)(avail - consumed);
+	if (left) {
+		dim3 grid(std::max(1u, std::min(8u, (left + 255) / 256)), s->T);
+		spectrum_carry_kernel<<<grid, 256, 0, st>>>(a, s->d_carry[s->cur ^ 1], consumed, left);
+		s->launches++;
+		WR_CUDA(cudaGetLastError());
+	}
+	s->cur ^= 1;
+	s->ncarry = left;
+	return (long)nrows;
+}
+
+} // namespace
+
+extern "C" {
+
+wr_spectrum *wr_spectrum_create(int device, unsigned fft_size, unsigned hop, unsigned n_streams, unsigned max_frames)
+{
+	// power of two only, as SpectrumSink::setFftSize enforces (spectrumsink.cxx:53-56)
+	if (fft_size < 8 || (fft_size & (fft_size - 1)) || fft_size > 8192 || hop == 0 || hop > fft_size
+			|| n_streams == 0 || n_streams > 65535 || max_frames == 0) {
+		wr::set_error("wr_spectrum_create: fft_size must be a power of two in [8, 8192], 0 < hop <= fft_size "
+				"(got N=%u hop=%u streams=%u)", fft_size, hop, n_streams);
+		return nullptr;
+	}
+	if (!wr::check_device(device))
+		return nullptr;
+	wr_spectrum *s = new wr_spectrum();
+	s->device = device;
+	s->N = fft_size;
+	s->hop = hop;
+	s->T = n_streams;
+	s->maxF = max_frames;
+	while ((1u << s->logN) < fft_size)
+		s->logN++;
+	s->maxRows = (unsigned)(((size_t)fft_size - 1 + max_frames - fft_size) / hop + 1);
+
+	std::vector<float> win(fft_size);
+	for (unsigned n = 0; n < fft_size; n++) // spectrumsink.cxx:71-74
+		win[n] = (float)(0.54 - 0.46 * cosf((float)(2 * M_PI * (float)n / (float)(fft_size - 1))));
+	std::vector<float2> tw(fft_size);
+	for (unsigned k = 0; k < fft_size; k++) {
+		double ang = -2.0 * M_PI * (double)k / (double)fft_size;
+		tw[k] = make_float2((float)cos(ang), (float)sin(ang));
+	}
+#define WR_SPEC_ALLOC(expr)                                               \
+	do {                                                                  \
+		cudaError_t e_ = (expr);                                          \
+		if (e_ != cudaSuccess) {                                          \
+			wr::set_error("%s: %s", #expr, cudaGetErrorString(e_));       \
+			free_spectrum(s);                                             \
+			return nullptr;                                               \
+		}                                                                 \
+	} while (0)
+	WR_SPEC_ALLOC(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+	WR_SPEC_ALLOC(cudaMalloc(&s->d_window, sizeof(float) * fft_size));
+	WR_SPEC_ALLOC(cudaMemcpy(s->d_window, win.data(), sizeof(float) * fft_size, cudaMemcpyHostToDevice));
+	WR_SPEC_ALLOC(cudaMalloc(&s->d_twiddle, sizeof(float2) * fft_size));
+	WR_SPEC_ALLOC(cudaMemcpy(s->d_twiddle, tw.data(), sizeof(float2) * fft_size, cudaMemcpyHostToDevice));
+	for (int i = 0; i < 2; i++) {
+		WR_SPEC_ALLOC(cudaMalloc(&s->d_carry[i], sizeof(float2) * (size_t)n_streams * fft_size));
+		WR_SPEC_ALLOC(cudaMemset(s->d_carry[i], 0, sizeof(float2) * (size_t)n_streams * fft_size));
+	}
+	WR_SPEC_ALLOC(cudaMalloc(&s->d_last, sizeof(float) * (size_t)n_streams * fft_size));
+	WR_SPEC_ALLOC(cudaMemset(s->d_last, 0, sizeof(float) * (size_t)n_streams * fft_size));
+	WR_SPEC_ALLOC(cudaFuncSetAttribute(spectrum_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			(int)(sizeof(float2) * 2 * 8192)));
+#undef WR_SPEC_ALLOC
+	return s;
+}
+
+void wr_spectrum_destroy(wr_spectrum *s) { free_spectrum(s); }
+
+long wr_spectrum_process_device(wr_spectrum *s, const float *iq_dev, size_t stride_frames, unsigned nframes,
+		float *rows_dev, size_t row_stride, void *cuda_stream)
+{
+	WR_REQUIRE(s && (iq_dev || nframes == 0), WR_EINVAL, "wr_spectrum_process_device: null argument");
+	WR_REQUIRE(nframes <= s->maxF, WR_EINVAL, "wr_spectrum_process_device: %u frames > max_frames %u", nframes, s->maxF);
+	if (!wr::use_device(s->device))
+		return WR_ENODEV;
+	return run(s, iq_dev, stride_frames, nframes, rows_dev, row_stride, cuda_stream ? (cudaStream_t)cuda_stream : s->st);
+}
+
+long wr_spectrum_process(wr_spectrum *s, const float *iq_host, unsigned nframes, float *rows_host, size_t row_stride)
+{
+	WR_REQUIRE(s && (iq_host || nframes == 0), WR_EINVAL, "wr_spectrum_process: null argument");
+	WR_REQUIRE(nframes <= s->maxF, WR_EINVAL, "wr_spectrum_process: %u frames > max_frames %u", nframes, s->maxF);
+	if (!wr::use_device(s->device))
+		return WR_ENODEV;
+	if (!s->d_in)
+		WR_CUDA(cudaMalloc(&s->d_in, sizeof(float) * 2 * (size_t)s->T * s->maxF));
+	if (rows_host && !s->d_rows)
+		WR_CUDA(cudaMalloc(&s->d_rows, sizeof(float) * (size_t)s->T * s->maxRows * s->N));
+	if (nframes)
+		WR_CUDA(cudaMemcpy2DAsync(s->d_in, sizeof(float) * 2 * (size_t)s->maxF, iq_host, sizeof(float) * 2 * (size_t)nframes,
+				sizeof(float) * 2 * (size_t)nframes, s->T, cudaMemcpyHostToDevice, s->st));
+	long nrows = run(s, s->d_in, s->maxF, nframes, rows_host ? s->d_rows : nullptr, (size_t)s->maxRows * s->N, s->st);
+	if (nrows < 0)
+		return nrows;
+	if (rows_host && nrows > 0)
+		WR_CUDA(cudaMemcpy2DAsync(rows_host, sizeof(float) * row_stride, s->d_rows, sizeof(float) * (size_t)s->maxRows * s->N,
+				sizeof(float) * (size_t)nrows * s->N, s->T, cudaMemcpyDeviceToHost, s->st));
+	WR_CUDA(cudaStreamSynchronize(s->st));
+	return nrows;
+}
+
+int wr_spectrum_get(wr_spectrum *s, unsigned stream, float *db_host)
+{
+	WR_REQUIRE(s && db_host && stream < s->T, WR_EINVAL, "wr_spectrum_get: bad argument");
+	if (!wr::use_device(s->device))
+		return WR_ENODEV;
+	WR_CUDA(cudaStreamSynchronize(s->st));
+	if (s->lastStream && s->lastStream != s->st)
+		WR_CUDA(cudaStreamSynchronize(s->lastStream));
+	if (!s->haveLast) {
+		// no transform yet: the reference's outbuf is still zero -> 10*log10f(0) - scaledb = -inf
+		float scaledb = 20 * log10f((float)s->N);
+		for (unsigned n = 0; n < s->N; n++)
+			db_host[n] = 10 * log10f(0.0f) - scaledb;
+		return WR_OK;
+	}
+	WR_CUDA(cudaMemcpy(db_host, s->d_last + (size_t)stream * s->N, sizeof(float) * s->N, cudaMemcpyDeviceToHost));
+	return WR_OK;
+}
+
+unsigned long long wr_spectrum_launch_count(const wr_spectrum *s) { return s ? s->launches : 0; }
+
+int wr_spectrum_sync(wr_spectrum *s)
+{
+	WR_REQUIRE(s, WR_EINVAL, "wr_spectrum_sync: null handle");
+	if (!wr::use_device(s->device))
+		return WR_ENODEV;
+	WR_CUDA(cudaStreamSynchronize(s->st));
+	return WR_OK;
+}
+
+} // extern "C"

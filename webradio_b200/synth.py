@@ -66,6 +66,15 @@ def structured(nframes, fs, ifs, modes, start=0, amp=0.5, noise_db=-30.0, seed=0
     return out
 
 
+def windowed_sinc(n, cutoff):
+    """Hamming windowed-sinc low-pass, n taps, cutoff as a fraction of the sample rate.  Tap VALUES
+    are an input of the FIR; the reference cannot design non-power-of-two lengths itself
+    (FIR_LENGTH is a compile-time 64, reference src/dsp/lowpass.cxx:39)."""
+    k = np.arange(n) - (n - 1) / 2.0
+    h = 2 * cutoff * np.sinc(2 * cutoff * k) * (0.54 - 0.46 * np.cos(2 * np.pi * np.arange(n) / max(n - 1, 1)))
+    return h.astype(np.float32)
+
+
 # Integer-legal variants of BASELINE.json configs (SURVEY.md 8d; the reference rejects
 # non-integer rate ratios, reference src/dsp/dspblock.cxx:119-130).
 WORKLOADS = {
