@@ -17,7 +17,7 @@ HARNESS  := tests/harness/libwr_blocks_harness.so
 BLOCKSRC := webradio_b200/dsp/dspblock.cxx webradio_b200/dsp/downconverter.cxx webradio_b200/dsp/lowpass.cxx \
             webradio_b200/dsp/demodulator.cxx webradio_b200/io/spectrumsink.cxx webradio_b200/dsp/gpubank.cxx
 
-.PHONY: all lib harness oracle clean
+.PHONY: all lib harness dropin oracle clean
 all: lib
 lib: $(LIB)
 
@@ -40,7 +40,19 @@ $(LIB): $(OBJ)
 harness: $(HARNESS)
 $(HARNESS): tests/harness/graph_harness.cxx $(BLOCKSRC) $(wildcard webradio_b200/dsp/*.h webradio_b200/io/*.h) $(LIB)
 	$(CXX) -std=c++11 -O2 -fPIC -Wall -shared -Iinclude -Iwebradio_b200 -Iwebradio_b200/dsp -Iwebradio_b200/io \
-	  -o $@ tests/harness/graph_harness.cxx $(BLOCKSRC) -Lwebradio_b200 -lwebradio_b200 -Wl,-rpath,'$$ORIGIN/../../webradio_b200' -lpthread
+	  -o $@ tests/harness/graph_harness.cxx $(BLOCKSRC) -Lwebradio_b200 -lwebradio_b200 -Wl,-Bsymbolic -Wl,-rpath,'$$ORIGIN/../../webradio_b200' -lpthread
+
+# The reference's own graph glue (src/radio.cxx, UNMODIFIED, compiled where it lies) linked against
+# the drop-in blocks.  Only buildable where the reference tree is mounted; the .so travels.
+REF ?= /root/reference
+DROPIN := tests/harness/libwr_radio_dropin.so
+dropin: $(LIB)
+	@if [ -f "$(REF)/src/radio.cxx" ]; then \
+	  $(CXX) -std=c++11 -O2 -fPIC -Wall -shared -DWR_QUIET_DEBUG -Iinclude -Itests/harness/stubs -Iwebradio_b200 \
+	    -Iwebradio_b200/dsp -Iwebradio_b200/io -I$(REF)/src \
+	    -o $(DROPIN) $(REF)/src/radio.cxx tests/harness/radio_dropin.cxx $(BLOCKSRC) \
+	    -Lwebradio_b200 -lwebradio_b200 -Wl,-Bsymbolic -Wl,-rpath,'$$ORIGIN/../../webradio_b200' -lpthread && echo "built $(DROPIN)"; \
+	else echo "reference tree not mounted: keeping prebuilt $(DROPIN) (if any)"; fi
 
 oracle:
 	$(MAKE) -C oracle port ref

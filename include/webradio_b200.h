@@ -103,6 +103,9 @@ int wr_rx_set_taps(wr_bank *b, unsigned rx, int stage, const float *coeff, unsig
 int wr_rx_set_mode(wr_bank *b, unsigned rx, int mode);
 /* Clear carried state (OR of WR_RESET_*); mirrors what ctor/deinit do in the reference. */
 int wr_rx_reset(wr_bank *b, unsigned rx, unsigned flags);
+/* Overwrite the NCO phase accumulator (31 bits), e.g. to carry a receiver over from another
+ * bank; takes effect at the next block boundary. */
+int wr_rx_set_phase(wr_bank *b, unsigned rx, uint32_t phase);
 /* Read back NCO phase (reference downconverter.h:58) as of the last completed block. */
 int wr_rx_get_phase(wr_bank *b, unsigned rx, uint32_t *phase);
 

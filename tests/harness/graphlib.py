@@ -22,7 +22,8 @@ _fp = C.POINTER(C.c_float)
 
 
 def _bind(path):
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL if "blocks" in path else C.RTLD_LOCAL)
+    # RTLD_LOCAL: both builds define the same C++ class names (DspBlock, LowPass, ...)
+    lib = C.CDLL(path, mode=C.RTLD_LOCAL)
     lib.wrh_graph_create.restype = C.c_void_p
     lib.wrh_graph_create.argtypes = [C.c_uint, C.c_uint]
     lib.wrh_graph_add_receiver.restype = C.c_int

@@ -1,0 +1,150 @@
+/*
+ * tests/harness/radio_dropin.cxx -- TEST DRIVER for the drop-in claim.
+ *
+ * Links the reference's UNMODIFIED graph glue (/root/reference/src/radio.cxx, compiled in place)
+ * against webradio_b200's DspBlock drop-in classes and drives it exactly as the reference's
+ * main() does (src/main.cxx:71-115): FrontEnd(factory) -> Receivers -> tuner()->start() ->
+ * Radio::run().  Only AudioStreamManager is a stub (tests/harness/stubs/audiostream.h).
+ * Built into tests/harness/libwr_radio_dropin.so where the reference tree is mounted; the
+ * prebuilt library travels to the GPU box.
+ */
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include <unistd.h>
+#include <fcntl.h>
+
+#include "radio.h"
+
+namespace {
+
+class ReplayTuner : public Tuner {
+public:
+	ReplayTuner(const string &name) : Tuner(name, "ReplayTuner"), cur(NULL), len(0) {}
+	void feed(const float *p, size_t n) { cur = p; len = n; }
+private:
+	bool init() { _outputSampleRate = inputSampleRate(); _outputChannels = inputChannels(); return true; }
+	void deinit() {}
+	bool process(const vector<sample_t> &in, vector<sample_t> &out)
+	{
+		(void)in;
+		if (!cur || len != out.size())
+			return false;
+		memcpy(out.data(), cur, len * sizeof(float));
+		return true;
+	}
+	const float *cur;
+	size_t len;
+};
+
+ReplayTuner *g_lastTuner = NULL;
+Tuner *replayFactory(const string &name) { return g_lastTuner = new ReplayTuner(name); }
+
+struct Rig {
+	FrontEnd *fe;
+	ReplayTuner *tuner;
+	std::vector<Receiver*> rx;
+	unsigned frames;
+};
+
+struct Quiet {
+	int saved;
+	Quiet() { fflush(stderr); saved = dup(2); int n = open("/dev/null", O_WRONLY); if (n >= 0) { dup2(n, 2); close(n); } }
+	~Quiet() { fflush(stderr); dup2(saved, 2); close(saved); }
+};
+
+} // namespace
+
+extern "C" {
+
+void *wrr_create(unsigned fs, unsigned block_frames, unsigned fft_size)
+{
+	Quiet q;
+	Rig *r = new Rig();
+	r->fe = new FrontEnd(replayFactory);
+	r->tuner = g_lastTuner;
+	r->frames = block_frames;
+	r->fe->tuner()->setSampleRate(fs);
+	r->fe->tuner()->setBlockSize(block_frames * 2);
+	r->fe->spectrum()->setFftSize(fft_size);
+	return r;
+}
+
+/* new Receiver() with the reference's defaults (80 kHz -> 240 k, 8 kHz -> 48 k, radio.cxx:78-82) */
+int wrr_add_receiver(void *h, int if_hz, const char *mode)
+{
+	Quiet q;
+	Rig *r = (Rig*)h;
+	Receiver *rx = new Receiver();
+	rx->setFrontEnd(r->fe);
+	rx->downconverter()->setIF(if_hz);
+	if (!rx->demodulator()->setModeString(mode))
+		return -1;
+	r->rx.push_back(rx);
+	return (int)r->rx.size() - 1;
+}
+
+int wrr_start(void *h)
+{
+	Quiet q;
+	return ((Rig*)h)->fe->tuner()->start() ? 0 : -1;
+}
+
+/* one Radio::run() (radio.cxx:56-59) over a caller-supplied tuner block */
+int wrr_run(void *h, const float *iq)
+{
+	Quiet q;
+	Rig *r = (Rig*)h;
+	r->tuner->feed(iq, (size_t)r->frames * 2);
+	Radio::run();
+	return 0;
+}
+
+/* what a web handler would do (receiverhandler.cxx:125-140) */
+int wrr_retune(void *h, int rx, int if_hz, const char *mode, unsigned chan_passband)
+{
+	Rig *r = (Rig*)h;
+	r->rx[rx]->downconverter()->setIF(if_hz);
+	if (chan_passband)
+		r->rx[rx]->channelFilter()->setPassband(chan_passband);
+	return r->rx[rx]->demodulator()->setModeString(mode) ? 0 : -1;
+}
+
+long wrr_audio(void *h, int rx, float *out, long cap)
+{
+	Rig *r = (Rig*)h;
+	const vector<float> &v = r->rx[rx]->stream()->last;
+	long n = (long)v.size();
+	if (out && cap > 0)
+		memcpy(out, v.data(), sizeof(float) * (size_t)(n < cap ? n : cap));
+	return n;
+}
+
+int wrr_spectrum(void *h, float *db)
+{
+	Rig *r = (Rig*)h;
+	r->fe->spectrum()->getSpectrum(db);
+	return (int)r->fe->spectrum()->fftSize();
+}
+
+unsigned wrr_counts(void *h, unsigned *n_frontends, unsigned *n_receivers)
+{
+	(void)h;
+	*n_frontends = (unsigned)Radio::frontEnds().size();
+	*n_receivers = (unsigned)Radio::receivers().size();
+	return 0;
+}
+
+void wrr_destroy(void *h)
+{
+	Quiet q;
+	Rig *r = (Rig*)h;
+	r->fe->tuner()->stop();
+	for (size_t i = 0; i < r->rx.size(); i++)
+		delete r->rx[i];
+	delete r->fe;
+	delete r;
+}
+
+} // extern "C"

@@ -25,7 +25,8 @@ def check_demod(mode, got, want, what):
     if mode in (capi.FM, "FM"):
         d = ulp_distance(got, want)
         assert d.max() <= FM_MAX_ULP, f"{what}: FM demod off by {d.max()} ULP"
-        assert (d == 0).mean() >= FM_MIN_EXACT, f"{what}: only {(d == 0).mean():.2%} FM samples exact"
+        if d.size >= 256:
+            assert (d == 0).mean() >= FM_MIN_EXACT, f"{what}: only {(d == 0).mean():.2%} FM samples exact"
     else:
         assert_biteq(got, want, what)
 

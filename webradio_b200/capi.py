@@ -24,7 +24,7 @@ SYMBOLS = [
     "wr_version", "wr_last_error", "wr_device_count", "wr_phase_step", "wr_build_sintable",
     "wr_lowpass_design",
     "wr_bank_create", "wr_bank_destroy", "wr_bank_set_sintable", "wr_rx_set_stream",
-    "wr_rx_set_phase_step", "wr_rx_set_taps", "wr_rx_set_mode", "wr_rx_reset", "wr_rx_get_phase",
+    "wr_rx_set_phase_step", "wr_rx_set_taps", "wr_rx_set_mode", "wr_rx_reset", "wr_rx_set_phase", "wr_rx_get_phase",
     "wr_bank_process", "wr_bank_process_device", "wr_bank_submit", "wr_bank_wait",
     "wr_bank_pipeline_depth", "wr_bank_run_device_steps", "wr_bank_run_host_steps", "wr_bank_stream", "wr_bank_sync", "wr_bank_keep_channel",
     "wr_bank_read_stage", "wr_bank_set_variant", "wr_bank_launch_count", "wr_bank_set_timing",
@@ -66,6 +66,7 @@ def lib():
     L.wr_rx_set_taps.argtypes = [vp, u, i, _fp, u]
     L.wr_rx_set_mode.argtypes = [vp, u, i]
     L.wr_rx_reset.argtypes = [vp, u, u]
+    L.wr_rx_set_phase.argtypes = [vp, u, C.c_uint32]
     L.wr_rx_get_phase.argtypes = [vp, u, C.POINTER(C.c_uint32)]
     L.wr_bank_process.argtypes = [vp, vp, u, vp, sz]
     L.wr_bank_process_device.argtypes = [vp, vp, sz, u, vp, sz, vp]
@@ -186,6 +187,9 @@ class Bank:
 
     def reset(self, rx, flags):
         _check(self.L.wr_rx_reset(self.h, rx, flags), "wr_rx_reset")
+
+    def set_phase(self, rx, phase):
+        _check(self.L.wr_rx_set_phase(self.h, rx, phase), "wr_rx_set_phase")
 
     def get_phase(self, rx):
         v = C.c_uint32(0)

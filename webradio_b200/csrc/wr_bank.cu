@@ -18,13 +18,17 @@ namespace {
 constexpr int kSlots = 3;        // pipeline depth of the submit/wait path
 constexpr int kThreadsV1 = 128;
 
+constexpr unsigned kSetPhase = 0x100u; // internal flag: overwrite the phase with a given value
+
 __global__ void reset_kernel(RxState *st, float2 *hist1, float *demod_hist, unsigned rx,
-		unsigned n1m1, unsigned n2m1, size_t dstride, unsigned flags)
+		unsigned n1m1, unsigned n2m1, size_t dstride, unsigned flags, uint32_t phaseValue)
 {
 	const unsigned tid = threadIdx.x;
 	if (tid == 0) {
 		if (flags & WR_RESET_PHASE)
 			st[rx].phase = 0;
+		if (flags & kSetPhase)
+			st[rx].phase = phaseValue & 0x7FFFFFFFu;
 		if (flags & WR_RESET_DEMOD) {
 			st[rx].prev_i = 0.0f;
 			st[rx].prev_q = 0.0f;
@@ -71,6 +75,7 @@ struct wr_bank {
 	std::vector<RxConf> h_conf;
 	std::vector<float> h_taps1, h_taps2;   // reversed, as the kernels read them
 	std::vector<unsigned> h_reset;         // pending WR_RESET_* per receiver
+	std::vector<uint32_t> h_phase;         // pending wr_rx_set_phase values
 	bool confDirty = true, taps1Dirty = true, taps2Dirty = true, resetDirty = false;
 	bool tableDirty = false;
 	std::vector<float> h_table;
@@ -148,7 +153,7 @@ int apply_pending(wr_bank *b, cudaStream_t st)
 			if (!b->h_reset[r])
 				continue;
 			reset_kernel<<<1, 128, 0, st>>>(b->d_state[b->cur], b->d_hist1[b->cur], b->d_demod[b->cur],
-					r, b->n1 - 1, b->n2 - 1, b->dstride, b->h_reset[r]);
+					r, b->n1 - 1, b->n2 - 1, b->dstride, b->h_reset[r], b->h_phase[r]);
 			b->launches++;
 			b->h_reset[r] = 0;
 		}
@@ -378,6 +383,7 @@ wr_bank *wr_bank_create(int device, unsigned n_streams, unsigned n_receivers, un
 	b->h_taps1.assign((size_t)R * n1, 0.0f);
 	b->h_taps2.assign((size_t)R * n2, 0.0f);
 	b->h_reset.assign(R, 0);
+	b->h_phase.assign(R, 0);
 	b->h_table.resize(WR_SINTABLE_SIZE);
 	wr_build_sintable(b->h_table.data());
 	b->tableDirty = true;
@@ -446,6 +452,16 @@ int wr_rx_reset(wr_bank *b, unsigned rx, unsigned flags)
 	WR_REQUIRE(b && rx < b->R, WR_EINVAL, "wr_rx_reset: rx %u out of range", rx);
 	std::lock_guard<std::mutex> lk(b->mu);
 	b->h_reset[rx] |= flags;
+	b->resetDirty = true;
+	return WR_OK;
+}
+
+int wr_rx_set_phase(wr_bank *b, unsigned rx, uint32_t phase)
+{
+	WR_REQUIRE(b && rx < b->R, WR_EINVAL, "wr_rx_set_phase: rx %u out of range", rx);
+	std::lock_guard<std::mutex> lk(b->mu);
+	b->h_reset[rx] = (b->h_reset[rx] & ~WR_RESET_PHASE) | kSetPhase;
+	b->h_phase[rx] = phase;
 	b->resetDirty = true;
 	return WR_OK;
 }

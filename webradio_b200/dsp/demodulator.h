@@ -1,0 +1,49 @@
+// demodulator.h -- AM / FM / USB / LSB demodulator block, CUDA-backed.  Same public interface as
+// WebRadio's src/dsp/demodulator.h:35-63.
+#ifndef DEMODULATOR_H_
+#define DEMODULATOR_H_
+
+#include <string>
+#include <vector>
+
+#include "dspblock.h"
+
+struct wr_stage;
+
+using namespace std;
+
+class Demodulator : public DspBlock
+{
+public:
+	Demodulator(const string &name = "<undefined>");
+	virtual ~Demodulator();
+
+	enum Mode {
+		AM,
+		FM,
+		USB,
+		LSB,
+		MAX_MODE
+	};
+
+	const Mode mode() const { return _mode; }
+	void setMode(const Mode mode) { _mode = mode; }
+	const string &modeString() const { return _modeStrings[_mode]; }
+	bool setModeString(const string &mode);
+
+	// ---- fused-bank hand-off ----
+	void setFused(bool fused) { _fused = fused; }
+
+private:
+	bool init();
+	void deinit();
+	bool process(const vector<sample_t> &inBuffer, vector<sample_t> &outBuffer);
+
+	volatile Mode _mode;
+	vector<string> _modeStrings;
+	float prev[2]; // prev_i, prev_q (reference demodulator.h:60-61)
+	wr_stage *stage;
+	bool _fused;
+};
+
+#endif /* DEMODULATOR_H_ */
