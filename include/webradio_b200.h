@@ -67,6 +67,11 @@ int32_t wr_phase_step(int if_hz, unsigned sample_rate);
  * (reference src/dsp/downconverter.cxx:49-51).  out has WR_SINTABLE_SIZE entries. */
 void wr_build_sintable(float *out);
 
+/* Diagnostic: checks that `table` (NULL = the default table) survives the exact 16-bit
+ * compression the shared-memory NCO kernels use (webradio_b200/csrc/wr_lo.h).  Returns 0 if
+ * every entry is reproduced bit for bit, -1 if the table cannot be represented (v1 kernels). */
+int wr_lo_compress_check(const float *table);
+
 /* Frequency-sampling low-pass design: replaces LowPass::init (window) + LowPass::recalculate
  * (reference src/dsp/lowpass.cxx:102-110,164-189).  Host code (cold path, K0 in SURVEY.md 2a).
  * ntaps a power of two reproduces the reference; other lengths use the same formulas mod ntaps. */

@@ -78,6 +78,7 @@ struct wr_bank {
 	std::vector<uint32_t> h_phase;         // pending wr_rx_set_phase values
 	bool confDirty = true, taps1Dirty = true, taps2Dirty = true, resetDirty = false;
 	bool tableDirty = false;
+	bool streamsDirty = true;              // receiver -> stream map changed (v2 regroups)
 	std::vector<float> h_table;
 	// pinned staging for the uploads
 	RxConf *p_conf = nullptr;
@@ -128,12 +129,20 @@ int apply_pending(wr_bank *b, cudaStream_t st)
 		WR_CUDA(cudaMemcpyAsync(b->d_table, b->p_table, sizeof(float) * WR_SINTABLE_SIZE,
 				cudaMemcpyHostToDevice, st));
 		b->tableDirty = false;
-		b->v2.tableStale = true;
+		int rc = wrd::v2_set_table(b->v2, b->h_table.data(), st);
+		if (rc != WR_OK)
+			return rc;
 	}
 	if (b->confDirty) {
 		memcpy(b->p_conf, b->h_conf.data(), sizeof(RxConf) * b->R);
 		WR_CUDA(cudaMemcpyAsync(b->d_conf, b->p_conf, sizeof(RxConf) * b->R, cudaMemcpyHostToDevice, st));
 		b->confDirty = false;
+		if (b->streamsDirty) {
+			int rc = wrd::v2_set_groups(b->v2, b->h_conf.data(), b->R, st);
+			if (rc != WR_OK)
+				return rc;
+			b->streamsDirty = false;
+		}
 	}
 	if (b->taps1Dirty) {
 		memcpy(b->p_taps1, b->h_taps1.data(), sizeof(float) * b->h_taps1.size());
@@ -412,6 +421,7 @@ int wr_rx_set_stream(wr_bank *b, unsigned rx, unsigned stream)
 	std::lock_guard<std::mutex> lk(b->mu);
 	b->h_conf[rx].stream = stream;
 	b->confDirty = true;
+	b->streamsDirty = true;
 	return WR_OK;
 }
 

@@ -2,6 +2,7 @@
 // the phase step and the filter design (K0 in SURVEY.md 2a stays on the host, as in the
 // reference).  None of this runs per sample.
 #include "wr_common.h"
+#include "wr_lo.h"
 
 #include <cmath>
 #include <cstdlib>
@@ -57,6 +58,43 @@ bool use_device(int device)
 	return true;
 }
 
+float lo_base_host(int s, const LoCoef &k)
+{
+	const float sf = (float)s;
+	const float w = fmaxf(32768.0f - fabsf(sf), k.eps);
+	const float u = sf * w;
+	const float au = fabsf(u);
+	float p = fmaf(au, k.a2, k.a1);
+	p = fmaf(au, p, k.a0);
+	return u * p;
+}
+
+bool lo_compress(const float *table, int16_t *delta, LoCoef *coef)
+{
+	LoCoef k = lo_coef();
+	// index 32768 (s = -32768): 32768 - |s| = 0, so B = -32768 * eps * a0 (higher terms vanish)
+	const float t = table[32768];
+	k.eps = (t < 0.0f) ? (-t / (32768.0f * k.a0)) : 0.0f;
+	if (!(k.eps < 1.0f))
+		return false;
+	for (uint32_t idx = 0; idx < WR_SINTABLE_SIZE; idx++) {
+		const float b = lo_base_host((int)(int16_t)(uint16_t)idx, k);
+		int32_t bb, tb;
+		memcpy(&bb, &b, 4);
+		memcpy(&tb, &table[idx], 4);
+		const int64_t d = (int64_t)tb - (int64_t)bb;
+		if (d < -32768 || d > 32767)
+			return false;
+		delta[idx] = (int16_t)d;
+		int32_t back = bb + delta[idx];
+		if (back != tb)
+			return false;
+	}
+	if (coef)
+		*coef = k;
+	return true;
+}
+
 } // namespace wr
 
 extern "C" {
@@ -96,6 +134,32 @@ void wr_build_sintable(float *out)
 		double angle = (double)((float)n * 2) * M_PI / (double)scale;
 		out[n] = sinf((float)angle);
 	}
+}
+
+// Diagnostic for the shared-memory NCO table (wr_lo.h): compresses `table` (NULL = the default
+// table), reconstructs every entry the way the v2 kernels do and compares bit for bit.
+// Returns 0 if all 65536 entries are reproduced exactly, -1 if the table cannot be represented.
+int wr_lo_compress_check(const float *table)
+{
+	std::vector<float> def;
+	if (!table) {
+		def.resize(WR_SINTABLE_SIZE);
+		wr_build_sintable(def.data());
+		table = def.data();
+	}
+	std::vector<int16_t> delta(WR_SINTABLE_SIZE);
+	wr::LoCoef k;
+	if (!wr::lo_compress(table, delta.data(), &k))
+		return -1;
+	for (uint32_t idx = 0; idx < WR_SINTABLE_SIZE; idx++) {
+		const float b = wr::lo_base_host((int)(int16_t)(uint16_t)idx, k);
+		int32_t bb;
+		memcpy(&bb, &b, 4);
+		bb += delta[idx];
+		if (memcmp(&bb, &table[idx], 4) != 0)
+			return -1;
+	}
+	return 0;
 }
 
 // Replaces LowPass::init's window (reference lowpass.cxx:102-110) and LowPass::recalculate
