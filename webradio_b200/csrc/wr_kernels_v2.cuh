@@ -341,6 +341,9 @@ inline int v2_set_table(V2Plan &p, const float *h_table, cudaStream_t st)
 		p.ok = false;
 		return WR_OK;
 	}
+	// the kernels index the table by the SIGNED 16-bit index from its middle (entry s lives at
+	// slot s + 32768): rotate the unsigned-indexed host array by half a turn
+	std::rotate(delta.begin(), delta.begin() + 32768, delta.end());
 	WR_CUDA(cudaMemcpyAsync(p.d_delta, delta.data(), kV2TableBytes, cudaMemcpyHostToDevice, st));
 	WR_CUDA(cudaStreamSynchronize(st)); // `delta` is a local
 	p.tableStale = false;
