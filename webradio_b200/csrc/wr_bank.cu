@@ -205,6 +205,8 @@ int launch_block(wr_bank *b, const float *iq_dev, size_t stream_stride, unsigned
 		wr::set_error("v2 kernels do not support this geometry (n1=%u d1=%u)", b->n1, b->d1);
 		return WR_EINVAL;
 	}
+	if (useV2 && !b->d_chan)
+		WR_CUDA(cudaMalloc(&b->d_chan, sizeof(float2) * (size_t)b->R * std::max(1u, b->maxM1)));
 
 	wrd::ChanArgs ca;
 	ca.iq = reinterpret_cast<const float2*>(iq_dev);
@@ -219,7 +221,7 @@ int launch_block(wr_bank *b, const float *iq_dev, size_t stream_stride, unsigned
 	ca.demod = b->d_demod[cur];
 	ca.dstride = b->dstride;
 	ca.demod_off = b->n2 - 1;
-	ca.chan = b->keepChan ? b->d_chan : nullptr;
+	ca.chan = (b->keepChan || useV2) ? b->d_chan : nullptr; // v2 always materialises the channel stream
 	ca.chan_stride = b->maxM1;
 	ca.F = F;
 	ca.M1 = M1;

@@ -6,16 +6,21 @@
 // The table cannot fit an SM as floats, but it can as 16-bit corrections to a closed-form base
 // (wr_lo.h): 128 KiB per CTA, bit-exact by construction and verified on the host.
 //
-// Shape: persistent grid, one 512-thread CTA per SM, each CTA loops over work items
+// Shape: persistent grid, one 1024-thread CTA per SM, warp-specialised.  Each CTA loops over
 //   item = (group of <= RB receivers listening to the same tuner stream, tile of TK outputs).
-// Per item the raw IQ the tile touches is loaded ONCE into registers (coalesced float2 loads,
-// J frames per thread) and re-used for every receiver of the group; per receiver the CTA
-//   1. mixes its frames (LO from the shared-memory table) into a shared-memory tile laid out
-//      period-major with an odd padded period, so that the FIR's lanes hit distinct banks,
-//   2. runs one thread per output over the taps in the reference's order (packed f32x2
-//      mul / add: I and Q in one instruction, each product and sum still rounded separately),
-//   3. demodulates in the epilogue and writes 4 bytes per channel-rate sample.
-// The last tile of a receiver also produces the carried state (mixed history, phase, prev I/Q).
+//   * MIXER warps load the raw IQ the tile touches ONCE into registers (coalesced float2 loads,
+//     J frames per thread), and for every receiver of the group mix it (LO from the
+//     shared-memory table) into one of two shared-memory tiles, laid out period-major with an
+//     odd padded period so that the FIR's lanes hit distinct banks;
+//   * CONSUMER warps run one thread per output over the taps in the reference's order (packed
+//     f32x2: I and Q in one instruction, each product and each sum still rounded separately;
+//     fully unrolled for the common (taps, decimation) pairs) and write the channel-rate IQ
+//     (8 bytes per output); on the last tile of a receiver they also write the carried state
+//     (mixed history, NCO phase).  The demodulator runs as a tiny elementwise kernel over the
+//     channel-rate stream (demod_kernel_v2): its double-precision atan2 is latency-bound and
+//     would otherwise sit on the consumers' critical path.
+// The two roles hand tiles over through named barriers (full/empty per buffer), so the
+// latency-bound tap chains of receiver g overlap the mixing of receiver g+1.
 #pragma once
 
 #include "wr_bank.cuh"
@@ -28,10 +33,23 @@
 
 namespace wrd {
 
-constexpr int kV2Threads = 512;
-constexpr int kV2J = 16;                          // raw frames held in registers per thread
-constexpr unsigned kV2Ucap = kV2Threads * kV2J;   // frames one tile may span
-constexpr unsigned kV2TableBytes = WR_SINTABLE_SIZE * 2;
+constexpr int kV2Threads = 1024;
+constexpr int kV2J = 8;                           // raw frames held in registers per mixer thread
+// Correction table in shared memory, indexed by the SIGNED 16-bit table index s from its middle:
+//     byte offset(s) = 2*s + 4*(s >> 6) + 4*(s >> 11)        (arithmetic shifts)
+// i.e. one padding word after every 32 words and another after every 1024.  A warp's 32 lookups
+// form an arithmetic progression in s (stride = IF step >> 15); without the padding, strides that
+// are multiples of a power of two pile onto a few banks (measured 6.5x wavefront excess on cfg2,
+// 32-way for IFs that are multiples of Fs/32).  With it the bank is (w + w/32 + w/1024) mod 32.
+constexpr int kLoPosMin = 2 * (-32768) + 4 * (-32768 >> 6) + 4 * (-32768 >> 11);   // -67648
+constexpr int kLoPosMax = 2 * 32767 + 4 * (32767 >> 6) + 4 * (32767 >> 11);        //  67638
+constexpr unsigned kV2TableBytes = ((unsigned)(kLoPosMax - kLoPosMin + 2) + 15u) & ~15u;
+constexpr unsigned kLoMidOffset = (unsigned)(-kLoPosMin);                           // byte offset of s = 0
+
+// named barriers (0 is __syncthreads)
+constexpr int kBarFull = 1;    // +buffer: tile written, consumers may read
+constexpr int kBarEmpty = 3;   // +buffer: tile consumed, mixers may overwrite
+constexpr int kBarCons = 5;    // among the consumer warps only
 
 struct V2Args {
 	const int16_t *delta;     // [65536] corrections (HBM copy, staged to shared memory per CTA)
@@ -40,13 +58,24 @@ struct V2Args {
 	const int2 *groups;       // {first index into order, count}
 	unsigned nGroups;
 	unsigned TK, ntiles, nItems;
+	unsigned NC;              // consumer warps (the other kV2Threads/32 - NC warps mix)
 	unsigned A;               // periods of history an output reaches back: ceil((n1-1)/d1)
 	unsigned off;             // A*d1 - (n1-1): offset of an output's first tap in its period
 	unsigned Dp;              // padded period (d1 or d1+1, odd)
-	unsigned magicD;          // ceil(2^32 / d1): u / d1 == umulhi(u, magicD) for u < kV2Ucap
-	unsigned Lcap;            // float2 slots of the mixed tile
+	unsigned magicD;          // ceil(2^32 / d1): u / d1 == umulhi(u, magicD) over a tile
+	unsigned Lcap;            // float2 slots of one mixed tile
 	float negzero;            // -0.0f, deliberately opaque to the compiler (see mul2_rn_exact)
 };
+
+__device__ __forceinline__ void bar_sync(int id, int count)
+{
+	asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void bar_arrive(int id, int count)
+{
+	asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory");
+}
 
 // Base of the compressed table; the host twin is wr::lo_base_host (same IEEE operations, same
 // constants: these literals must stay identical to wr::lo_coef() in wr_lo.h).
@@ -65,11 +94,14 @@ __device__ __forceinline__ float lo_base(int s, float eps)
 	return __fmul_rn(u, p);
 }
 
-// dmid32 = shared-space byte address of the MIDDLE of the correction table (entry for s = 0)
-__device__ __forceinline__ float lo_value(int s, uint32_t dmid32, float eps)
+// dmid32 = shared-space byte address of the table entry of s = 0; q = phase << 1 (so that the
+// signed table index is q >> 16 and its padding terms q >> 22 and q >> 27).
+__device__ __forceinline__ float lo_value(int q, uint32_t dmid32, float eps)
 {
+	const int s = q >> 16;
+	const uint32_t addr = dmid32 + 2u * (uint32_t)s + 4u * (uint32_t)(q >> 22) + 4u * (uint32_t)(q >> 27);
 	int d;
-	asm("ld.shared.s16 %0, [%1];" : "=r"(d) : "r"(dmid32 + 2u * (uint32_t)s));
+	asm("ld.shared.s16 %0, [%1];" : "=r"(d) : "r"(addr));
 	return __int_as_float(__float_as_int(lo_base(s, eps)) + d);
 }
 
@@ -77,10 +109,10 @@ __device__ __forceinline__ float lo_value(int s, uint32_t dmid32, float eps)
 // reference's sinTable[sinidx], sinTable[cosidx] (downconverter.cxx:100-102).
 __device__ __forceinline__ void lo_sincos(uint32_t p, uint32_t dmid32, float eps, float &sn, float &cs)
 {
-	const int ss = (int)(p << 1) >> 16;                    // table index as signed 16 bit
-	const int sc = (int)((p + 0x20000000u) << 1) >> 16;    // + a quarter turn
-	sn = lo_value(ss, dmid32, eps);
-	cs = lo_value(sc, dmid32, eps);
+	const int qs = (int)(p << 1);
+	const int qc = (int)((p << 1) + 0x40000000u);   // + a quarter turn
+	sn = lo_value(qs, dmid32, eps);
+	cs = lo_value(qc, dmid32, eps);
 }
 
 // Packed (I,Q) product, each half rounded exactly like a scalar multiply.
@@ -100,171 +132,266 @@ __device__ __forceinline__ float2 mul2_rn_exact(float2 a, float2 b, float2 nz)
 	return r;
 }
 
-template <int NT, int J, bool kPad>
+// Tile geometry of one work item, identical for both roles and every receiver of the group.
+struct TileGeo {
+	bool last;
+	unsigned kstart, nout;
+	int fb0;          // frame index (relative to the block) of local coordinate u = 0
+	unsigned U;       // frames to mix
+	unsigned nhist;   // leading frames that lie before the block (carried history)
+};
+
+__device__ __forceinline__ TileGeo tile_geo(const ChanArgs &a, const V2Args &v, unsigned tile)
+{
+	TileGeo g;
+	g.last = (tile == v.ntiles - 1);
+	g.kstart = tile * v.TK;
+	const unsigned kend = min(g.kstart + v.TK, a.M1);
+	g.nout = kend > g.kstart ? kend - g.kstart : 0;
+	g.fb0 = ((int)g.kstart - (int)v.A) * (int)a.d1;   // aligned to a decimation period
+	// frames the outputs need: up to (kend-1)*d1; the last tile runs on to F-1 (history)
+	g.U = g.nout ? (unsigned)((int)((kend - 1) * a.d1) - g.fb0 + 1) : 0;
+	if (g.last)
+		g.U = (unsigned)((int)a.F - g.fb0);
+	g.nhist = g.fb0 < 0 ? (unsigned)(-g.fb0) : 0;
+	return g;
+}
+
+// One output of the channel FIR with taps and decimation known at compile time: straight-line
+// code, every shared-memory offset an immediate.  Same tap order and rounding as the generic loop.
+template <int N1, int D1, int DP>
+__device__ __forceinline__ float2 fir_unrolled(const float2 *__restrict__ base, const float2 *__restrict__ rt2, float2 nz)
+{
+	constexpr int A = (N1 - 1 + D1 - 1) / D1;
+	constexpr int OFF = A * D1 - (N1 - 1);
+	float2 acc = make_float2(0.0f, 0.0f);
+	#pragma unroll
+	for (int j = 0; j < N1; j++) {
+		const int u = OFF + j;
+		const int pos = (u / D1) * DP + (u % D1);
+		acc = __fadd2_rn(acc, mul2_rn_exact(rt2[j], base[pos], nz));
+		// keep the scheduler from hoisting every load of the chain to the top (64 registers per
+		// thread at 1024 threads per CTA): loads may only run ~8 taps ahead of the adds
+		if ((j & 7) == 7)
+			asm volatile("" ::: "memory");
+	}
+	return acc;
+}
+
+template <int NT, int J, bool kPad, int N1C, int D1C>
 __global__ void __launch_bounds__(NT, 1) chan_kernel_v2(const ChanArgs a, const V2Args v)
 {
 	extern __shared__ __align__(16) unsigned char wr_smem_v2[];
-	int16_t *dtab = reinterpret_cast<int16_t*>(wr_smem_v2);
-	float2 *s = reinterpret_cast<float2*>(wr_smem_v2 + kV2TableBytes);
-	float2 *rt2 = s + v.Lcap;                 // taps, each duplicated {c, c} for the packed multiply
-	float2 *co = rt2 + a.n1;                  // channel outputs of the tile
-
 	const unsigned tid = threadIdx.x;
 	const unsigned n1 = a.n1, d1 = a.d1;
-	const float2 nz = make_float2(v.negzero, v.negzero);
-	const float eps = v.eps;
-	const uint32_t smem32 = (uint32_t)__cvta_generic_to_shared(wr_smem_v2);
-	const uint32_t dmid32 = smem32 + 65536u;          // entry of s = 0
-	const uint32_t tile32 = smem32 + kV2TableBytes;   // mixed tile
-	const unsigned padMagic = kPad ? v.magicD : 0u;   // pos(u) = u + u / d1 when the period is padded
+	const unsigned tileBytes = v.Lcap * 8u;
+	float2 *rt2 = reinterpret_cast<float2*>(wr_smem_v2 + kV2TableBytes + 2 * (size_t)tileBytes); // taps {c, c}
 
 	// stage the correction table (128 KiB) once per CTA
 	{
 		const uint4 *g = reinterpret_cast<const uint4*>(v.delta);
-		uint4 *d = reinterpret_cast<uint4*>(dtab);
+		uint4 *d = reinterpret_cast<uint4*>(wr_smem_v2);
 		#pragma unroll 4
 		for (unsigned i = tid; i < kV2TableBytes / 16; i += NT)
 			d[i] = __ldg(g + i);
 	}
 	__syncthreads();
 
-	for (unsigned item = blockIdx.x; item < v.nItems; item += gridDim.x) {
-		const unsigned tile = item % v.ntiles;
-		const int2 grp = v.groups[item / v.ntiles];
-		const unsigned stream = a.conf[v.order[grp.x]].stream;
-		const float2 *__restrict__ in = a.iq + (size_t)stream * a.stream_stride;
+	// items are numbered tile-fastest; a CTA steps through them with stride gridDim.x
+	const unsigned stepT = gridDim.x % v.ntiles, stepG = gridDim.x / v.ntiles;
+	const unsigned NCT = v.NC * 32;        // consumer threads
+	const unsigned NMT = NT - NCT;         // mixer threads
+	// Shared-space addresses and loop constants, bounced through a shuffle so that the compiler
+	// keeps them in registers instead of re-deriving them in every unrolled mix body.
+	const uint32_t smem32 = __shfl_sync(0xffffffffu, (uint32_t)__cvta_generic_to_shared(wr_smem_v2), 0);
 
-		// ---- tile geometry (identical for every receiver of the group) ----
-		const bool last = (tile == v.ntiles - 1);
-		const unsigned k0 = tile * v.TK;
-		const unsigned kend = min(k0 + v.TK, a.M1);
-		const unsigned kstart = k0 ? k0 - 1 : 0;   // one extra output: the FM look-back sample
-		const unsigned extra = k0 - kstart;
-		const unsigned nout = kend > kstart ? kend - kstart : 0;
-		// local frame coordinate u = f - fb0, fb0 aligned to a decimation period
-		const int fb0 = ((int)kstart - (int)v.A) * (int)d1;
-		// frames the outputs need: up to (kend-1)*d1; the last tile runs on to F-1 (history)
-		unsigned U = nout ? (unsigned)((int)((kend - 1) * d1) - fb0 + 1) : 0;
-		if (last)
-			U = (unsigned)((int)a.F - fb0);
-		const int jeff = (int)((U + NT - 1) / NT);          // uniform trip count of the mix loop
-		const unsigned nhist = fb0 < 0 ? (unsigned)(-fb0) : 0; // leading frames that are history
+	if (tid >= NCT) {
+		// =============================== MIXER warps ===============================
+		const unsigned mt = tid - NCT;
+		const uint32_t dmid32 = smem32 + kLoMidOffset;                   // table entry of s = 0
+		const float eps = __shfl_sync(0xffffffffu, v.eps, 0);
+		const unsigned padMagic = kPad ? __shfl_sync(0xffffffffu, v.magicD, 0) : 0u; // pos(u) = u + u / d1
+		unsigned n = 0;
+		unsigned tile = blockIdx.x % v.ntiles, gidx = blockIdx.x / v.ntiles;
+		for (unsigned item = blockIdx.x; item < v.nItems; item += gridDim.x) {
+			const TileGeo g = tile_geo(a, v, tile);
+			const int2 grp = v.groups[gidx];
+			tile += stepT; gidx += stepG;
+			if (tile >= v.ntiles) { tile -= v.ntiles; gidx++; }
+			const unsigned stream = a.conf[v.order[grp.x]].stream;
+			const float2 *__restrict__ in = a.iq + (size_t)stream * a.stream_stride;
+			const int jeff = (int)((g.U + NMT - 1) / NMT);   // uniform trip count of the mix loop
 
-		// ---- raw IQ of the tile, once, into registers ----
-		float2 raw[J];
-		#pragma unroll
-		for (int j = 0; j < J; j++) {
-			const unsigned u = tid + j * NT;
-			const int f = fb0 + (int)u;
-			raw[j] = (u < U && f >= 0) ? __ldg(in + f) : make_float2(0.0f, 0.0f);
-		}
-
-		for (int gi = 0; gi < grp.y; gi++) {
-			const unsigned r = v.order[grp.x + gi];
-			const RxConf cf = a.conf[r];
-			const RxState st = a.st_in[r];
-
-			// ---- 1. mix into the shared tile (slots past U or before the block hold zeros) ----
-			const uint32_t pstep = (uint32_t)cf.step * NT;
-			uint32_t p = st.phase + (uint32_t)(fb0 + (int)tid) * (uint32_t)cf.step;
+			// raw IQ of the tile, once, into registers
+			float2 raw[J];
 			#pragma unroll
 			for (int j = 0; j < J; j++) {
-				if (j < jeff) {
-					const unsigned u = tid + j * NT;
-					float sn, cs;
-					lo_sincos(p, dmid32, eps, sn, cs);
-					const float2 m = mix(raw[j], cs, sn);
-					const unsigned pos = kPad ? u + __umulhi(u, padMagic) : u;
-					asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(tile32 + 8u * pos), "f"(m.x), "f"(m.y) : "memory");
-					p += pstep;
-				}
+				const unsigned u = mt + j * NMT;
+				const int f = g.fb0 + (int)u;
+				raw[j] = (u < g.U && f >= 0) ? __ldg(in + f) : make_float2(0.0f, 0.0f);
 			}
-			if (nhist) { // first tile: frames before the block come from the carried history
-				for (unsigned u = tid; u < nhist; u += NT) {
-					const unsigned pos = kPad ? u + __umulhi(u, padMagic) : u;
-					const int hidx = (int)(n1 - 1) + fb0 + (int)u;
-					s[pos] = hidx >= 0 ? a.hist_in[(size_t)r * (n1 - 1) + hidx] : make_float2(0.0f, 0.0f);
-				}
-			}
-			for (unsigned i = tid; i < n1; i += NT) {
-				const float c = a.taps1[(size_t)r * n1 + i];
-				rt2[i] = make_float2(c, c);
-			}
-			__syncthreads();
 
-			// ---- 2. FIR: one thread per output, taps in the reference's order ----
-			for (unsigned o = tid; o < nout; o += NT) {
-				float2 acc = make_float2(0.0f, 0.0f);
-				unsigned j = 0, q = v.off;
-				const float2 *base = s + (size_t)o * v.Dp;
-				while (j < n1) {
-					const unsigned lim = min(d1 - q, n1 - j);
-					const float2 *x = base + q;
-					const float2 *c = rt2 + j;
-					unsigned t = 0;
-					for (; t + 4 <= lim; t += 4) {
-						const float2 x0 = x[t], x1 = x[t + 1], x2 = x[t + 2], x3 = x[t + 3];
-						const float2 c0 = c[t], c1 = c[t + 1], c2 = c[t + 2], c3 = c[t + 3];
-						acc = __fadd2_rn(acc, mul2_rn_exact(c0, x0, nz));
-						acc = __fadd2_rn(acc, mul2_rn_exact(c1, x1, nz));
-						acc = __fadd2_rn(acc, mul2_rn_exact(c2, x2, nz));
-						acc = __fadd2_rn(acc, mul2_rn_exact(c3, x3, nz));
-					}
-					for (; t < lim; t++)
-						acc = __fadd2_rn(acc, mul2_rn_exact(c[t], x[t], nz));
-					j += lim;
-					base += v.Dp;
-					q = 0;
-				}
-				co[o] = acc;
-			}
-			if (last) {
-				// carried state: the last n1-1 mixed frames of [history | block]
-				for (unsigned i = tid; i + 1 < n1; i += NT) {
-					const unsigned u = (unsigned)((int)a.F - (int)(n1 - 1) + (int)i - fb0);
-					const unsigned pos = kPad ? u + __umulhi(u, padMagic) : u;
-					a.hist_out[(size_t)r * (n1 - 1) + i] = s[pos];
-				}
-				if (tid == 0) {
-					a.st_out[r].phase = phase_at(st.phase, cf.step, a.F);
-					if (a.M1 == 0) {
-						a.st_out[r].prev_i = st.prev_i;
-						a.st_out[r].prev_q = st.prev_q;
+			for (int gi = 0; gi < grp.y; gi++, n++) {
+				const unsigned r = v.order[grp.x + gi];
+				const int32_t step = a.conf[r].step;
+				const uint32_t phase0 = a.st_in[r].phase;
+				const uint32_t tile32 = smem32 + kV2TableBytes + (n & 1) * tileBytes;
+				if (n >= 2)
+					bar_sync(kBarEmpty + (n & 1), NT);       // consumers are done with this buffer
+
+				// mix (slots past U or before the block get zeros: raw is zero there)
+				const uint32_t pstep = (uint32_t)step * NMT;
+				uint32_t p = phase0 + (uint32_t)(g.fb0 + (int)mt) * (uint32_t)step;
+				#pragma unroll
+				for (int j = 0; j < J; j += 2) {
+					// two bodies per (uniform) trip test: independent chains for the scheduler.
+					// The second one may run past U; its slot is still inside the tile buffer.
+					if (j < jeff) {
+						#pragma unroll
+						for (int jj = j; jj < j + 2; jj++) {
+							const unsigned u = mt + jj * NMT;
+							float sn, cs;
+							lo_sincos(p, dmid32, eps, sn, cs);
+							const float2 m = mix(raw[jj], cs, sn);
+							const unsigned pos = kPad ? u + __umulhi(u, padMagic) : u;
+							asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(tile32 + 8u * pos), "f"(m.x), "f"(m.y) : "memory");
+							p += pstep;
+						}
 					}
 				}
-			}
-			__syncthreads();
-
-			// ---- 3. demodulator epilogue ----
-			for (unsigned o = tid + extra; o < nout; o += NT) {
-				const unsigned k = kstart + o;
-				const float2 cur = co[o];
-				const float2 prev = o ? co[o - 1] : make_float2(st.prev_i, st.prev_q);
-				a.demod[(size_t)r * a.dstride + a.demod_off + k] = demod(cf.mode, cur, prev);
-				if (a.chan)
-					a.chan[(size_t)r * a.chan_stride + k] = cur;
-				if (k == a.M1 - 1) {
-					a.st_out[r].prev_i = cur.x;
-					a.st_out[r].prev_q = cur.y;
+				if (g.nhist) { // first tile: frames before the block come from the carried history
+					for (unsigned u = mt; u < g.nhist; u += NMT) {
+						const unsigned pos = kPad ? u + __umulhi(u, padMagic) : u;
+						const int hidx = (int)(n1 - 1) + g.fb0 + (int)u;
+						const float2 h = hidx >= 0 ? a.hist_in[(size_t)r * (n1 - 1) + hidx] : make_float2(0.0f, 0.0f);
+						asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(tile32 + 8u * pos), "f"(h.x), "f"(h.y) : "memory");
+					}
 				}
+				bar_arrive(kBarFull + (n & 1), NT);
 			}
-			// the next receiver's mix overwrites s / rt2 only after every thread passed the
-			// barrier above; co is rewritten only after the next receiver's first barrier
 		}
-		__syncthreads(); // co of the last receiver is read above while the next item refills s
+		// drain the (up to two) hand-backs nobody waited for, so no barrier is left half-arrived
+		for (unsigned m = n >= 2 ? n - 2 : 0; m < n; m++)
+			bar_sync(kBarEmpty + (m & 1), NT);
+	} else {
+		// ============================== CONSUMER warps ==============================
+		const float2 nz = make_float2(v.negzero, v.negzero);
+		const unsigned padMagic = kPad ? v.magicD : 0u;
+		unsigned n = 0;
+		unsigned tile = blockIdx.x % v.ntiles, gidx = blockIdx.x / v.ntiles;
+		for (unsigned item = blockIdx.x; item < v.nItems; item += gridDim.x) {
+			const TileGeo g = tile_geo(a, v, tile);
+			const int2 grp = v.groups[gidx];
+			tile += stepT; gidx += stepG;
+			if (tile >= v.ntiles) { tile -= v.ntiles; gidx++; }
+			for (int gi = 0; gi < grp.y; gi++, n++) {
+				const unsigned r = v.order[grp.x + gi];
+				const float2 *s = reinterpret_cast<const float2*>(wr_smem_v2 + kV2TableBytes + (n & 1) * (size_t)tileBytes);
+
+				for (unsigned i = tid; i < n1; i += NCT) {
+					const float c = a.taps1[(size_t)r * n1 + i];
+					rt2[i] = make_float2(c, c);
+				}
+				bar_sync(kBarCons, NCT);
+				bar_sync(kBarFull + (n & 1), NT);            // the mixers finished this tile
+
+				// FIR: one thread per output, taps in the reference's order
+				for (unsigned o = tid; o < g.nout; o += NCT) {
+					float2 acc;
+					if constexpr (N1C > 0) {
+						acc = fir_unrolled<N1C, D1C, kPad ? D1C + 1 : D1C>(s + (size_t)o * v.Dp, rt2, nz);
+					} else {
+						acc = make_float2(0.0f, 0.0f);
+						unsigned j = 0, q = v.off;
+						const float2 *base = s + (size_t)o * v.Dp;
+						while (j < n1) {
+							const unsigned lim = min(d1 - q, n1 - j);
+							const float2 *x = base + q;
+							const float2 *c = rt2 + j;
+							unsigned t = 0;
+							for (; t + 4 <= lim; t += 4) {
+								const float2 x0 = x[t], x1 = x[t + 1], x2 = x[t + 2], x3 = x[t + 3];
+								const float2 c0 = c[t], c1 = c[t + 1], c2 = c[t + 2], c3 = c[t + 3];
+								acc = __fadd2_rn(acc, mul2_rn_exact(c0, x0, nz));
+								acc = __fadd2_rn(acc, mul2_rn_exact(c1, x1, nz));
+								acc = __fadd2_rn(acc, mul2_rn_exact(c2, x2, nz));
+								acc = __fadd2_rn(acc, mul2_rn_exact(c3, x3, nz));
+							}
+							for (; t < lim; t++)
+								acc = __fadd2_rn(acc, mul2_rn_exact(c[t], x[t], nz));
+							j += lim;
+							base += v.Dp;
+							q = 0;
+						}
+					}
+					a.chan[(size_t)r * a.chan_stride + g.kstart + o] = acc;
+				}
+				if (g.last) {
+					// carried state: the last n1-1 mixed frames of [history | block], NCO phase
+					for (unsigned i = tid; i + 1 < n1; i += NCT) {
+						const unsigned u = (unsigned)((int)a.F - (int)(n1 - 1) + (int)i - g.fb0);
+						const unsigned pos = kPad ? u + __umulhi(u, padMagic) : u;
+						a.hist_out[(size_t)r * (n1 - 1) + i] = s[pos];
+					}
+					if (tid == 0)
+						a.st_out[r].phase = phase_at(a.st_in[r].phase, a.conf[r].step, a.F);
+				}
+				bar_sync(kBarCons, NCT);                     // every consumer is done reading the tile
+				bar_arrive(kBarEmpty + (n & 1), NT);         // hand it back to the mixers
+			}
+		}
 	}
+}
+
+// Demodulator over the channel-rate stream (K3): one thread per output sample.  Also carries
+// prev_i / prev_q (reference demodulator.cxx:110-111) to the next block.
+__global__ void __launch_bounds__(256) demod_kernel_v2(const ChanArgs a, unsigned R)
+{
+	const unsigned r = blockIdx.y;
+	const RxConf cf = a.conf[r];
+	const RxState st = a.st_in[r];
+	const float2 *__restrict__ ch = a.chan + (size_t)r * a.chan_stride;
+	for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < a.M1; k += gridDim.x * blockDim.x) {
+		const float2 cur = ch[k];
+		const float2 prev = k ? ch[k - 1] : make_float2(st.prev_i, st.prev_q);
+		a.demod[(size_t)r * a.dstride + a.demod_off + k] = demod(cf.mode, cur, prev);
+		if (k == a.M1 - 1) {
+			a.st_out[r].prev_i = cur.x;
+			a.st_out[r].prev_q = cur.y;
+		}
+	}
+	if (a.M1 == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+		a.st_out[r].prev_i = st.prev_i;
+		a.st_out[r].prev_q = st.prev_q;
+	}
+	(void)R;
 }
 
 // ------------------------------------------------------------------ host side ----
 
+typedef void (*V2Kernel)(const ChanArgs, const V2Args);
+
+// Fully unrolled FIR for the geometries of the BASELINE configs and the reference's shipped
+// point; anything else takes the generic tap loop.
+inline V2Kernel v2_pick_kernel(unsigned n1, unsigned d1)
+{
+	if (n1 == 64 && d1 == 10) return chan_kernel_v2<kV2Threads, kV2J, true, 64, 10>;
+	if (n1 == 127 && d1 == 50) return chan_kernel_v2<kV2Threads, kV2J, true, 127, 50>;
+	if (n1 == 255 && d1 == 50) return chan_kernel_v2<kV2Threads, kV2J, true, 255, 50>;
+	if (n1 == 127 && d1 == 40) return chan_kernel_v2<kV2Threads, kV2J, true, 127, 40>;
+	if (d1 % 2 == 0) return chan_kernel_v2<kV2Threads, kV2J, true, 0, 0>;
+	return chan_kernel_v2<kV2Threads, kV2J, false, 0, 0>;
+}
+
 struct V2Plan {
 	bool ok = false;
+	V2Kernel kernel = nullptr;
 	bool tableStale = true;
 	bool groupsStale = true;
 	int device = 0;
 	int numSMs = 0;
 	unsigned n1 = 0, d1 = 0;
-	unsigned TK = 0, RB = 2, A = 0, off = 0, Dp = 0, magicD = 0, Lcap = 0;
+	unsigned TK = 0, RB = 2, NC = 0, Ucap = 0, A = 0, off = 0, Dp = 0, magicD = 0, Lcap = 0;
 	size_t smemBytes = 0;
 	int16_t *d_delta = nullptr;
 	wr::LoCoef coef = {};
@@ -303,27 +430,33 @@ inline int v2_init(V2Plan &p, int device, unsigned n1, unsigned d1)
 	p.off = p.A * d1 - (n1 - 1);
 	p.Dp = (d1 % 2 == 0) ? d1 + 1 : d1;    // odd period: FIR lanes (stride Dp float2) spread over all banks
 	p.magicD = (unsigned)((0x100000000ull + d1 - 1) / d1);
-	for (unsigned u = 0; u < kV2Ucap + d1; u++) // the reciprocal must be exact over the tile
+	// Split the 32 warps: as many mixers as two tile buffers fit next to the 128 KiB table.
+	const unsigned warps = kV2Threads / 32;
+	unsigned nc = 4;
+	if (const char *e = getenv("WR_V2_NC"))
+		nc = (unsigned)std::min<int>(std::max(1, atoi(e)), (int)warps - 4);
+	for (; nc < warps - 3; nc++) {
+		const unsigned ucap = kV2J * 32 * (warps - nc);
+		const long periods = (long)(ucap / d1) - 2 - (long)p.A;
+		if (periods < 1)
+			return WR_OK;                  // decimation too large for one tile: v1 serves it
+		unsigned tk = (unsigned)std::min<long>(periods, 1023);
+		if (tk >= 32)
+			tk = (tk / 32) * 32;           // whole warps of outputs
+		const unsigned lcap = ucap + ucap / d1 + 2;
+		const size_t smem = kV2TableBytes + sizeof(float2) * (2 * (size_t)lcap + n1 + 2);
+		if (smem <= (size_t)prop.sharedMemPerBlockOptin) {
+			p.NC = nc; p.Ucap = ucap; p.TK = tk; p.Lcap = lcap; p.smemBytes = smem;
+			break;
+		}
+	}
+	if (!p.NC)
+		return WR_OK;
+	for (unsigned u = 0; u < p.Ucap + d1; u++) // the reciprocal must be exact over the tile
 		if ((unsigned)(((unsigned long long)u * p.magicD) >> 32) != u / d1)
 			return WR_OK;
-	// frames a tile spans: (TK + 1 + A) periods, plus up to two more on the last tile
-	const long periods = (long)(kV2Ucap / d1) - 3 - (long)p.A;
-	if (periods < 1)
-		return WR_OK;
-	unsigned tk = (unsigned)std::min<long>(periods, 1023);
-	if (tk + 1 >= 32)
-		tk = ((tk + 1) / 32) * 32 - 1;     // TK + 1 outputs (with the FM helper) fill whole warps
-	p.TK = tk;
-	p.Lcap = kV2Ucap + kV2Ucap / d1 + 2;
-	p.smemBytes = kV2TableBytes + sizeof(float2) * ((size_t)p.Lcap + n1 + tk + 2);
-	if (p.smemBytes > (size_t)prop.sharedMemPerBlockOptin)
-		return WR_OK;
-	if (p.Dp != d1)
-		WR_CUDA(cudaFuncSetAttribute(chan_kernel_v2<kV2Threads, kV2J, true>,
-				cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
-	else
-		WR_CUDA(cudaFuncSetAttribute(chan_kernel_v2<kV2Threads, kV2J, false>,
-				cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
+	p.kernel = v2_pick_kernel(n1, d1);
+	WR_CUDA(cudaFuncSetAttribute(p.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
 	WR_CUDA(cudaMalloc(&p.d_delta, kV2TableBytes));
 	p.tableStale = true;
 	p.groupsStale = true;
@@ -341,11 +474,14 @@ inline int v2_set_table(V2Plan &p, const float *h_table, cudaStream_t st)
 		p.ok = false;
 		return WR_OK;
 	}
-	// the kernels index the table by the SIGNED 16-bit index from its middle (entry s lives at
-	// slot s + 32768): rotate the unsigned-indexed host array by half a turn
-	std::rotate(delta.begin(), delta.begin() + 32768, delta.end());
-	WR_CUDA(cudaMemcpyAsync(p.d_delta, delta.data(), kV2TableBytes, cudaMemcpyHostToDevice, st));
-	WR_CUDA(cudaStreamSynchronize(st)); // `delta` is a local
+	// lay the corrections out the way the kernels address them (signed index, padded rows)
+	std::vector<int16_t> padded(kV2TableBytes / 2, 0);
+	for (int sidx = -32768; sidx < 32768; sidx++) {
+		const int pos = 2 * sidx + 4 * (sidx >> 6) + 4 * (sidx >> 11);
+		padded[(size_t)(pos - kLoPosMin) / 2] = delta[(uint16_t)sidx];
+	}
+	WR_CUDA(cudaMemcpyAsync(p.d_delta, padded.data(), kV2TableBytes, cudaMemcpyHostToDevice, st));
+	WR_CUDA(cudaStreamSynchronize(st)); // `padded` is a local
 	p.tableStale = false;
 	return WR_OK;
 }
@@ -387,7 +523,6 @@ inline int v2_set_groups(V2Plan &p, const RxConf *h_conf, unsigned R, cudaStream
 
 inline int v2_launch_chan(V2Plan &p, ChanArgs &ca, unsigned R, cudaStream_t st, unsigned long long *launches)
 {
-	(void)R;
 	V2Args v;
 	const wr::LoCoef &k = p.coef;
 	v.delta = p.d_delta;
@@ -396,6 +531,7 @@ inline int v2_launch_chan(V2Plan &p, ChanArgs &ca, unsigned R, cudaStream_t st, 
 	v.groups = p.d_groups;
 	v.nGroups = p.nGroups;
 	v.TK = p.TK;
+	v.NC = p.NC;
 	v.ntiles = std::max(1u, (ca.M1 + p.TK - 1) / p.TK);
 	v.nItems = v.ntiles * p.nGroups;
 	v.A = p.A;
@@ -407,10 +543,15 @@ inline int v2_launch_chan(V2Plan &p, ChanArgs &ca, unsigned R, cudaStream_t st, 
 	ca.TK = p.TK;
 	ca.ntiles = v.ntiles;
 	const unsigned grid = std::min<unsigned>(v.nItems, (unsigned)p.numSMs);
-	if (p.Dp != p.d1)
-		chan_kernel_v2<kV2Threads, kV2J, true><<<grid, kV2Threads, p.smemBytes, st>>>(ca, v);
-	else
-		chan_kernel_v2<kV2Threads, kV2J, false><<<grid, kV2Threads, p.smemBytes, st>>>(ca, v);
+	p.kernel<<<grid, kV2Threads, p.smemBytes, st>>>(ca, v);
+	(*launches)++;
+	if (cudaGetLastError() != cudaSuccess)
+		return WR_ECUDA;
+	// demodulate the channel-rate stream this kernel just wrote
+	{
+		const unsigned blocks = std::max(1u, std::min((ca.M1 + 255) / 256, 64u));
+		demod_kernel_v2<<<dim3(blocks, R), 256, 0, st>>>(ca, R);
+	}
 	(*launches)++;
 	return WR_OK;
 }
