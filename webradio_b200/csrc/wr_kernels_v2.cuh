@@ -36,15 +36,17 @@ namespace wrd {
 constexpr int kV2Threads = 1024;
 constexpr int kV2J = 8;                           // raw frames held in registers per mixer thread
 // Correction table in shared memory, indexed by the SIGNED 16-bit table index s from its middle:
-//     byte offset(s) = 2*s + 4*(s >> 6) + 4*(s >> 11)        (arithmetic shifts)
-// i.e. one padding word after every 32 words and another after every 1024.  A warp's 32 lookups
-// form an arithmetic progression in s (stride = IF step >> 15); without the padding, strides that
-// are multiples of a power of two pile onto a few banks (measured 6.5x wavefront excess on cfg2,
-// 32-way for IFs that are multiples of Fs/32).  With it the bank is (w + w/32 + w/1024) mod 32.
-constexpr int kLoPosMin = 2 * (-32768) + 4 * (-32768 >> 6) + 4 * (-32768 >> 11);   // -67648
-constexpr int kLoPosMax = 2 * 32767 + 4 * (32767 >> 6) + 4 * (32767 >> 11);        //  67638
-constexpr unsigned kV2TableBytes = ((unsigned)(kLoPosMax - kLoPosMin + 2) + 15u) & ~15u;
-constexpr unsigned kLoMidOffset = (unsigned)(-kLoPosMin);                           // byte offset of s = 0
+//     entry slot(s) = (s * 1057) >> 10        (arithmetic shift; = s + floor(33 s / 1024))
+// i.e. one padding entry after every ~31 entries.  A warp's 32 lookups form an arithmetic
+// progression in s (stride = IF step >> 15); without padding, strides that are multiples of a
+// power of two pile onto a few banks (measured 6.5x wavefront excess on cfg2, 32-way for IFs that
+// are multiples of Fs/32).  The slot map is strictly increasing (injective) and moves the bank
+// by ~1 per 64, per 2048 and per 1024*odd entries of stride alike.
+constexpr int kLoPadMul = 1057, kLoPadShift = 10;
+constexpr int kLoSlotMin = (-32768 * kLoPadMul) >> kLoPadShift;   // -33824
+constexpr int kLoSlotMax = (32767 * kLoPadMul) >> kLoPadShift;    //  33822
+constexpr unsigned kV2TableBytes = ((unsigned)(kLoSlotMax - kLoSlotMin + 1) * 2u + 15u) & ~15u;
+constexpr unsigned kLoMidOffset = (unsigned)(-kLoSlotMin) * 2u;   // byte offset of the entry of s = 0
 
 // named barriers (0 is __syncthreads)
 constexpr int kBarFull = 1;    // +buffer: tile written, consumers may read
@@ -55,7 +57,7 @@ struct V2Args {
 	const int16_t *delta;     // [65536] corrections (HBM copy, staged to shared memory per CTA)
 	float eps;                // table-dependent clamp of the base polynomial (wr_lo.h)
 	const unsigned *order;    // receivers sorted by stream
-	const int2 *groups;       // {first index into order, count}
+	const int4 *groups;       // {first index into order, count, stream, unused}
 	unsigned nGroups;
 	unsigned TK, ntiles, nItems;
 	unsigned NC;              // consumer warps (the other kV2Threads/32 - NC warps mix)
@@ -63,7 +65,8 @@ struct V2Args {
 	unsigned off;             // A*d1 - (n1-1): offset of an output's first tap in its period
 	unsigned Dp;              // padded period (d1 or d1+1, odd)
 	unsigned magicD;          // ceil(2^32 / d1): u / d1 == umulhi(u, magicD) over a tile
-	unsigned Lcap;            // float2 slots of one mixed tile
+	unsigned Ucap;            // frames one tile buffer holds
+	unsigned Lcap;            // float2 slots of one mixed tile (Ucap plus period padding)
 	float negzero;            // -0.0f, deliberately opaque to the compiler (see mul2_rn_exact)
 };
 
@@ -95,11 +98,11 @@ __device__ __forceinline__ float lo_base(int s, float eps)
 }
 
 // dmid32 = shared-space byte address of the table entry of s = 0; q = phase << 1 (so that the
-// signed table index is q >> 16 and its padding terms q >> 22 and q >> 27).
+// signed table index is q >> 16).
 __device__ __forceinline__ float lo_value(int q, uint32_t dmid32, float eps)
 {
 	const int s = q >> 16;
-	const uint32_t addr = dmid32 + 2u * (uint32_t)s + 4u * (uint32_t)(q >> 22) + 4u * (uint32_t)(q >> 27);
+	const uint32_t addr = dmid32 + 2u * (uint32_t)((s * kLoPadMul) >> kLoPadShift);
 	int d;
 	asm("ld.shared.s16 %0, [%1];" : "=r"(d) : "r"(addr));
 	return __int_as_float(__float_as_int(lo_base(s, eps)) + d);
@@ -215,38 +218,45 @@ __global__ void __launch_bounds__(NT, 1) chan_kernel_v2(const ChanArgs a, const 
 		unsigned tile = blockIdx.x % v.ntiles, gidx = blockIdx.x / v.ntiles;
 		for (unsigned item = blockIdx.x; item < v.nItems; item += gridDim.x) {
 			const TileGeo g = tile_geo(a, v, tile);
-			const int2 grp = v.groups[gidx];
+			const int4 grp = __ldg(v.groups + gidx);
 			tile += stepT; gidx += stepG;
 			if (tile >= v.ntiles) { tile -= v.ntiles; gidx++; }
-			const unsigned stream = a.conf[v.order[grp.x]].stream;
-			const float2 *__restrict__ in = a.iq + (size_t)stream * a.stream_stride;
-			const int jeff = (int)((g.U + NMT - 1) / NMT);   // uniform trip count of the mix loop
+			// parameters of the group's first receiver, fetched alongside the raw tile
+			unsigned r = __ldg(v.order + grp.x);
+			int32_t step = a.conf[r].step;
+			uint32_t phase0 = a.st_in[r].phase;
 
-			// raw IQ of the tile, once, into registers
+			// raw IQ of the tile, once, into registers (zeros before the block and past U)
+			const float2 *__restrict__ src = a.iq + (size_t)(unsigned)grp.z * a.stream_stride + (g.fb0 + (int)mt);
+			const unsigned ulim = g.U - g.nhist;
 			float2 raw[J];
 			#pragma unroll
 			for (int j = 0; j < J; j++) {
 				const unsigned u = mt + j * NMT;
-				const int f = g.fb0 + (int)u;
-				raw[j] = (u < g.U && f >= 0) ? __ldg(in + f) : make_float2(0.0f, 0.0f);
+				raw[j] = (u - g.nhist < ulim) ? __ldg(src + j * NMT) : make_float2(0.0f, 0.0f);
 			}
 
 			for (int gi = 0; gi < grp.y; gi++, n++) {
-				const unsigned r = v.order[grp.x + gi];
-				const int32_t step = a.conf[r].step;
-				const uint32_t phase0 = a.st_in[r].phase;
+				// this receiver's parameters were fetched one iteration ago; fetch the next one's
+				const unsigned rcur = r;
+				const int32_t stepcur = step;
+				const uint32_t phasecur = phase0;
+				if (gi + 1 < grp.y) {
+					r = __ldg(v.order + grp.x + gi + 1);
+					step = a.conf[r].step;
+					phase0 = a.st_in[r].phase;
+				}
 				const uint32_t tile32 = smem32 + kV2TableBytes + (n & 1) * tileBytes;
 				if (n >= 2)
 					bar_sync(kBarEmpty + (n & 1), NT);       // consumers are done with this buffer
 
 				// mix (slots past U or before the block get zeros: raw is zero there)
-				const uint32_t pstep = (uint32_t)step * NMT;
-				uint32_t p = phase0 + (uint32_t)(g.fb0 + (int)mt) * (uint32_t)step;
+				const uint32_t pstep = (uint32_t)stepcur * NMT;
+				uint32_t p = phasecur + (uint32_t)(g.fb0 + (int)mt) * (uint32_t)stepcur;
 				#pragma unroll
 				for (int j = 0; j < J; j += 2) {
-					// two bodies per (uniform) trip test: independent chains for the scheduler.
-					// The second one may run past U; its slot is still inside the tile buffer.
-					if (j < jeff) {
+					// two bodies per (uniform) trip test: independent chains for the scheduler
+					if (j * NMT < g.U) {
 						#pragma unroll
 						for (int jj = j; jj < j + 2; jj++) {
 							const unsigned u = mt + jj * NMT;
@@ -254,7 +264,8 @@ __global__ void __launch_bounds__(NT, 1) chan_kernel_v2(const ChanArgs a, const 
 							lo_sincos(p, dmid32, eps, sn, cs);
 							const float2 m = mix(raw[jj], cs, sn);
 							const unsigned pos = kPad ? u + __umulhi(u, padMagic) : u;
-							asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(tile32 + 8u * pos), "f"(m.x), "f"(m.y) : "memory");
+							if (u < g.U) // slots past the tile's last frame may lie outside the buffer
+								asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(tile32 + 8u * pos), "f"(m.x), "f"(m.y) : "memory");
 							p += pstep;
 						}
 					}
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(NT, 1) chan_kernel_v2(const ChanArgs a, const 
 					for (unsigned u = mt; u < g.nhist; u += NMT) {
 						const unsigned pos = kPad ? u + __umulhi(u, padMagic) : u;
 						const int hidx = (int)(n1 - 1) + g.fb0 + (int)u;
-						const float2 h = hidx >= 0 ? a.hist_in[(size_t)r * (n1 - 1) + hidx] : make_float2(0.0f, 0.0f);
+						const float2 h = hidx >= 0 ? a.hist_in[(size_t)rcur * (n1 - 1) + hidx] : make_float2(0.0f, 0.0f);
 						asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(tile32 + 8u * pos), "f"(h.x), "f"(h.y) : "memory");
 					}
 				}
@@ -281,9 +292,21 @@ __global__ void __launch_bounds__(NT, 1) chan_kernel_v2(const ChanArgs a, const 
 		unsigned tile = blockIdx.x % v.ntiles, gidx = blockIdx.x / v.ntiles;
 		for (unsigned item = blockIdx.x; item < v.nItems; item += gridDim.x) {
 			const TileGeo g = tile_geo(a, v, tile);
-			const int2 grp = v.groups[gidx];
+			const int4 grp = __ldg(v.groups + gidx);
 			tile += stepT; gidx += stepG;
 			if (tile >= v.ntiles) { tile -= v.ntiles; gidx++; }
+			// one otherwise idle consumer warp pulls the NEXT item's raw tile into L2 while this
+			// one is processed, so the mixers' loads see L2 rather than HBM latency
+			if (tid >= NCT - 32 && item + gridDim.x < v.nItems) {
+				const TileGeo gn = tile_geo(a, v, tile);
+				const unsigned nstream = (unsigned)__ldg(v.groups + gidx).z;
+				const int f0 = max(gn.fb0, 0);
+				const int f1 = gn.fb0 + (int)gn.U;
+				const char *base = reinterpret_cast<const char*>(a.iq + (size_t)nstream * a.stream_stride + f0);
+				const int bytes = (f1 - f0) * 8;
+				for (int off = (int)(tid & 31) * 128; off < bytes; off += 32 * 128)
+					asm volatile("prefetch.global.L2 [%0];" :: "l"(base + off));
+			}
 			for (int gi = 0; gi < grp.y; gi++, n++) {
 				const unsigned r = v.order[grp.x + gi];
 				const float2 *s = reinterpret_cast<const float2*>(wr_smem_v2 + kV2TableBytes + (n & 1) * (size_t)tileBytes);
@@ -396,7 +419,7 @@ struct V2Plan {
 	int16_t *d_delta = nullptr;
 	wr::LoCoef coef = {};
 	unsigned *d_order = nullptr;
-	int2 *d_groups = nullptr;
+	int4 *d_groups = nullptr;
 	unsigned nGroups = 0;
 	unsigned capR = 0;
 };
@@ -430,25 +453,28 @@ inline int v2_init(V2Plan &p, int device, unsigned n1, unsigned d1)
 	p.off = p.A * d1 - (n1 - 1);
 	p.Dp = (d1 % 2 == 0) ? d1 + 1 : d1;    // odd period: FIR lanes (stride Dp float2) spread over all banks
 	p.magicD = (unsigned)((0x100000000ull + d1 - 1) / d1);
-	// Split the 32 warps: as many mixers as two tile buffers fit next to the 128 KiB table.
+	// Two tile buffers next to the table: the tile holds as many frames as shared memory allows
+	// (a multiple of 256, at most kV2J frames per mixer thread).
 	const unsigned warps = kV2Threads / 32;
-	unsigned nc = 4;
-	if (const char *e = getenv("WR_V2_NC"))
-		nc = (unsigned)std::min<int>(std::max(1, atoi(e)), (int)warps - 4);
-	for (; nc < warps - 3; nc++) {
-		const unsigned ucap = kV2J * 32 * (warps - nc);
+	for (unsigned ucap = kV2J * 32 * (warps - 4); ucap >= 1024; ucap -= 256) {
 		const long periods = (long)(ucap / d1) - 2 - (long)p.A;
 		if (periods < 1)
 			return WR_OK;                  // decimation too large for one tile: v1 serves it
-		unsigned tk = (unsigned)std::min<long>(periods, 1023);
-		if (tk >= 32)
-			tk = (tk / 32) * 32;           // whole warps of outputs
+		const unsigned tk = (unsigned)std::min<long>(periods, 1024);
 		const unsigned lcap = ucap + ucap / d1 + 2;
 		const size_t smem = kV2TableBytes + sizeof(float2) * (2 * (size_t)lcap + n1 + 2);
-		if (smem <= (size_t)prop.sharedMemPerBlockOptin) {
-			p.NC = nc; p.Ucap = ucap; p.TK = tk; p.Lcap = lcap; p.smemBytes = smem;
-			break;
-		}
+		if (smem > (size_t)prop.sharedMemPerBlockOptin)
+			continue;
+		// mixers: exactly as many warps as cover the tile with kV2J frames per thread (no idle
+		// slots in the unrolled mix loop); the remaining warps (>= 4, one per scheduler) consume
+		const unsigned nm = (ucap + kV2J * 32 - 1) / (kV2J * 32);
+		if (nm + 4 > warps)
+			continue;
+		unsigned nc = warps - nm;
+		if (const char *e = getenv("WR_V2_NC"))
+			nc = (unsigned)std::min<int>(std::max(4, atoi(e)), (int)(warps - nm));
+		p.NC = nc; p.Ucap = ucap; p.TK = tk; p.Lcap = lcap; p.smemBytes = smem;
+		break;
 	}
 	if (!p.NC)
 		return WR_OK;
@@ -476,10 +502,8 @@ inline int v2_set_table(V2Plan &p, const float *h_table, cudaStream_t st)
 	}
 	// lay the corrections out the way the kernels address them (signed index, padded rows)
 	std::vector<int16_t> padded(kV2TableBytes / 2, 0);
-	for (int sidx = -32768; sidx < 32768; sidx++) {
-		const int pos = 2 * sidx + 4 * (sidx >> 6) + 4 * (sidx >> 11);
-		padded[(size_t)(pos - kLoPosMin) / 2] = delta[(uint16_t)sidx];
-	}
+	for (int sidx = -32768; sidx < 32768; sidx++)
+		padded[(size_t)(((sidx * kLoPadMul) >> kLoPadShift) - kLoSlotMin)] = delta[(uint16_t)sidx];
 	WR_CUDA(cudaMemcpyAsync(p.d_delta, padded.data(), kV2TableBytes, cudaMemcpyHostToDevice, st));
 	WR_CUDA(cudaStreamSynchronize(st)); // `padded` is a local
 	p.tableStale = false;
@@ -496,12 +520,12 @@ inline int v2_set_groups(V2Plan &p, const RxConf *h_conf, unsigned R, cudaStream
 		order[r] = r;
 	std::stable_sort(order.begin(), order.end(),
 			[&](unsigned x, unsigned y) { return h_conf[x].stream < h_conf[y].stream; });
-	std::vector<int2> groups;
+	std::vector<int4> groups;
 	for (unsigned i = 0; i < R;) {
 		unsigned n = 1;
 		while (i + n < R && n < p.RB && h_conf[order[i + n]].stream == h_conf[order[i]].stream)
 			n++;
-		groups.push_back(make_int2((int)i, (int)n));
+		groups.push_back(make_int4((int)i, (int)n, (int)h_conf[order[i]].stream, 0));
 		i += n;
 	}
 	if (R > p.capR) {
@@ -510,11 +534,11 @@ inline int v2_set_groups(V2Plan &p, const RxConf *h_conf, unsigned R, cudaStream
 		p.d_order = nullptr;
 		p.d_groups = nullptr;
 		WR_CUDA(cudaMalloc(&p.d_order, sizeof(unsigned) * R));
-		WR_CUDA(cudaMalloc(&p.d_groups, sizeof(int2) * R));
+		WR_CUDA(cudaMalloc(&p.d_groups, sizeof(int4) * R));
 		p.capR = R;
 	}
 	WR_CUDA(cudaMemcpyAsync(p.d_order, order.data(), sizeof(unsigned) * R, cudaMemcpyHostToDevice, st));
-	WR_CUDA(cudaMemcpyAsync(p.d_groups, groups.data(), sizeof(int2) * groups.size(), cudaMemcpyHostToDevice, st));
+	WR_CUDA(cudaMemcpyAsync(p.d_groups, groups.data(), sizeof(int4) * groups.size(), cudaMemcpyHostToDevice, st));
 	WR_CUDA(cudaStreamSynchronize(st)); // locals
 	p.nGroups = (unsigned)groups.size();
 	p.groupsStale = false;
@@ -538,6 +562,7 @@ inline int v2_launch_chan(V2Plan &p, ChanArgs &ca, unsigned R, cudaStream_t st, 
 	v.off = p.off;
 	v.Dp = p.Dp;
 	v.magicD = p.magicD;
+	v.Ucap = p.Ucap;
 	v.Lcap = p.Lcap;
 	v.negzero = -0.0f;
 	ca.TK = p.TK;
