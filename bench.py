@@ -257,7 +257,7 @@ def gpu_arm(args, w, wname):
     import torch
     import torch.distributed as dist
 
-    from webradio_b200 import capi
+    from webradio_b200 import capi, shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -291,8 +291,10 @@ def gpu_arm(args, w, wname):
     block_bytes = 8 * F * T
     nbuf = max(2, -(-int(1.25 * L2_BYTES) // block_bytes))
     nbuf = min(nbuf, max(2, steps + warmup))
+    # weak scaling: this rank owns its own copy of the workload's tuners and receivers
+    mine = shard.weak_scaling_shard(T, R, rank, world)
     gen = torch.Generator(device="cuda")
-    gen.manual_seed(0xB200 + rank)
+    gen.manual_seed(0xB200 + mine.tuners[0])
     inputs = []
     for _ in range(nbuf):
         u8 = torch.randint(0, 256, (T, F, 2), generator=gen, device="cuda", dtype=torch.int32)
@@ -333,12 +335,9 @@ def gpu_arm(args, w, wname):
     ev1.synchronize()
     launches = bank.launch_count() - launches0
     barrier()
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        tmax = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
-    value = world * R * F * steps / (ms * 1e-3) / 1e6
+    # the job finishes when its slowest rank does: MAX over ranks of the device time
+    ms = shard.reduce_max_ms(ev0.elapsed_time(ev1), device="cuda")
+    value = shard.job_throughput(R * F * steps, world, ms) / 1e6
 
     # ---- per-kernel device time (CUDA events around each kernel, same inputs, K more steps) ----
     bank.set_timing(True)

@@ -7,9 +7,11 @@
 // (frames left over from the previous call) and the new block, so the kernel reads through a
 // two-segment view instead of first concatenating them in HBM.
 #include "wr_common.h"
+#include "wr_fft.cuh"
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #ifndef M_PI
@@ -118,6 +120,92 @@ __global__ void __launch_bounds__(1024) spectrum_kernel_v1(const SpecArgs a)
 	}
 }
 
+// Register-blocked transform, N = R1 * 256 (see wr_fft.cuh): one 256-thread CTA per FFT frame.
+constexpr int kRowPitch = 257; // float2 per 256-point row: odd pitch keeps pass 3's column reads conflict-free
+
+template <int R1>
+__global__ void __launch_bounds__(256, 2) spectrum_kernel_v2(const SpecArgs a)
+{
+	extern __shared__ float2 wr_fft_smem[];
+	constexpr unsigned N = R1 * 256;
+	float2 *sm = wr_fft_smem;
+	float2 *tw256 = wr_fft_smem + R1 * kRowPitch;   // exp(-2*pi*i*k/256)
+	const unsigned t = blockIdx.y;
+	const unsigned m = blockIdx.x + a.first_row;
+	const size_t start = (size_t)m * a.hop;
+	const unsigned tid = threadIdx.x;
+
+	tw256[tid] = __ldg(a.twiddle + tid * R1);
+
+	// ---- pass 1: window fused into the load, radix-R1 over the stride-256 index ----
+	{
+		float2 v[R1];
+		#pragma unroll
+		for (int j = 0; j < R1; j++) {
+			const unsigned n = tid + 256u * j;
+			const float2 x = view(a, t, start + n);
+			const float w = __ldg(a.window + n);
+			v[j] = make_float2(__fmul_rn(x.x, w), __fmul_rn(x.y, w)); // inbuf[n] *= window[n] (spectrumsink.cxx:110-113)
+		}
+		wrfft::RegDft<R1>::run(v);
+		// twiddle W_N^(tid * k1), built up from W_N^tid by repeated multiplication
+		const float2 w1 = __ldg(a.twiddle + tid);
+		float2 cur = w1;
+		sm[tid] = v[0];
+		#pragma unroll
+		for (int k1 = 1; k1 < R1; k1++) {
+			sm[k1 * kRowPitch + tid] = wrfft::cmul(v[k1], cur);
+			cur = wrfft::cmul(cur, w1);
+		}
+	}
+	__syncthreads();
+
+	// ---- pass 2: radix-16 over the stride-16 index of every 256-point row ----
+	#pragma unroll
+	for (unsigned i = 0; i < (R1 * 16 + 255) / 256; i++) {
+		const unsigned bf = tid + 256 * i;
+		if (bf < R1 * 16) {
+			const unsigned b = bf & 15, k1 = bf >> 4;
+			float2 *row = sm + k1 * kRowPitch + b;
+			float2 u[16];
+			#pragma unroll
+			for (int q = 0; q < 16; q++)
+				u[q] = row[16 * q];
+			wrfft::RegDft<16>::run(u);
+			#pragma unroll
+			for (int ka = 0; ka < 16; ka++)
+				row[16 * ka] = ka ? wrfft::cmul(u[ka], tw256[(b * ka) & 255]) : u[0];
+		}
+	}
+	__syncthreads();
+
+	// ---- pass 3: radix-16 over the contiguous index; dB + fft-shift fused into the store ----
+	float *rowout = a.rows ? a.rows + (size_t)t * a.row_stride + (size_t)m * N : nullptr;
+	float *last = (m == a.nrows - 1) ? a.last + (size_t)t * N : nullptr;
+	#pragma unroll
+	for (unsigned i = 0; i < (R1 * 16 + 255) / 256; i++) {
+		const unsigned bf = tid + 256 * i;
+		if (bf < R1 * 16) {
+			const unsigned k1 = bf % R1, ka = bf / R1;
+			const float2 *row = sm + k1 * kRowPitch + 16 * ka;
+			float2 u[16];
+			#pragma unroll
+			for (int q = 0; q < 16; q++)
+				u[q] = row[q];
+			wrfft::RegDft<16>::run(u);
+			#pragma unroll
+			for (int kb = 0; kb < 16; kb++) {
+				const unsigned k = bf + R1 * 16 * kb;           // = k1 + R1 * (ka + 16 * kb)
+				const unsigned o = (k + N / 2) & (N - 1);        // fft-shift (spectrumsink.cxx:139)
+				const float p = __fadd_rn(__fmul_rn(u[kb].x, u[kb].x), __fmul_rn(u[kb].y, u[kb].y));
+				const float db = __fsub_rn(__fmul_rn(10.0f, log10f(p)), a.scaledb);
+				if (rowout) rowout[o] = db;
+				if (last) last[o] = db;
+			}
+		}
+	}
+}
+
 // leftover frames of [carry | in] starting at `from` become the next call's carry
 __global__ void spectrum_carry_kernel(const SpecArgs a, float2 *next, size_t from, unsigned count)
 {
@@ -143,6 +231,7 @@ struct wr_spectrum {
 	float *d_last = nullptr;   // [T][N]
 	bool haveLast = false;
 	cudaStream_t lastStream = nullptr; // stream of the most recent launch
+	bool forceV1 = false;              // env WR_FFT_V1=1: radix-4 shared-memory kernel for every size
 	unsigned long long launches = 0;
 };
 
@@ -195,9 +284,20 @@ long run(wr_spectrum *s, const float *iq_dev, size_t in_stride, unsigned nframes
 		// that one is computed; the reference transforms every frame and discards all but the last
 		a.first_row = rows_dev ? 0 : nrows - 1;
 		dim3 grid(nrows - a.first_row, s->T);
-		unsigned threads = std::min(1024u, std::max(32u, s->N / 4));
-		size_t smem = sizeof(float2) * 2 * (size_t)s->N;
-		spectrum_kernel_v1<<<grid, threads, smem, st>>>(a);
+		if (s->N >= 512 && !s->forceV1) {
+			const size_t smem = sizeof(float2) * ((size_t)(s->N / 256) * kRowPitch + 256);
+			switch (s->N / 256) {
+			case 2: spectrum_kernel_v2<2><<<grid, 256, smem, st>>>(a); break;
+			case 4: spectrum_kernel_v2<4><<<grid, 256, smem, st>>>(a); break;
+			case 8: spectrum_kernel_v2<8><<<grid, 256, smem, st>>>(a); break;
+			case 16: spectrum_kernel_v2<16><<<grid, 256, smem, st>>>(a); break;
+			default: spectrum_kernel_v2<32><<<grid, 256, smem, st>>>(a); break;
+			}
+		} else {
+			unsigned threads = std::min(1024u, std::max(32u, s->N / 4));
+			size_t smem = sizeof(float2) * 2 * (size_t)s->N;
+			spectrum_kernel_v1<<<grid, threads, smem, st>>>(a);
+		}
 		s->launches++;
 		WR_CUDA(cudaGetLastError());
 		s->haveLast = true;
@@ -271,6 +371,12 @@ wr_spectrum *wr_spectrum_create(int device, unsigned fft_size, unsigned hop, uns
 	WR_SPEC_ALLOC(cudaMemset(s->d_last, 0, sizeof(float) * (size_t)n_streams * fft_size));
 	WR_SPEC_ALLOC(cudaFuncSetAttribute(spectrum_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize,
 			(int)(sizeof(float2) * 2 * 8192)));
+	WR_SPEC_ALLOC(cudaFuncSetAttribute(spectrum_kernel_v2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			(int)(sizeof(float2) * (16 * kRowPitch + 256))));
+	WR_SPEC_ALLOC(cudaFuncSetAttribute(spectrum_kernel_v2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			(int)(sizeof(float2) * (32 * kRowPitch + 256))));
+	if (const char *e = getenv("WR_FFT_V1"))
+		s->forceV1 = atoi(e) != 0;
 #undef WR_SPEC_ALLOC
 	return s;
 }
