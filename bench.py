@@ -70,11 +70,11 @@ def algorithmic_bytes(w):
     return 8 * F * T + 4 * R * (F // w["d1"] // w["d2"])
 
 
-def chan_kernel_bytes(w):
-    """The fused mix+FIR+demod kernel alone: reads the tuner block(s) once, writes the demodulated
-    stream (4 B per channel-rate sample per receiver)."""
+def chan_kernel_bytes(w, variant):
+    """The dominant kernel alone: reads the tuner block(s) once and writes, per channel-rate
+    sample per receiver, the demodulated float (v1: demod fused in) or the IQ pair (v2)."""
     F, T, R = w["frames"], w["n_streams"], w["n_rx"]
-    return 8 * F * T + 4 * R * (F // w["d1"])
+    return 8 * F * T + (8 if variant == 2 else 4) * R * (F // w["d1"])
 
 
 # ------------------------------------------------------------------ clocks ----
@@ -391,14 +391,17 @@ def gpu_arm(args, w, wname):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
-    kb = chan_kernel_bytes(w)
+    variant_used = bank.variant_in_use()
+    kb = chan_kernel_bytes(w, variant_used)
     achieved = kb / (chan_ms_avg * 1e-3) / 1e9 if chan_ms_avg > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(wname, {}).get("chan_kernel_dram_bytes_per_launch")
     roofline = {
-        "bound": "hbm", "kernel": "fused NCO mix + channel FIR + demod", "achieved": achieved, "peak": peak,
+        "bound": "hbm",
+        "kernel": "chan_kernel_v2: fused NCO mix + channel FIR" if variant_used == 2 else "chan_kernel_v1: fused NCO mix + channel FIR + demod",
+        "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": kb, "kernel_ms": chan_ms_avg, "audio_kernel_ms": audio_ms_avg,
         "kernel_share_of_step": chan_ms_avg / max(chan_ms_avg + audio_ms_avg, 1e-12),
@@ -429,7 +432,7 @@ def gpu_arm(args, w, wname):
             "cpu_baseline": cpu,
             "hbm_gbs_algorithmic_whole_step": algorithmic_bytes(w) * steps / (ms * 1e-3) / 1e9,
             "tuner_msamples_per_s": world * T * F * steps / (ms * 1e-3) / 1e6,
-            "kernel_variant": args.variant,
+            "kernel_variant": variant_used,
         }
         print(json.dumps(line), flush=True)
     bank.close()

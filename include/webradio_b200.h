@@ -160,6 +160,8 @@ long wr_bank_read_stage(wr_bank *b, unsigned rx, int stage, float *out_host, siz
 /* Selects the kernel family: 0 = auto (default), 1 = v1 generic kernels (NCO table read from
  * L2), 2 = v2 kernels (NCO table resident in shared memory).  For tests and profiling. */
 int wr_bank_set_variant(wr_bank *b, int variant);
+/* Which family ran the last block: 1 or 2 (0 before the first block). */
+int wr_bank_variant_in_use(const wr_bank *b);
 /* Kernel launches issued by this bank since creation (for bench.py's gpu_launches). */
 unsigned long long wr_bank_launch_count(const wr_bank *b);
 /* Per-launch device timing with CUDA events on the launch stream.  While enabled every block

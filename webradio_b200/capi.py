@@ -27,7 +27,7 @@ SYMBOLS = [
     "wr_rx_set_phase_step", "wr_rx_set_taps", "wr_rx_set_mode", "wr_rx_reset", "wr_rx_set_phase", "wr_rx_get_phase",
     "wr_bank_process", "wr_bank_process_device", "wr_bank_submit", "wr_bank_wait",
     "wr_bank_pipeline_depth", "wr_bank_run_device_steps", "wr_bank_run_host_steps", "wr_bank_stream", "wr_bank_sync", "wr_bank_keep_channel",
-    "wr_bank_read_stage", "wr_bank_set_variant", "wr_bank_launch_count", "wr_bank_set_timing",
+    "wr_bank_read_stage", "wr_bank_set_variant", "wr_bank_variant_in_use", "wr_bank_launch_count", "wr_bank_set_timing",
     "wr_bank_kernel_times",
     "wr_stage_create", "wr_stage_destroy", "wr_stage_mix", "wr_stage_fir_config", "wr_stage_fir",
     "wr_stage_fir_reset", "wr_stage_demod",
@@ -84,6 +84,7 @@ def lib():
     L.wr_bank_read_stage.restype = C.c_long
     L.wr_bank_read_stage.argtypes = [vp, u, i, _fp, sz]
     L.wr_bank_set_variant.argtypes = [vp, i]
+    L.wr_bank_variant_in_use.argtypes = [vp]
     L.wr_bank_launch_count.restype = C.c_ulonglong
     L.wr_bank_launch_count.argtypes = [vp]
     L.wr_bank_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]
@@ -255,6 +256,9 @@ class Bank:
 
     def set_variant(self, v):
         _check(self.L.wr_bank_set_variant(self.h, v), "wr_bank_set_variant")
+
+    def variant_in_use(self):
+        return int(self.L.wr_bank_variant_in_use(self.h))
 
     def launch_count(self):
         return int(self.L.wr_bank_launch_count(self.h))

@@ -89,6 +89,7 @@ struct wr_bank {
 	int head = 0, tail = 0, inflight = 0;
 
 	int variant = 0;
+	int variantInUse = 0;
 	wrd::V2Plan v2;
 	unsigned long long launches = 0;
 	// optional per-launch device timing: a ring of event triples drained into accumulators
@@ -245,20 +246,45 @@ int launch_block(wr_bank *b, const float *iq_dev, size_t stream_stride, unsigned
 	if (tev)
 		WR_CUDA(cudaEventRecord(tev[1], st));
 
-	wrd::AudioArgs aa;
-	aa.x = b->d_demod[cur];
-	aa.x_next = b->d_demod[nxt];
-	aa.dstride = b->dstride;
-	aa.taps2 = b->d_taps2;
-	aa.audio = audio_dev;
-	aa.audio_stride = audio_stride;
-	aa.M1 = M1;
-	aa.M2 = M2;
-	aa.n2 = b->n2;
-	aa.d2 = b->d2;
-	aa.TK = 128;
-	aa.ntiles = (M2 + aa.TK - 1) / aa.TK;
-	{
+	if (useV2) {
+		// demodulator + audio FIR over the channel-rate IQ the v2 kernel wrote
+		wrd::DemodAudioArgs da;
+		da.chan = b->d_chan;
+		da.chan_stride = b->maxM1;
+		da.conf = b->d_conf;
+		da.st_in = b->d_state[cur];
+		da.st_out = b->d_state[nxt];
+		da.x = b->d_demod[cur];
+		da.x_next = b->d_demod[nxt];
+		da.dstride = b->dstride;
+		da.taps2 = b->d_taps2;
+		da.audio = audio_dev;
+		da.audio_stride = audio_stride;
+		da.M1 = M1;
+		da.M2 = M2;
+		da.n2 = b->n2;
+		da.d2 = b->d2;
+		da.TK = 128;
+		da.ntiles = (M2 + da.TK - 1) / da.TK;
+		size_t lmax = (size_t)da.TK * b->d2 + b->n2 - 1;
+		size_t smem = sizeof(float) * (((lmax + 3) & ~(size_t)3) + b->n2);
+		dim3 grid(da.ntiles + 1, b->R);
+		wrd::demod_audio_kernel_v2<kThreadsV1><<<grid, kThreadsV1, smem, st>>>(da);
+		b->launches++;
+	} else {
+		wrd::AudioArgs aa;
+		aa.x = b->d_demod[cur];
+		aa.x_next = b->d_demod[nxt];
+		aa.dstride = b->dstride;
+		aa.taps2 = b->d_taps2;
+		aa.audio = audio_dev;
+		aa.audio_stride = audio_stride;
+		aa.M1 = M1;
+		aa.M2 = M2;
+		aa.n2 = b->n2;
+		aa.d2 = b->d2;
+		aa.TK = 128;
+		aa.ntiles = (M2 + aa.TK - 1) / aa.TK;
 		size_t lmax = (size_t)(aa.TK - 1) * b->d2 + b->n2;
 		size_t smem = sizeof(float) * (((lmax + 3) & ~(size_t)3) + b->n2);
 		dim3 grid(aa.ntiles + 1, b->R);
@@ -272,6 +298,7 @@ int launch_block(wr_bank *b, const float *iq_dev, size_t stream_stride, unsigned
 		b->tCount++;
 	}
 
+	b->variantInUse = useV2 ? 2 : 1;
 	b->cur = nxt;
 	b->lastM1 = M1;
 	b->lastM2 = M2;
@@ -656,6 +683,8 @@ int wr_bank_set_variant(wr_bank *b, int variant)
 	b->variant = variant;
 	return WR_OK;
 }
+
+int wr_bank_variant_in_use(const wr_bank *b) { return b ? b->variantInUse : 0; }
 
 unsigned long long wr_bank_launch_count(const wr_bank *b) { return b ? b->launches : 0; }
 

@@ -16,9 +16,9 @@
 //     f32x2: I and Q in one instruction, each product and each sum still rounded separately;
 //     fully unrolled for the common (taps, decimation) pairs) and write the channel-rate IQ
 //     (8 bytes per output); on the last tile of a receiver they also write the carried state
-//     (mixed history, NCO phase).  The demodulator runs as a tiny elementwise kernel over the
-//     channel-rate stream (demod_kernel_v2): its double-precision atan2 is latency-bound and
-//     would otherwise sit on the consumers' critical path.
+//     (mixed history, NCO phase).  The demodulator runs fused into the audio-FIR kernel over the
+//     channel-rate stream (demod_audio_kernel_v2): its double-precision atan2 is latency-bound
+//     and would otherwise sit on the consumers' critical path.
 // The two roles hand tiles over through named barriers (full/empty per buffer), so the
 // latency-bound tap chains of receiver g overlap the mixing of receiver g+1.
 #pragma once
@@ -366,28 +366,93 @@ __global__ void __launch_bounds__(NT, 1) chan_kernel_v2(const ChanArgs a, const 
 	}
 }
 
-// Demodulator over the channel-rate stream (K3): one thread per output sample.  Also carries
-// prev_i / prev_q (reference demodulator.cxx:110-111) to the next block.
-__global__ void __launch_bounds__(256) demod_kernel_v2(const ChanArgs a, unsigned R)
+// Demodulator + audio FIR (K3 + K4) over the channel-rate stream the kernel above wrote.
+// Grid (tiles + 1, receivers).  A tile stages [history | demodulated samples] for its outputs in
+// shared memory -- demodulating the n2-1 samples of overlap with the previous tile again rather
+// than waiting for another CTA -- and runs one thread per audio output over the taps in the
+// reference's order.  The extra CTA per receiver writes the carried state: audio-FIR history,
+// prev_i / prev_q (reference demodulator.cxx:110-111), and the demodulated samples past the last
+// audio output.
+struct DemodAudioArgs {
+	const float2 *chan;      // [R][chan_stride] channel-rate IQ of this block
+	size_t chan_stride;
+	const RxConf *conf;
+	const RxState *st_in;
+	RxState *st_out;
+	float *x;                // demod side `cur`: [0,n2-1) history (read), then this block's samples (written)
+	float *x_next;           // demod side `cur^1`: receives the next block's history
+	size_t dstride;
+	const float *taps2;      // [R][n2] reversed
+	float *audio;
+	size_t audio_stride;
+	unsigned M1, M2, n2, d2;
+	unsigned TK, ntiles;
+};
+
+// sample i of [history | demod(chan)] for receiver r
+__device__ __forceinline__ float demod_at(const DemodAudioArgs &a, const float *xr, const float2 *ch,
+		int mode, float2 prev0, unsigned i)
 {
-	const unsigned r = blockIdx.y;
+	if (i < a.n2 - 1)
+		return xr[i];
+	const unsigned k = i - (a.n2 - 1);
+	return demod(mode, ch[k], k ? ch[k - 1] : prev0);
+}
+
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) demod_audio_kernel_v2(const DemodAudioArgs a)
+{
+	extern __shared__ float4 wr_smem_da[];
+	const unsigned r = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+	const unsigned n2 = a.n2, d2 = a.d2;
 	const RxConf cf = a.conf[r];
 	const RxState st = a.st_in[r];
+	const float2 prev0 = make_float2(st.prev_i, st.prev_q);
 	const float2 *__restrict__ ch = a.chan + (size_t)r * a.chan_stride;
-	for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < a.M1; k += gridDim.x * blockDim.x) {
-		const float2 cur = ch[k];
-		const float2 prev = k ? ch[k - 1] : make_float2(st.prev_i, st.prev_q);
-		a.demod[(size_t)r * a.dstride + a.demod_off + k] = demod(cf.mode, cur, prev);
-		if (k == a.M1 - 1) {
-			a.st_out[r].prev_i = cur.x;
-			a.st_out[r].prev_q = cur.y;
+	float *xr = a.x + (size_t)r * a.dstride;
+
+	if (tile == a.ntiles) {
+		// next block's history: the last n2-1 samples of [history | demod]
+		for (unsigned i = tid; i + 1 < n2; i += kThreads)
+			a.x_next[(size_t)r * a.dstride + i] = demod_at(a, xr, ch, cf.mode, prev0, a.M1 + i);
+		// demodulated samples no audio output of this block consumed
+		for (unsigned k = a.M2 * d2 + tid; k < a.M1; k += kThreads)
+			xr[(n2 - 1) + k] = demod(cf.mode, ch[k], k ? ch[k - 1] : prev0);
+		if (tid == 0) {
+			const float2 lastc = a.M1 ? ch[a.M1 - 1] : prev0;
+			a.st_out[r].prev_i = lastc.x;
+			a.st_out[r].prev_q = lastc.y;
 		}
+		return;
 	}
-	if (a.M1 == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
-		a.st_out[r].prev_i = st.prev_i;
-		a.st_out[r].prev_q = st.prev_q;
+
+	const unsigned Lmax = a.TK * d2 + n2 - 1;
+	float *s = reinterpret_cast<float*>(wr_smem_da);
+	float *rt = s + ((Lmax + 3) & ~3u);
+	const unsigned m0 = tile * a.TK;
+	const unsigned mend = min(m0 + a.TK, a.M2);
+	const unsigned nout = mend - m0;
+	// staged window: what the outputs read ((nout-1)*d2 + n2 samples) extended to the end of
+	// the tile's own decimation periods, so that every sample k in [m0*d2, mend*d2) is produced
+	// (and written to the demod stream in HBM) by exactly one tile
+	const unsigned L = nout * d2 + n2 - 1;
+	const unsigned i0 = m0 * d2;
+	for (unsigned i = tid; i < L; i += kThreads) {
+		const float v = demod_at(a, xr, ch, cf.mode, prev0, i0 + i);
+		s[i] = v;
+		if (i >= n2 - 1)
+			xr[i0 + i] = v;
 	}
-	(void)R;
+	for (unsigned i = tid; i < n2; i += kThreads)
+		rt[i] = a.taps2[(size_t)r * n2 + i];
+	__syncthreads();
+	for (unsigned o = tid; o < nout; o += kThreads) {
+		float acc = 0.0f;
+		const float *p = s + (size_t)o * d2;
+		for (unsigned j = 0; j < n2; j++)
+			tap1(acc, rt[j], p[j]);
+		a.audio[(size_t)r * a.audio_stride + m0 + o] = acc;
+	}
 }
 
 // ------------------------------------------------------------------ host side ----
@@ -547,6 +612,7 @@ inline int v2_set_groups(V2Plan &p, const RxConf *h_conf, unsigned R, cudaStream
 
 inline int v2_launch_chan(V2Plan &p, ChanArgs &ca, unsigned R, cudaStream_t st, unsigned long long *launches)
 {
+	(void)R;
 	V2Args v;
 	const wr::LoCoef &k = p.coef;
 	v.delta = p.d_delta;
@@ -572,12 +638,6 @@ inline int v2_launch_chan(V2Plan &p, ChanArgs &ca, unsigned R, cudaStream_t st, 
 	(*launches)++;
 	if (cudaGetLastError() != cudaSuccess)
 		return WR_ECUDA;
-	// demodulate the channel-rate stream this kernel just wrote
-	{
-		const unsigned blocks = std::max(1u, std::min((ca.M1 + 255) / 256, 64u));
-		demod_kernel_v2<<<dim3(blocks, R), 256, 0, st>>>(ca, R);
-	}
-	(*launches)++;
 	return WR_OK;
 }
 
