@@ -41,7 +41,7 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=None)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--workload", default="cfg2", choices=sorted(synth.WORKLOADS) + ["cfg4"])
-    p.add_argument("--variant", type=int, default=0, help="kernel family: 0 auto, 1 v1, 2 v2")
+    p.add_argument("--variant", type=int, default=0, help="kernel family: 0 auto, 1 v1, 2 v2, 3 v3")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU baseline sample")
     return p.parse_args()
@@ -74,7 +74,7 @@ def chan_kernel_bytes(w, variant):
     """The dominant kernel alone: reads the tuner block(s) once and writes, per channel-rate
     sample per receiver, the demodulated float (v1: demod fused in) or the IQ pair (v2)."""
     F, T, R = w["frames"], w["n_streams"], w["n_rx"]
-    return 8 * F * T + (8 if variant == 2 else 4) * R * (F // w["d1"])
+    return 8 * F * T + (8 if variant >= 2 else 4) * R * (F // w["d1"])
 
 
 # ------------------------------------------------------------------ clocks ----
@@ -400,7 +400,7 @@ def gpu_arm(args, w, wname):
         traffic = json.load(open(tpath)).get(wname, {}).get("chan_kernel_dram_bytes_per_launch")
     roofline = {
         "bound": "hbm",
-        "kernel": "chan_kernel_v2: fused NCO mix + channel FIR" if variant_used == 2 else "chan_kernel_v1: fused NCO mix + channel FIR + demod",
+        "kernel": f"chan_kernel_v{variant_used}: fused NCO mix + channel FIR" if variant_used >= 2 else "chan_kernel_v1: fused NCO mix + channel FIR + demod",
         "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": kb, "kernel_ms": chan_ms_avg, "audio_kernel_ms": audio_ms_avg,

@@ -71,6 +71,9 @@ void wr_build_sintable(float *out);
  * compression the shared-memory NCO kernels use (webradio_b200/csrc/wr_lo.h).  Returns 0 if
  * every entry is reproduced bit for bit, -1 if the table cannot be represented (v1 kernels). */
 int wr_lo_compress_check(const float *table);
+/* Same check for the packed-arithmetic compression the v3 kernels use
+ * (webradio_b200/csrc/wr_lo3.h).  -1 means the v3 kernels stand aside for v2/v1. */
+int wr_lo3_compress_check(const float *table);
 
 /* Frequency-sampling low-pass design: replaces LowPass::init (window) + LowPass::recalculate
  * (reference src/dsp/lowpass.cxx:102-110,164-189).  Host code (cold path, K0 in SURVEY.md 2a).
@@ -157,10 +160,12 @@ int wr_bank_keep_channel(wr_bank *b, int keep);
  * number of floats written, or a negative error. */
 long wr_bank_read_stage(wr_bank *b, unsigned rx, int stage, float *out_host, size_t cap_floats);
 
-/* Selects the kernel family: 0 = auto (default), 1 = v1 generic kernels (NCO table read from
- * L2), 2 = v2 kernels (NCO table resident in shared memory).  For tests and profiling. */
+/* Selects the kernel family: 0 = auto (default: the newest one that supports the geometry and
+ * the block length), 1 = v1 generic kernels (NCO table read from L2), 2 = v2 kernels (NCO table
+ * resident in shared memory, tile per work item), 3 = v3 kernels (streaming ring of mixed
+ * slots, packed NCO arithmetic).  For tests and profiling. */
 int wr_bank_set_variant(wr_bank *b, int variant);
-/* Which family ran the last block: 1 or 2 (0 before the first block). */
+/* Which family ran the last block: 1, 2 or 3 (0 before the first block). */
 int wr_bank_variant_in_use(const wr_bank *b);
 /* Kernel launches issued by this bank since creation (for bench.py's gpu_launches). */
 unsigned long long wr_bank_launch_count(const wr_bank *b);

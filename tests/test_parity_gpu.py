@@ -34,7 +34,7 @@ def check_demod(mode, got, want, what):
         assert_biteq(got, want, what)
 
 
-VARIANTS = [1, 2]
+VARIANTS = [1, 2, 3]
 
 
 def make_bank(variant, *args, **kw):
@@ -130,7 +130,7 @@ def test_bank_golden_chain(wro, name, variant):
             try:
                 audio = bank.process(u8_to_iq(g["iq_u8"][b]))
             except capi.WrError as e:
-                if variant == 2 and "do not support" in str(e):
+                if variant in (2, 3) and "do not support" in str(e):
                     pytest.skip(str(e))
                 raise
             assert_biteq(bank.read_stage(0, capi.STAGE_CHANNEL, F), g["channel"][b], f"{name} channel b{b}")
@@ -172,7 +172,7 @@ def run_bank_vs_oracle(wro, variant, fs, F, n_streams, ifs, modes, n1, d1, n2, d
             try:
                 audio = bank.process(iq)
             except capi.WrError as e:
-                if variant == 2 and "do not support" in str(e):
+                if variant in (2, 3) and "do not support" in str(e):
                     pytest.skip(str(e))
                 raise
             for r in check_rx:
@@ -257,7 +257,7 @@ def test_bank_state_reset_and_retune(wro, variant):
             try:
                 got = bank.process(iq)[0]
             except capi.WrError as e:
-                if variant == 2 and "do not support" in str(e):
+                if variant in (2, 3) and "do not support" in str(e):
                     pytest.skip(str(e))
                 raise
             assert_biteq(got, rx.process(iq), f"before reset b{b}")

@@ -4,6 +4,7 @@
 #include "wr_bank.cuh"
 #include "wr_kernels_v1.cuh"
 #include "wr_kernels_v2.cuh"
+#include "wr_kernels_v3.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -91,6 +92,7 @@ struct wr_bank {
 	int variant = 0;
 	int variantInUse = 0;
 	wrd::V2Plan v2;
+	wrd::V3Plan v3;
 	unsigned long long launches = 0;
 	// optional per-launch device timing: a ring of event triples drained into accumulators
 	bool timing = false;
@@ -133,6 +135,9 @@ int apply_pending(wr_bank *b, cudaStream_t st)
 		int rc = wrd::v2_set_table(b->v2, b->h_table.data(), st);
 		if (rc != WR_OK)
 			return rc;
+		rc = wrd::v3_set_table(b->v3, b->h_table.data(), st);
+		if (rc != WR_OK)
+			return rc;
 	}
 	if (b->confDirty) {
 		memcpy(b->p_conf, b->h_conf.data(), sizeof(RxConf) * b->R);
@@ -140,6 +145,9 @@ int apply_pending(wr_bank *b, cudaStream_t st)
 		b->confDirty = false;
 		if (b->streamsDirty) {
 			int rc = wrd::v2_set_groups(b->v2, b->h_conf.data(), b->R, st);
+			if (rc != WR_OK)
+				return rc;
+			rc = wrd::v3_set_groups(b->v3, b->h_conf.data(), b->R, st);
 			if (rc != WR_OK)
 				return rc;
 			b->streamsDirty = false;
@@ -201,7 +209,12 @@ int launch_block(wr_bank *b, const float *iq_dev, size_t stream_stride, unsigned
 		WR_CUDA(cudaEventRecord(tev[0], st));
 	}
 
-	bool useV2 = (b->variant == 2) || (b->variant == 0 && wrd::v2_supported(b->v2));
+	const bool useV3 = (b->variant == 3 || b->variant == 0) && wrd::v3_supported(b->v3, F);
+	if (b->variant == 3 && !useV3) {
+		wr::set_error("v3 kernels do not support this geometry (n1=%u d1=%u, %u frames)", b->n1, b->d1, F);
+		return WR_EINVAL;
+	}
+	bool useV2 = useV3 || (b->variant == 2) || (b->variant == 0 && wrd::v2_supported(b->v2));
 	if (b->variant == 2 && !wrd::v2_supported(b->v2)) {
 		wr::set_error("v2 kernels do not support this geometry (n1=%u d1=%u)", b->n1, b->d1);
 		return WR_EINVAL;
@@ -229,7 +242,11 @@ int launch_block(wr_bank *b, const float *iq_dev, size_t stream_stride, unsigned
 	ca.n1 = b->n1;
 	ca.d1 = b->d1;
 
-	if (useV2) {
+	if (useV3) {
+		rc = wrd::v3_launch_chan(b->v3, ca, st, &b->launches);
+		if (rc != WR_OK)
+			return rc;
+	} else if (useV2) {
 		rc = wrd::v2_launch_chan(b->v2, ca, b->R, st, &b->launches);
 		if (rc != WR_OK)
 			return rc;
@@ -298,7 +315,7 @@ int launch_block(wr_bank *b, const float *iq_dev, size_t stream_stride, unsigned
 		b->tCount++;
 	}
 
-	b->variantInUse = useV2 ? 2 : 1;
+	b->variantInUse = useV3 ? 3 : useV2 ? 2 : 1;
 	b->cur = nxt;
 	b->lastM1 = M1;
 	b->lastM2 = M2;
@@ -317,6 +334,7 @@ void free_bank(wr_bank *b)
 	if (b->d2h)
 		cudaStreamSynchronize(b->d2h);
 	wrd::v2_destroy(b->v2);
+	wrd::v3_destroy(b->v3);
 	cudaFree(b->d_table);
 	cudaFree(b->d_taps1);
 	cudaFree(b->d_taps2);
@@ -426,7 +444,7 @@ wr_bank *wr_bank_create(int device, unsigned n_streams, unsigned n_receivers, un
 	wr_build_sintable(b->h_table.data());
 	b->tableDirty = true;
 
-	if (wrd::v2_init(b->v2, device, n1, d1) != WR_OK) {
+	if (wrd::v2_init(b->v2, device, n1, d1) != WR_OK || wrd::v3_init(b->v3, device, n1, d1) != WR_OK) {
 		free_bank(b);
 		return nullptr;
 	}
@@ -679,7 +697,7 @@ long wr_bank_read_stage(wr_bank *b, unsigned rx, int stage, float *out, size_t c
 
 int wr_bank_set_variant(wr_bank *b, int variant)
 {
-	WR_REQUIRE(b && variant >= 0 && variant <= 2, WR_EINVAL, "wr_bank_set_variant: bad variant %d", variant);
+	WR_REQUIRE(b && variant >= 0 && variant <= 3, WR_EINVAL, "wr_bank_set_variant: bad variant %d", variant);
 	b->variant = variant;
 	return WR_OK;
 }

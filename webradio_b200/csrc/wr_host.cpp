@@ -3,6 +3,7 @@
 // reference).  None of this runs per sample.
 #include "wr_common.h"
 #include "wr_lo.h"
+#include "wr_lo3.h"
 
 #include <cmath>
 #include <cstdlib>
@@ -95,6 +96,72 @@ bool lo_compress(const float *table, int16_t *delta, LoCoef *coef)
 	return true;
 }
 
+
+static inline float lo3_F(int s)
+{
+	// 2^23 + (s + 32768): what the device builds with one byte permute of the biased phase
+	const uint32_t bits = 0x4B000000u | ((uint32_t)(s + 32768) & 0xFFFFu);
+	float f;
+	memcpy(&f, &bits, 4);
+	return f;
+}
+
+static inline float lo3_poly(float y)
+{
+	float p = fmaf(y, WR_LO3_C3, WR_LO3_C2);
+	p = fmaf(y, p, WR_LO3_C1);
+	return fmaf(y, p, WR_LO3_C0);
+}
+
+float lo3_base_host(int s, const Lo3Coef &k)
+{
+	const float t = fmaf(lo3_F(s), WR_LO3_TSCALE, WR_LO3_TBIAS);
+	const float y = t * t;
+	float w = fmaf(y, -1.0f, 1.0f);
+	w = w + k.eps;
+	const float u = t * w;
+	return u * lo3_poly(y);
+}
+
+int lo3_slot_host(int s)
+{
+	const float sl = fmaf(lo3_F(s), WR_LO3_SLOTK, WR_LO3_SLOTM);
+	int32_t bits;
+	memcpy(&bits, &sl, 4);
+	return bits - WR_LO3_SLOTBITS;
+}
+
+bool lo3_compress(const float *table, int16_t *delta, Lo3Coef *coef)
+{
+	Lo3Coef k;
+	// index 32768 (s = -32768, t = -1): 1 - y = 0, so base = (-1 * eps) * poly(1)
+	const float t = table[32768];
+	k.eps = (t < 0.0f) ? (t / (-1.0f * lo3_poly(1.0f))) : 0.0f;
+	if (!(k.eps < 1e-3f))
+		return false;
+	int prev = WR_LO3_SLOT_MIN - 1;
+	for (int s = -32768; s < 32768; s++) {
+		const int slot = lo3_slot_host(s);
+		if (slot <= prev || slot > WR_LO3_SLOT_MAX)
+			return false;
+		prev = slot;
+		const uint32_t idx = (uint32_t)s & 0xFFFFu;
+		const float b = lo3_base_host(s, k);
+		int32_t bb, tb;
+		memcpy(&bb, &b, 4);
+		memcpy(&tb, &table[idx], 4);
+		const int64_t d = (int64_t)tb - (int64_t)bb;
+		if (d < -32768 || d > 32767)
+			return false;
+		delta[idx] = (int16_t)d;
+		if (bb + (int32_t)delta[idx] != tb)
+			return false;
+	}
+	if (coef)
+		*coef = k;
+	return true;
+}
+
 } // namespace wr
 
 extern "C" {
@@ -153,6 +220,31 @@ int wr_lo_compress_check(const float *table)
 		return -1;
 	for (uint32_t idx = 0; idx < WR_SINTABLE_SIZE; idx++) {
 		const float b = wr::lo_base_host((int)(int16_t)(uint16_t)idx, k);
+		int32_t bb;
+		memcpy(&bb, &b, 4);
+		bb += delta[idx];
+		if (memcmp(&bb, &table[idx], 4) != 0)
+			return -1;
+	}
+	return 0;
+}
+
+// Same diagnostic for the packed-arithmetic compression of the v3 kernels (wr_lo3.h).
+int wr_lo3_compress_check(const float *table)
+{
+	std::vector<float> def;
+	if (!table) {
+		def.resize(WR_SINTABLE_SIZE);
+		wr_build_sintable(def.data());
+		table = def.data();
+	}
+	std::vector<int16_t> delta(WR_SINTABLE_SIZE);
+	wr::Lo3Coef k;
+	if (!wr::lo3_compress(table, delta.data(), &k))
+		return -1;
+	for (int s = -32768; s < 32768; s++) {
+		const uint32_t idx = (uint32_t)s & 0xFFFFu;
+		const float b = wr::lo3_base_host(s, k);
 		int32_t bb;
 		memcpy(&bb, &b, 4);
 		bb += delta[idx];

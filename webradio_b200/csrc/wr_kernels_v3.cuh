@@ -1,0 +1,606 @@
+// wr_kernels_v3.cuh -- fused NCO mix + decimating channel FIR (K1+K2 of SURVEY.md 2a), third
+// generation: a STREAMING RING of mixed slots instead of one tile per work item.
+//
+// What v2 measured (profiles/r02_v2_stalls.md): its per-item set-up was 21% of all instructions,
+// the mixers spent 21% of their time waiting for a tile buffer and 18% waiting for raw loads, and
+// the consumer's single dependent FADD2 chain per tile took ~5100 clk because the warp scheduler
+// is fair -- a latency-bound warp gets one issue slot per round like everyone else, so a role
+// that needs 5x the instructions of the others per hand-over is the critical path.
+//
+// Shape of v3.  Persistent grid, one 512-thread CTA per SM.  A CTA owns a contiguous range of
+// "units" (receiver group, pass): a pass is SF = 32*NG*d1 consecutive frames of the block, i.e.
+// GO = 32*NG channel-rate outputs per receiver.
+//   * 10 MIXER warps (320 threads, J = SF/320 frames each).  The raw IQ of a unit is held in
+//     registers (loaded one unit ahead) and shared by the <= RB receivers of the group that
+//     listen to that stream.  Per (receiver, pass) the mixers fill one of S ring slots in shared
+//     memory: [A periods of halo | GO periods], period-major.  The halo -- the last A*d1 mixed
+//     frames of the receiver's previous pass -- never leaves the mixer threads that produced it:
+//     they keep it in registers and store it again into the next slot, so nothing is mixed twice
+//     and slots are self-contained.
+//   * S FIR warps, warp w owning slot w (every S-th pass): one thread per output over the taps in the
+//     reference's order (packed f32x2, products and sums rounded separately), samples and taps
+//     fetched two taps at a time with 128-bit loads.  With S-1 passes in flight every warp of the
+//     CTA has about the same number of instructions per pass, which is what a fair scheduler
+//     needs to keep all of them busy.
+//   * Slots are handed over with named barriers (full/empty per slot); a small descriptor per
+//     slot tells the FIR warp which receiver and which outputs it holds.
+// NCO: the sine and cosine table entries of a frame are reconstructed TOGETHER in the two halves
+// of packed f32x2 registers (wr_lo3.h): one byte permute per entry builds the float index, ten
+// packed instructions produce both bases and both padded table positions.
+#pragma once
+
+#include "wr_bank.cuh"
+#include "wr_device.cuh"
+#include "wr_kernels_v2.cuh"   // bar_sync / bar_arrive / mul2_rn_exact
+#include "wr_lo3.h"
+
+#include <algorithm>
+#include <vector>
+
+namespace wrd {
+
+constexpr int kV3Mixers = 320;                 // mixer threads (10 warps)
+constexpr int kV3Slots = 6;                    // ring slots
+constexpr int kV3Fir = kV3Slots;               // FIR warps: warp w owns slot w (so no barrier is ever shared by two waiters)
+constexpr int kV3Threads = kV3Mixers + 32 * kV3Fir;
+constexpr unsigned kV3TableBytes = (((unsigned)(WR_LO3_SLOT_MAX - WR_LO3_SLOT_MIN + 1) * 2u) + 15u) & ~15u;
+constexpr unsigned kV3MidOffset = (unsigned)(-(WR_LO3_SLOT_MIN)) * 2u;   // byte offset of slot 0
+
+// named barriers (0 is __syncthreads): full 1..S, empty S+1..2S, mixers-only 2S+1
+constexpr int kV3BarFull = 1;
+constexpr int kV3BarEmpty = 1 + kV3Slots;
+constexpr int kV3BarMix = 1 + 2 * kV3Slots;
+
+constexpr int v3_pad_period(int d)
+{
+	// period-major layout: the FIR's lanes step DP float2 apart and load 16 bytes each, so a
+	// quarter-warp covers all 32 banks iff 2*DP = 4 (mod 8) words, i.e. DP = 2 (mod 4)
+	int dp = d;
+	while (dp % 4 != 2)
+		dp += 1;
+	return dp;
+}
+
+template <int N1, int D1>
+struct V3Geo {
+	static constexpr int A = (N1 - 1 + D1 - 1) / D1;       // periods of halo
+	static constexpr int OFF = A * D1 - (N1 - 1);          // offset of an output's first tap in its period
+	static constexpr int DP = v3_pad_period(D1);
+	static constexpr int NG = (32 * D1 >= 1280) ? 1 : 1280 / (32 * D1);   // output groups per slot
+	static constexpr int GO = 32 * NG;                     // outputs per slot
+	static constexpr int SF = GO * D1;                     // frames per pass
+	static constexpr int J = SF / kV3Mixers;               // frames per mixer thread
+	static constexpr int HF = A * D1;                      // halo frames
+	static constexpr int SLOT = (A + GO) * DP;             // float2 entries of one ring slot
+	static constexpr int TAPOFF = OFF & 1;                 // taps stored shifted so that tap pairs are 16-byte aligned
+	static constexpr unsigned kTapsStride = (((unsigned)(N1 + 1) * 8u) + 15u) & ~15u;
+	static_assert(D1 % 2 == 0, "v3 needs an even decimation (128-bit sample loads)");
+	static_assert(SF % kV3Mixers == 0, "pass length must be a multiple of the mixer thread count");
+	static_assert(HF <= kV3Mixers, "halo must fit the last frame of each mixer thread");
+	static_assert(HF <= SF, "a pass must be at least as long as the halo");
+	static_assert(N1 <= kV3Mixers, "taps are staged one per mixer thread");
+};
+
+struct V3Args {
+	const int16_t *delta;     // padded corrections (wr_lo3.h), staged to shared memory per CTA
+	float eps;
+	const unsigned *order;    // receivers sorted by stream
+	const int4 *groups;       // {first index into order, count, stream, unused}
+	unsigned nGroups;
+	unsigned P;               // passes per block: ceil(F / SF)
+	float negzero;            // -0.0f, opaque to the compiler (mul2_rn_exact)
+	unsigned prmtHi;          // 0x4B00, opaque to the compiler so that it stays in a register (lo3_sincos)
+};
+
+// ---- packed f32x2 helpers -------------------------------------------------------------------
+typedef unsigned long long f2_t;
+
+__device__ __forceinline__ f2_t f2_pack(float lo, float hi)
+{
+	f2_t r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+
+__device__ __forceinline__ void f2_unpack(f2_t v, float &lo, float &hi)
+{
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c)
+{
+	f2_t r;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+	return r;
+}
+
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b)
+{
+	f2_t r;
+	asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+	return r;
+}
+
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b)
+{
+	f2_t r;
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+	return r;
+}
+
+// Packed constants of the table reconstruction, built once per thread.
+struct Lo3Regs {
+	f2_t tscale, tbias, slotk, slotm, neg1, one, eps, c0, c1, c2, c3;
+	uint32_t cbase;   // shared-space address of slot 0 minus 2 * WR_LO3_SLOTBITS (mod 2^32)
+	uint32_t hi;      // 0x4B00: exponent bytes of the float index
+};
+
+__device__ __forceinline__ Lo3Regs lo3_regs(float eps, uint32_t dmid32, uint32_t hi)
+{
+	Lo3Regs k;
+	k.tscale = f2_pack(WR_LO3_TSCALE, WR_LO3_TSCALE);
+	k.tbias = f2_pack(WR_LO3_TBIAS, WR_LO3_TBIAS);
+	k.slotk = f2_pack(WR_LO3_SLOTK, WR_LO3_SLOTK);
+	k.slotm = f2_pack(WR_LO3_SLOTM, WR_LO3_SLOTM);
+	k.neg1 = f2_pack(-1.0f, -1.0f);
+	k.one = f2_pack(1.0f, 1.0f);
+	k.eps = f2_pack(eps, eps);
+	k.c0 = f2_pack(WR_LO3_C0, WR_LO3_C0);
+	k.c1 = f2_pack(WR_LO3_C1, WR_LO3_C1);
+	k.c2 = f2_pack(WR_LO3_C2, WR_LO3_C2);
+	k.c3 = f2_pack(WR_LO3_C3, WR_LO3_C3);
+	k.cbase = dmid32 - 2u * (uint32_t)WR_LO3_SLOTBITS;
+	k.hi = hi;
+	return k;
+}
+
+// sin/cos of the NCO for the BIASED doubled phase qb = (phase << 1) + 0x80000000: exactly the
+// reference's sinTable[sinidx], sinTable[cosidx] (downconverter.cxx:100-102).  The bias turns
+// the signed table index into the low 16 bits of a float's mantissa with one byte permute.
+__device__ __forceinline__ void lo3_sincos(uint32_t qb, const Lo3Regs &k, float &sn, float &cs)
+{
+	uint32_t fs, fc;
+	const uint32_t qc = qb + 0x40000000u;      // + a quarter turn
+	asm("prmt.b32 %0, %1, %2, 0x5432;" : "=r"(fs) : "r"(qb), "r"(k.hi));
+	asm("prmt.b32 %0, %1, %2, 0x5432;" : "=r"(fc) : "r"(qc), "r"(k.hi));
+	const f2_t F = f2_pack(__uint_as_float(fs), __uint_as_float(fc));
+	const f2_t SL = f2_fma(F, k.slotk, k.slotm);
+	const f2_t T = f2_fma(F, k.tscale, k.tbias);
+	const f2_t Y = f2_mul(T, T);
+	f2_t W = f2_fma(Y, k.neg1, k.one);
+	W = f2_add(W, k.eps);
+	const f2_t U = f2_mul(T, W);
+	f2_t P = f2_fma(Y, k.c3, k.c2);
+	P = f2_fma(Y, P, k.c1);
+	P = f2_fma(Y, P, k.c0);
+	const f2_t B = f2_mul(U, P);
+	float sls, slc, bs, bc;
+	f2_unpack(SL, sls, slc);
+	f2_unpack(B, bs, bc);
+	int ds, dc;
+	asm("ld.shared.s16 %0, [%1];" : "=r"(ds) : "r"(k.cbase + 2u * __float_as_uint(sls)));
+	asm("ld.shared.s16 %0, [%1];" : "=r"(dc) : "r"(k.cbase + 2u * __float_as_uint(slc)));
+	sn = __int_as_float(__float_as_int(bs) + ds);
+	cs = __int_as_float(__float_as_int(bc) + dc);
+}
+
+__device__ __forceinline__ void sts64(uint32_t addr, float2 v)
+{
+	asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+
+__device__ __forceinline__ float2 lds64(uint32_t addr)
+{
+	float2 v;
+	asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+	return v;
+}
+
+__device__ __forceinline__ void lds128(uint32_t addr, float2 &a, float2 &b)
+{
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y) : "r"(addr));
+}
+
+// position (in float2 entries from the slot base) of the frame v frames after the start of the halo
+template <int D1, int DP>
+__device__ __forceinline__ unsigned v3_pos(unsigned v)
+{
+	return (v / D1) * DP + (v % D1);
+}
+
+// One output of the channel FIR: taps in the reference's order (lowpass.cxx:151-159), every
+// offset an immediate.  base32 = shared address of the first frame of the output's first period,
+// taps32 = shared address of the {c, c} tap pairs.
+template <int N1, int D1, int DP>
+__device__ __forceinline__ float2 fir3(uint32_t base32, uint32_t taps32, float2 nz)
+{
+	using G = V3Geo<N1, D1>;
+	float2 acc = make_float2(0.0f, 0.0f);
+	int j = 0;
+	if (G::OFF & 1) {
+		const float2 x = lds64(base32 + 8u * v3_pos<D1, DP>(G::OFF));
+		const float2 c = lds64(taps32 + 8u * (G::TAPOFF + 0));
+		acc = __fadd2_rn(acc, mul2_rn_exact(c, x, nz));
+		j = 1;
+	}
+	#pragma unroll
+	for (; j + 1 < N1; j += 2) {
+		float2 x0, x1, c0, c1;
+		lds128(base32 + 8u * v3_pos<D1, DP>(G::OFF + j), x0, x1);
+		lds128(taps32 + 8u * (G::TAPOFF + j), c0, c1);
+		acc = __fadd2_rn(acc, mul2_rn_exact(c0, x0, nz));
+		acc = __fadd2_rn(acc, mul2_rn_exact(c1, x1, nz));
+	}
+	if (j < N1) {
+		const float2 x = lds64(base32 + 8u * v3_pos<D1, DP>(G::OFF + j));
+		const float2 c = lds64(taps32 + 8u * (G::TAPOFF + j));
+		acc = __fadd2_rn(acc, mul2_rn_exact(c, x, nz));
+	}
+	return acc;
+}
+
+template <int N1, int D1, int RB>
+__global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a, const V3Args v)
+{
+	using G = V3Geo<N1, D1>;
+	constexpr int NMT = kV3Mixers, J = G::J, S = kV3Slots, C = kV3Fir;
+	constexpr unsigned kSlotBytes = (unsigned)G::SLOT * 8u;
+	constexpr unsigned kBarCount = NMT + 32;
+	extern __shared__ __align__(16) unsigned char wr_smem_v3[];
+	const unsigned tid = threadIdx.x;
+
+	// stage the correction table once per CTA
+	{
+		const uint4 *g = reinterpret_cast<const uint4*>(v.delta);
+		uint4 *d = reinterpret_cast<uint4*>(wr_smem_v3);
+		#pragma unroll 4
+		for (unsigned i = tid; i < kV3TableBytes / 16; i += kV3Threads)
+			d[i] = __ldg(g + i);
+	}
+	__syncthreads();
+
+	const uint32_t smem32 = (uint32_t)__cvta_generic_to_shared(wr_smem_v3);
+	const uint32_t ring32 = smem32 + kV3TableBytes;
+	const uint32_t taps32 = ring32 + S * kSlotBytes;
+	const uint32_t desc32 = taps32 + RB * G::kTapsStride;
+
+	const unsigned P = v.P;
+	const unsigned long long U = (unsigned long long)v.nGroups * P;
+	const unsigned u0 = (unsigned)((unsigned long long)blockIdx.x * U / gridDim.x);
+	const unsigned u1 = (unsigned)((unsigned long long)(blockIdx.x + 1) * U / gridDim.x);
+
+	if (tid < NMT) {
+		// ================================= MIXER warps =================================
+		const unsigned mt = tid;
+		const Lo3Regs lo = lo3_regs(v.eps, smem32 + kV3MidOffset, v.prmtHi);
+		uint32_t posMain[J];
+		#pragma unroll
+		for (int j = 0; j < J; j++)
+			posMain[j] = 8u * v3_pos<D1, G::DP>((unsigned)G::HF + mt + (unsigned)j * NMT);
+		const bool isTail = mt >= (unsigned)(NMT - G::HF);
+		const unsigned ti = mt - (unsigned)(NMT - G::HF);          // halo frame this thread carries
+		const uint32_t posHalo = 8u * v3_pos<D1, G::DP>(isTail ? ti : 0u);
+
+		float2 raw[J], rawN[J];
+		float2 tail[RB];
+		uint32_t qb[RB];          // biased doubled phase of this thread's frame j = 0 of the current pass
+		uint32_t qstep[RB];       // 2 * NMT * step
+		unsigned rx[RB];
+		#pragma unroll
+		for (int rl = 0; rl < RB; rl++) {
+			tail[rl] = make_float2(0.0f, 0.0f);
+			qb[rl] = 0; qstep[rl] = 0; rx[rl] = 0;
+		}
+		#pragma unroll
+		for (int j = 0; j < J; j++)
+			rawN[j] = make_float2(0.0f, 0.0f);
+
+		unsigned n = 0, base = 0, slot = 0;
+		unsigned rg = u0 / P, p = u0 % P;
+		bool newrg = true, havePrefetch = false;
+		int cnt = 0;
+		const float2 *__restrict__ src = nullptr;   // stream of the current group
+
+		for (unsigned unit = u0; unit < u1; unit++) {
+			if (newrg) {
+				// the FIR warps may still read the previous group's taps: drain the ring
+				for (unsigned m = (n > base + S ? n - S : base); m < n; m++)
+					bar_sync(kV3BarEmpty + (int)(m % S), kBarCount);
+				base = n;
+				const int4 grp = __ldg(v.groups + rg);
+				cnt = grp.y;
+				src = a.iq + (size_t)(unsigned)grp.z * a.stream_stride;
+				#pragma unroll
+				for (int rl = 0; rl < RB; rl++) {
+					if (rl < cnt) {
+						const unsigned r = __ldg(v.order + grp.x + rl);
+						const int32_t step = a.conf[r].step;
+						const uint32_t ph0 = a.st_in[r].phase;
+						rx[rl] = r;
+						qstep[rl] = 2u * (uint32_t)NMT * (uint32_t)step;
+						qb[rl] = ((ph0 + (p * (unsigned)G::SF + mt) * (uint32_t)step) << 1) + 0x80000000u;
+						if (mt < (unsigned)N1) {
+							const float c = a.taps1[(size_t)r * N1 + mt];
+							sts64(taps32 + rl * G::kTapsStride + 8u * (G::TAPOFF + mt), make_float2(c, c));
+						}
+						if (isTail) {
+							if (p == 0) {
+								// frames before the block: the carried history (zeros beyond it)
+								const int hidx = (int)(N1 - 1) - G::HF + (int)ti;
+								tail[rl] = hidx >= 0 ? a.hist_in[(size_t)r * (N1 - 1) + hidx] : make_float2(0.0f, 0.0f);
+							} else {
+								// the range starts inside the block: mix the halo frames once
+								const unsigned f = p * (unsigned)G::SF - (unsigned)G::HF + ti;
+								float sn, cs;
+								lo3_sincos(((ph0 + f * (uint32_t)step) << 1) + 0x80000000u, lo, sn, cs);
+								tail[rl] = mix(__ldg(src + f), cs, sn);
+							}
+						}
+					}
+				}
+				havePrefetch = false;
+			}
+			// raw IQ of this unit (registers); frames past the block read as zero
+			const unsigned f0 = p * (unsigned)G::SF + mt;
+			if (havePrefetch) {
+				#pragma unroll
+				for (int j = 0; j < J; j++)
+					raw[j] = rawN[j];
+			} else {
+				#pragma unroll
+				for (int j = 0; j < J; j++) {
+					const unsigned f = f0 + (unsigned)j * NMT;
+					raw[j] = f < a.F ? __ldg(src + f) : make_float2(0.0f, 0.0f);
+				}
+			}
+			const bool lastPass = (p + 1 == P);
+			const bool nextSame = !lastPass && (unit + 1 < u1);
+			// pull the unit four passes ahead into L2 while this one is mixed
+			if (p + 4 < P && ((size_t)(p + 4) * G::SF + (size_t)mt * 16) < a.F)
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(src + (size_t)(p + 4) * G::SF) + (size_t)mt * 128));
+
+			#pragma unroll
+			for (int rl = 0; rl < RB; rl++) {
+				if (rl < cnt) {
+					if (n >= base + S)
+						bar_sync(kV3BarEmpty + (int)slot, kBarCount);      // the FIR warp is done with this slot
+					const uint32_t slot32 = ring32 + slot * kSlotBytes;
+					if (isTail)
+						sts64(slot32 + posHalo, tail[rl]);
+					if (rl == cnt - 1 && nextSame) {
+						// last receiver of the unit: fetch the next unit's raw IQ behind the mixing
+						#pragma unroll
+						for (int j = 0; j < J; j++) {
+							const unsigned f = f0 + (unsigned)G::SF + (unsigned)j * NMT;
+							rawN[j] = f < a.F ? __ldg(src + f) : make_float2(0.0f, 0.0f);
+						}
+					}
+					uint32_t q = qb[rl];
+					#pragma unroll
+					for (int j = 0; j < J; j++) {
+						float sn, cs;
+						lo3_sincos(q, lo, sn, cs);
+						const float2 m = mix(raw[j], cs, sn);
+						sts64(slot32 + posMain[j], m);
+						if (j == J - 1)
+							tail[rl] = m;      // only meaningful (and only used) in the tail threads
+						q += qstep[rl];
+					}
+					qb[rl] = q;   // J * qstep = 2 * SF * step further: frame j = 0 of the next pass
+					if (mt == 0) {
+						const unsigned k0 = p * (unsigned)G::GO;
+						const unsigned nout = a.M1 > k0 ? min(a.M1 - k0, (unsigned)G::GO) : 0u;
+						asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
+								:: "r"(desc32 + slot * 16u), "r"(rx[rl]), "r"(k0), "r"(nout), "r"((unsigned)rl) : "memory");
+					}
+					if (lastPass) {
+						// carried state: the last N1-1 mixed frames of [history | block], NCO phase
+						bar_sync(kV3BarMix, NMT);
+						const unsigned fp = a.F - p * (unsigned)G::SF;          // frames of this pass, 1..SF
+						if (mt < (unsigned)(N1 - 1)) {
+							const unsigned vv = (unsigned)G::HF + fp - (unsigned)(N1 - 1) + mt;
+							a.hist_out[(size_t)rx[rl] * (N1 - 1) + mt] = lds64(slot32 + 8u * v3_pos<D1, G::DP>(vv));
+						}
+						if (mt == 0)
+							a.st_out[rx[rl]].phase = phase_at(a.st_in[rx[rl]].phase, a.conf[rx[rl]].step, a.F);
+					}
+					bar_arrive(kV3BarFull + (int)slot, kBarCount);
+					n++;
+					slot = (slot + 1 == S) ? 0u : slot + 1;
+				}
+			}
+			havePrefetch = nextSame;
+			p++;
+			newrg = false;
+			if (p == P) {
+				p = 0;
+				rg++;
+				newrg = true;
+			}
+		}
+		// tell every FIR warp to stop, then collect the hand-backs nobody waited for
+		const unsigned N = n;
+		for (int i = 0; i < C; i++) {
+			if (n >= base + S)
+				bar_sync(kV3BarEmpty + (int)slot, kBarCount);
+			if (mt == 0)
+				asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
+						:: "r"(desc32 + slot * 16u), "r"(0u), "r"(0u), "r"(0u), "r"(0xFFFFFFFFu) : "memory");
+			bar_arrive(kV3BarFull + (int)slot, kBarCount);
+			n++;
+			slot = (slot + 1 == S) ? 0u : slot + 1;
+		}
+		for (unsigned m = (n > base + S ? n - S : base); m < N; m++)
+			bar_sync(kV3BarEmpty + (int)(m % S), kBarCount);
+	} else {
+		// ================================== FIR warps ==================================
+		const unsigned fw = (tid - NMT) >> 5, lane = tid & 31;
+		const float2 nz = make_float2(v.negzero, v.negzero);
+		for (unsigned n = fw; ; n += C) {
+			const unsigned slot = n % S;
+			bar_sync(kV3BarFull + (int)slot, kBarCount);
+			unsigned r, k0, nout, rl;
+			asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r), "=r"(k0), "=r"(nout), "=r"(rl) : "r"(desc32 + slot * 16u));
+			if (rl == 0xFFFFFFFFu)
+				break;
+			const uint32_t slot32 = ring32 + slot * kSlotBytes;
+			const uint32_t t32 = taps32 + rl * G::kTapsStride;
+			#pragma unroll 1
+			for (int g = 0; g < G::NG; g++) {
+				const unsigned o = (unsigned)g * 32u + lane;
+				if ((unsigned)g * 32u < nout) {     // warp-uniform
+					const float2 acc = fir3<N1, D1, G::DP>(slot32 + 8u * o * (unsigned)G::DP, t32, nz);
+					if (o < nout)
+						a.chan[(size_t)r * a.chan_stride + k0 + o] = acc;
+				}
+			}
+			bar_arrive(kV3BarEmpty + (int)slot, kBarCount);
+		}
+	}
+}
+
+// ------------------------------------------------------------------ host side ----
+
+typedef void (*V3Kernel)(const ChanArgs, const V3Args);
+
+struct V3Plan {
+	bool ok = false;
+	V3Kernel kernel = nullptr;
+	int device = 0;
+	int numSMs = 0;
+	unsigned n1 = 0, d1 = 0;
+	unsigned SF = 0, RB = 1;
+	size_t smemBytes = 0;
+	int16_t *d_delta = nullptr;
+	wr::Lo3Coef coef = {};
+	unsigned *d_order = nullptr;
+	int4 *d_groups = nullptr;
+	unsigned nGroups = 0;
+	unsigned capR = 0;
+};
+
+template <int N1, int D1, int RB>
+inline void v3_fill(V3Plan &p)
+{
+	using G = V3Geo<N1, D1>;
+	p.kernel = chan_kernel_v3<N1, D1, RB>;
+	p.SF = G::SF;
+	p.RB = RB;
+	p.smemBytes = kV3TableBytes + (size_t)kV3Slots * G::SLOT * 8 + (size_t)RB * G::kTapsStride + (size_t)kV3Slots * 16;
+}
+
+inline void v3_destroy(V3Plan &p)
+{
+	cudaFree(p.d_delta);
+	cudaFree(p.d_order);
+	cudaFree(p.d_groups);
+	p.d_delta = nullptr;
+	p.d_order = nullptr;
+	p.d_groups = nullptr;
+	p.ok = false;
+}
+
+// v3 is built for the geometries of the BASELINE configs and the reference's shipped point;
+// everything else stays with v2 / v1.
+inline int v3_init(V3Plan &p, int device, unsigned n1, unsigned d1)
+{
+	p.device = device;
+	p.n1 = n1;
+	p.d1 = d1;
+	p.ok = false;
+	p.kernel = nullptr;
+	if (n1 == 64 && d1 == 10) v3_fill<64, 10, 4>(p);
+	else if (n1 == 127 && d1 == 50) v3_fill<127, 50, 4>(p);
+	else if (n1 == 255 && d1 == 50) v3_fill<255, 50, 2>(p);
+	else if (n1 == 127 && d1 == 40) v3_fill<127, 40, 4>(p);
+	else return WR_OK;
+	cudaDeviceProp prop;
+	WR_CUDA(cudaGetDeviceProperties(&prop, device));
+	p.numSMs = prop.multiProcessorCount;
+	if (p.smemBytes > (size_t)prop.sharedMemPerBlockOptin)
+		return WR_OK;
+	WR_CUDA(cudaFuncSetAttribute(p.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
+	WR_CUDA(cudaMalloc(&p.d_delta, kV3TableBytes));
+	p.ok = true;
+	return WR_OK;
+}
+
+inline bool v3_supported(const V3Plan &p, unsigned F) { return p.ok && F >= p.SF; }
+
+// (Re)compress the NCO table after it changed; v3 turns itself off if it is not representable.
+inline int v3_set_table(V3Plan &p, const float *h_table, cudaStream_t st)
+{
+	if (!p.d_delta)
+		return WR_OK;
+	std::vector<int16_t> delta(WR_SINTABLE_SIZE);
+	if (!wr::lo3_compress(h_table, delta.data(), &p.coef)) {
+		p.ok = false;
+		return WR_OK;
+	}
+	std::vector<int16_t> padded(kV3TableBytes / 2, 0);
+	for (int s = -32768; s < 32768; s++)
+		padded[(size_t)(wr::lo3_slot_host(s) - WR_LO3_SLOT_MIN)] = delta[(uint16_t)s];
+	WR_CUDA(cudaMemcpyAsync(p.d_delta, padded.data(), kV3TableBytes, cudaMemcpyHostToDevice, st));
+	WR_CUDA(cudaStreamSynchronize(st)); // `padded` is a local
+	return WR_OK;
+}
+
+// Receivers sorted by stream and cut into groups of <= RB that share one.
+inline int v3_set_groups(V3Plan &p, const RxConf *h_conf, unsigned R, cudaStream_t st)
+{
+	if (!p.d_delta)
+		return WR_OK;
+	std::vector<unsigned> order(R);
+	for (unsigned r = 0; r < R; r++)
+		order[r] = r;
+	std::stable_sort(order.begin(), order.end(),
+			[&](unsigned x, unsigned y) { return h_conf[x].stream < h_conf[y].stream; });
+	std::vector<int4> groups;
+	for (unsigned i = 0; i < R;) {
+		unsigned n = 1;
+		while (i + n < R && n < p.RB && h_conf[order[i + n]].stream == h_conf[order[i]].stream)
+			n++;
+		groups.push_back(make_int4((int)i, (int)n, (int)h_conf[order[i]].stream, 0));
+		i += n;
+	}
+	if (R > p.capR) {
+		cudaFree(p.d_order);
+		cudaFree(p.d_groups);
+		p.d_order = nullptr;
+		p.d_groups = nullptr;
+		WR_CUDA(cudaMalloc(&p.d_order, sizeof(unsigned) * R));
+		WR_CUDA(cudaMalloc(&p.d_groups, sizeof(int4) * R));
+		p.capR = R;
+	}
+	WR_CUDA(cudaMemcpyAsync(p.d_order, order.data(), sizeof(unsigned) * R, cudaMemcpyHostToDevice, st));
+	WR_CUDA(cudaMemcpyAsync(p.d_groups, groups.data(), sizeof(int4) * groups.size(), cudaMemcpyHostToDevice, st));
+	WR_CUDA(cudaStreamSynchronize(st)); // locals
+	p.nGroups = (unsigned)groups.size();
+	return WR_OK;
+}
+
+inline int v3_launch_chan(V3Plan &p, ChanArgs &ca, cudaStream_t st, unsigned long long *launches)
+{
+	V3Args v;
+	v.delta = p.d_delta;
+	v.eps = p.coef.eps;
+	v.order = p.d_order;
+	v.groups = p.d_groups;
+	v.nGroups = p.nGroups;
+	v.P = (ca.F + p.SF - 1) / p.SF;
+	v.negzero = -0.0f;
+	v.prmtHi = 0x4B00u;
+	const unsigned long long units = (unsigned long long)v.nGroups * v.P;
+	const unsigned grid = (unsigned)std::min<unsigned long long>(units, (unsigned long long)p.numSMs);
+	p.kernel<<<grid, kV3Threads, p.smemBytes, st>>>(ca, v);
+	(*launches)++;
+	const cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) {
+		wr::set_error("chan_kernel_v3 launch (grid %u, %d threads, %zu bytes of shared memory): %s",
+				grid, kV3Threads, p.smemBytes, cudaGetErrorString(e));
+		return WR_ECUDA;
+	}
+	return WR_OK;
+}
+
+} // namespace wrd
