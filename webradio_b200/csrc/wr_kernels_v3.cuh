@@ -72,8 +72,8 @@ struct V3Geo {
 	static constexpr int J = SF / kV3Mixers;               // frames per mixer thread
 	static constexpr int HF = A * D1;                      // halo frames
 	static constexpr int SLOT = (A + GO) * DP;             // float2 entries of one ring slot
-	static constexpr int TAPOFF = OFF & 1;                 // taps stored shifted so that tap pairs are 16-byte aligned
-	static constexpr unsigned kTapsStride = (((unsigned)(N1 + 1) * 8u) + 15u) & ~15u;
+	static constexpr int TAPOFF = (4 - (OFF & 1)) & 3;     // taps stored shifted so that groups of four are 16-byte aligned
+	static constexpr unsigned kTapsStride = (((unsigned)(N1 + 3) * 4u) + 15u) & ~15u;
 	static_assert(D1 % 2 == 0, "v3 needs an even decimation (128-bit sample loads)");
 	static_assert(SF % kV3Mixers == 0, "pass length must be a multiple of the mixer thread count");
 	static_assert(HF <= kV3Mixers, "halo must fit the last frame of each mixer thread");
@@ -189,6 +189,11 @@ __device__ __forceinline__ void sts64(uint32_t addr, float2 v)
 	asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
 
+__device__ __forceinline__ void sts32(uint32_t addr, float v)
+{
+	asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ float2 lds64(uint32_t addr)
 {
 	float2 v;
@@ -196,9 +201,37 @@ __device__ __forceinline__ float2 lds64(uint32_t addr)
 	return v;
 }
 
-__device__ __forceinline__ void lds128(uint32_t addr, float2 &a, float2 &b)
+__device__ __forceinline__ float lds32(uint32_t addr)
 {
-	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y) : "r"(addr));
+	float v;
+	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+	return v;
+}
+
+__device__ __forceinline__ f2_t lds64p(uint32_t addr)
+{
+	f2_t v;
+	asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+	return v;
+}
+
+__device__ __forceinline__ void lds128p(uint32_t addr, f2_t &a, f2_t &b)
+{
+	asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+
+__device__ __forceinline__ float4 lds128f(uint32_t addr)
+{
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+	return v;
+}
+
+__device__ __forceinline__ f2_t ldg64p(const float2 *p)
+{
+	f2_t v;
+	asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(v) : "l"(p));
+	return v;
 }
 
 // position (in float2 entries from the slot base) of the frame v frames after the start of the halo
@@ -208,34 +241,47 @@ __device__ __forceinline__ unsigned v3_pos(unsigned v)
 	return (v / D1) * DP + (v % D1);
 }
 
+// One tap of LowPass::process for the I/Q pair (lowpass.cxx:155-156): the product is rounded on
+// its own (fma(c, x, -0) == RN(c * x), see mul2_rn_exact), then added.  {c, c} is the broadcast
+// operand form of the packed instruction, so a tap is one 32-bit register.
+__device__ __forceinline__ f2_t tap3(f2_t acc, float c, f2_t x, f2_t nz)
+{
+	return f2_add(acc, f2_fma(x, f2_pack(c, c), nz));
+}
+
 // One output of the channel FIR: taps in the reference's order (lowpass.cxx:151-159), every
 // offset an immediate.  base32 = shared address of the first frame of the output's first period,
-// taps32 = shared address of the {c, c} tap pairs.
+// taps32 = shared address of the receiver's taps (plain floats, four per 128-bit load).
 template <int N1, int D1, int DP>
-__device__ __forceinline__ float2 fir3(uint32_t base32, uint32_t taps32, float2 nz)
+__device__ __forceinline__ f2_t fir3(uint32_t base32, uint32_t taps32, f2_t nz)
 {
 	using G = V3Geo<N1, D1>;
-	float2 acc = make_float2(0.0f, 0.0f);
+	f2_t acc = 0ull;
 	int j = 0;
 	if (G::OFF & 1) {
-		const float2 x = lds64(base32 + 8u * v3_pos<D1, DP>(G::OFF));
-		const float2 c = lds64(taps32 + 8u * (G::TAPOFF + 0));
-		acc = __fadd2_rn(acc, mul2_rn_exact(c, x, nz));
+		acc = tap3(acc, lds32(taps32 + 4u * (G::TAPOFF + 0)), lds64p(base32 + 8u * v3_pos<D1, DP>(G::OFF)), nz);
 		j = 1;
 	}
 	#pragma unroll
-	for (; j + 1 < N1; j += 2) {
-		float2 x0, x1, c0, c1;
-		lds128(base32 + 8u * v3_pos<D1, DP>(G::OFF + j), x0, x1);
-		lds128(taps32 + 8u * (G::TAPOFF + j), c0, c1);
-		acc = __fadd2_rn(acc, mul2_rn_exact(c0, x0, nz));
-		acc = __fadd2_rn(acc, mul2_rn_exact(c1, x1, nz));
+	for (; j + 3 < N1; j += 4) {
+		f2_t x0, x1, x2, x3;
+		const float4 c = lds128f(taps32 + 4u * (G::TAPOFF + j));
+		lds128p(base32 + 8u * v3_pos<D1, DP>(G::OFF + j), x0, x1);
+		lds128p(base32 + 8u * v3_pos<D1, DP>(G::OFF + j + 2), x2, x3);
+		acc = tap3(acc, c.x, x0, nz);
+		acc = tap3(acc, c.y, x1, nz);
+		acc = tap3(acc, c.z, x2, nz);
+		acc = tap3(acc, c.w, x3, nz);
 	}
-	if (j < N1) {
-		const float2 x = lds64(base32 + 8u * v3_pos<D1, DP>(G::OFF + j));
-		const float2 c = lds64(taps32 + 8u * (G::TAPOFF + j));
-		acc = __fadd2_rn(acc, mul2_rn_exact(c, x, nz));
+	if (j + 1 < N1) {
+		f2_t x0, x1;
+		lds128p(base32 + 8u * v3_pos<D1, DP>(G::OFF + j), x0, x1);
+		acc = tap3(acc, lds32(taps32 + 4u * (G::TAPOFF + j)), x0, nz);
+		acc = tap3(acc, lds32(taps32 + 4u * (G::TAPOFF + j + 1)), x1, nz);
+		j += 2;
 	}
+	if (j < N1)
+		acc = tap3(acc, lds32(taps32 + 4u * (G::TAPOFF + j)), lds64p(base32 + 8u * v3_pos<D1, DP>(G::OFF + j)), nz);
 	return acc;
 }
 
@@ -249,17 +295,29 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 	extern __shared__ __align__(16) unsigned char wr_smem_v3[];
 	const unsigned tid = threadIdx.x;
 
-	// stage the correction table once per CTA
-	{
-		const uint4 *g = reinterpret_cast<const uint4*>(v.delta);
-		uint4 *d = reinterpret_cast<uint4*>(wr_smem_v3);
-		#pragma unroll 4
-		for (unsigned i = tid; i < kV3TableBytes / 16; i += kV3Threads)
-			d[i] = __ldg(g + i);
+	// Stage the correction table once per CTA: one thread issues bulk copies (TMA, no tensor map
+	// needed for a contiguous range) that complete on an mbarrier, so the 132 KiB transfer runs
+	// behind the first group's set-up and raw loads instead of in front of them.
+	__shared__ __align__(8) unsigned long long wr_table_bar;
+	const uint32_t bar32 = (uint32_t)__cvta_generic_to_shared(&wr_table_bar);
+	if (tid == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar32) : "memory");
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
+	if (tid == 0) {
+		const uint32_t dst32 = (uint32_t)__cvta_generic_to_shared(wr_smem_v3);
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar32), "r"(kV3TableBytes) : "memory");
+		constexpr unsigned kChunk = 16384;
+		for (unsigned off = 0; off < kV3TableBytes; off += kChunk) {
+			const unsigned nb = min(kChunk, kV3TableBytes - off);
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+					:: "r"(dst32 + off), "l"(reinterpret_cast<const char*>(v.delta) + off), "r"(nb), "r"(bar32) : "memory");
+		}
+	}
 
-	const uint32_t smem32 = (uint32_t)__cvta_generic_to_shared(wr_smem_v3);
+	uint32_t smem32 = (uint32_t)__cvta_generic_to_shared(wr_smem_v3);
+	asm volatile("" : "+r"(smem32));   // opaque: keeps the window base in a register instead of re-deriving it per pass
 	const uint32_t ring32 = smem32 + kV3TableBytes;
 	const uint32_t taps32 = ring32 + S * kSlotBytes;
 	const uint32_t desc32 = taps32 + RB * G::kTapsStride;
@@ -273,6 +331,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 		// ================================= MIXER warps =================================
 		const unsigned mt = tid;
 		const Lo3Regs lo = lo3_regs(v.eps, smem32 + kV3MidOffset, v.prmtHi);
+		const f2_t nzp = f2_pack(v.negzero, v.negzero);
 		uint32_t posMain[J];
 		#pragma unroll
 		for (int j = 0; j < J; j++)
@@ -280,8 +339,11 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 		const bool isTail = mt >= (unsigned)(NMT - G::HF);
 		const unsigned ti = mt - (unsigned)(NMT - G::HF);          // halo frame this thread carries
 		const uint32_t posHalo = 8u * v3_pos<D1, G::DP>(isTail ? ti : 0u);
+		const unsigned Pfull = a.F / (unsigned)G::SF;              // passes that lie entirely inside the block
+		const bool pfLine = mt < (unsigned)(G::SF / 16);           // this thread prefetches line mt of a pass
+		const unsigned pfOff = 4u * (unsigned)G::SF + 15u * mt;    // float2 units from this thread's frame j = 0
 
-		float2 raw[J], rawN[J];
+		f2_t rawA[J], rawB[J];    // raw IQ of the current / the next pass, {i, q} packed (ping-pong)
 		float2 tail[RB];
 		uint32_t qb[RB];          // biased doubled phase of this thread's frame j = 0 of the current pass
 		uint32_t qstep[RB];       // 2 * NMT * step
@@ -291,132 +353,149 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 			tail[rl] = make_float2(0.0f, 0.0f);
 			qb[rl] = 0; qstep[rl] = 0; rx[rl] = 0;
 		}
-		#pragma unroll
-		for (int j = 0; j < J; j++)
-			rawN[j] = make_float2(0.0f, 0.0f);
 
 		unsigned n = 0, base = 0, slot = 0;
-		unsigned rg = u0 / P, p = u0 % P;
-		bool newrg = true, havePrefetch = false;
-		int cnt = 0;
-		const float2 *__restrict__ src = nullptr;   // stream of the current group
-
-		for (unsigned unit = u0; unit < u1; unit++) {
-			if (newrg) {
-				// the FIR warps may still read the previous group's taps: drain the ring
-				for (unsigned m = (n > base + S ? n - S : base); m < n; m++)
-					bar_sync(kV3BarEmpty + (int)(m % S), kBarCount);
-				base = n;
-				const int4 grp = __ldg(v.groups + rg);
-				cnt = grp.y;
-				src = a.iq + (size_t)(unsigned)grp.z * a.stream_stride;
+		unsigned unit = u0;
+		bool tableReady = false;
+		while (unit < u1) {
+			// ---- a run of consecutive passes [p0, pend) of one receiver group ----
+			const unsigned rg = unit / P, p0 = unit - rg * P;
+			const unsigned pend = min(P, p0 + (u1 - unit));
+			// the FIR warps may still read the previous group's taps: drain the ring
+			for (unsigned m = (n > base + S ? n - S : base); m < n; m++)
+				bar_sync(kV3BarEmpty + (int)(m % S), kBarCount);
+			base = n;
+			const int4 grp = __ldg(v.groups + rg);
+			const int cnt = grp.y;
+			const float2 *__restrict__ src = a.iq + (size_t)(unsigned)grp.z * a.stream_stride;
+			// this thread's frame j = 0 of the current pass; frames past the block read as zero
+			const float2 *rawp = src + (size_t)p0 * G::SF + mt;
+			#pragma unroll
+			for (int j = 0; j < J; j++) {
+				const unsigned f = p0 * (unsigned)G::SF + mt + (unsigned)j * NMT;
+				rawA[j] = f < a.F ? ldg64p(src + f) : 0ull;
+			}
+			uint32_t ph0[RB];
+			int32_t step[RB];
+			#pragma unroll
+			for (int rl = 0; rl < RB; rl++) {
+				ph0[rl] = 0; step[rl] = 0;
+				if (rl < cnt) {
+					const unsigned r = __ldg(v.order + grp.x + rl);
+					step[rl] = a.conf[r].step;
+					ph0[rl] = a.st_in[r].phase;
+					rx[rl] = r;
+					qstep[rl] = 2u * (uint32_t)NMT * (uint32_t)step[rl];
+					qb[rl] = ((ph0[rl] + (p0 * (unsigned)G::SF + mt) * (uint32_t)step[rl]) << 1) + 0x80000000u;
+					if (mt < (unsigned)N1)
+						sts32(taps32 + rl * G::kTapsStride + 4u * (G::TAPOFF + mt), a.taps1[(size_t)r * N1 + mt]);
+					if (isTail && p0 == 0) {
+						// frames before the block: the carried history (zeros beyond it)
+						const int hidx = (int)(N1 - 1) - G::HF + (int)ti;
+						tail[rl] = hidx >= 0 ? a.hist_in[(size_t)r * (N1 - 1) + hidx] : make_float2(0.0f, 0.0f);
+					}
+				}
+			}
+			if (!tableReady) {
+				// first use of the NCO table: the bulk copies must have landed
+				uint32_t done;
+				do {
+					asm volatile("{\n\t.reg .pred p;\n\t"
+							"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+							"selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar32) : "memory");
+				} while (!done);
+				tableReady = true;
+			}
+			if (isTail && p0 != 0) {
+				// the run starts inside the block: mix the halo frames once
 				#pragma unroll
 				for (int rl = 0; rl < RB; rl++) {
 					if (rl < cnt) {
-						const unsigned r = __ldg(v.order + grp.x + rl);
-						const int32_t step = a.conf[r].step;
-						const uint32_t ph0 = a.st_in[r].phase;
-						rx[rl] = r;
-						qstep[rl] = 2u * (uint32_t)NMT * (uint32_t)step;
-						qb[rl] = ((ph0 + (p * (unsigned)G::SF + mt) * (uint32_t)step) << 1) + 0x80000000u;
-						if (mt < (unsigned)N1) {
-							const float c = a.taps1[(size_t)r * N1 + mt];
-							sts64(taps32 + rl * G::kTapsStride + 8u * (G::TAPOFF + mt), make_float2(c, c));
-						}
-						if (isTail) {
-							if (p == 0) {
-								// frames before the block: the carried history (zeros beyond it)
-								const int hidx = (int)(N1 - 1) - G::HF + (int)ti;
-								tail[rl] = hidx >= 0 ? a.hist_in[(size_t)r * (N1 - 1) + hidx] : make_float2(0.0f, 0.0f);
+						const unsigned f = p0 * (unsigned)G::SF - (unsigned)G::HF + ti;
+						float sn, cs;
+						lo3_sincos(((ph0[rl] + f * (uint32_t)step[rl]) << 1) + 0x80000000u, lo, sn, cs);
+						tail[rl] = mix(__ldg(src + f), cs, sn);
+					}
+				}
+			}
+
+			// One pass: `cur` holds its raw IQ, `nxt` receives the next one's while the last
+			// receiver of the group is mixed.
+			auto do_pass = [&](f2_t (&cur)[J], f2_t (&nxt)[J], const unsigned p) {
+				const bool lastPass = (p + 1 == P);
+				const bool more = (p + 1 < pend);
+				// pull the pass four ahead into L2 while this one is mixed: one 128-byte line per thread
+				if (pfLine && p + 4 < Pfull)
+					asm volatile("prefetch.global.L2 [%0];" :: "l"(rawp + pfOff));
+				#pragma unroll
+				for (int rl = 0; rl < RB; rl++) {
+					if (rl < cnt) {
+						if (n >= base + S)
+							bar_sync(kV3BarEmpty + (int)slot, kBarCount);      // the FIR warp is done with this slot
+						const uint32_t slot32 = ring32 + slot * kSlotBytes;
+						if (isTail)
+							sts64(slot32 + posHalo, tail[rl]);
+						if (rl == cnt - 1 && more) {
+							// last receiver of the pass: fetch the next pass's raw IQ behind the mixing
+							if (p + 1 < Pfull) {
+								#pragma unroll
+								for (int j = 0; j < J; j++)
+									nxt[j] = ldg64p(rawp + G::SF + j * NMT);
 							} else {
-								// the range starts inside the block: mix the halo frames once
-								const unsigned f = p * (unsigned)G::SF - (unsigned)G::HF + ti;
-								float sn, cs;
-								lo3_sincos(((ph0 + f * (uint32_t)step) << 1) + 0x80000000u, lo, sn, cs);
-								tail[rl] = mix(__ldg(src + f), cs, sn);
+								#pragma unroll
+								for (int j = 0; j < J; j++) {
+									const unsigned f = (p + 1) * (unsigned)G::SF + mt + (unsigned)j * NMT;
+									nxt[j] = f < a.F ? ldg64p(src + f) : 0ull;
+								}
 							}
 						}
-					}
-				}
-				havePrefetch = false;
-			}
-			// raw IQ of this unit (registers); frames past the block read as zero
-			const unsigned f0 = p * (unsigned)G::SF + mt;
-			if (havePrefetch) {
-				#pragma unroll
-				for (int j = 0; j < J; j++)
-					raw[j] = rawN[j];
-			} else {
-				#pragma unroll
-				for (int j = 0; j < J; j++) {
-					const unsigned f = f0 + (unsigned)j * NMT;
-					raw[j] = f < a.F ? __ldg(src + f) : make_float2(0.0f, 0.0f);
-				}
-			}
-			const bool lastPass = (p + 1 == P);
-			const bool nextSame = !lastPass && (unit + 1 < u1);
-			// pull the unit four passes ahead into L2 while this one is mixed
-			if (p + 4 < P && ((size_t)(p + 4) * G::SF + (size_t)mt * 16) < a.F)
-				asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(src + (size_t)(p + 4) * G::SF) + (size_t)mt * 128));
-
-			#pragma unroll
-			for (int rl = 0; rl < RB; rl++) {
-				if (rl < cnt) {
-					if (n >= base + S)
-						bar_sync(kV3BarEmpty + (int)slot, kBarCount);      // the FIR warp is done with this slot
-					const uint32_t slot32 = ring32 + slot * kSlotBytes;
-					if (isTail)
-						sts64(slot32 + posHalo, tail[rl]);
-					if (rl == cnt - 1 && nextSame) {
-						// last receiver of the unit: fetch the next unit's raw IQ behind the mixing
+						uint32_t q = qb[rl];
 						#pragma unroll
 						for (int j = 0; j < J; j++) {
-							const unsigned f = f0 + (unsigned)G::SF + (unsigned)j * NMT;
-							rawN[j] = f < a.F ? __ldg(src + f) : make_float2(0.0f, 0.0f);
+							// downconverter.cxx:109-110:  I' = i*cos + q*sin ;  Q' = q*cos - i*sin
+							float sn, cs, ic, qc, is, qs;
+							lo3_sincos(q, lo, sn, cs);
+							f2_unpack(f2_fma(cur[j], f2_pack(cs, cs), nzp), ic, qc);
+							f2_unpack(f2_fma(cur[j], f2_pack(sn, sn), nzp), is, qs);
+							const float2 m = make_float2(__fadd_rn(ic, qs), __fsub_rn(qc, is));
+							sts64(slot32 + posMain[j], m);
+							if (j == J - 1)
+								tail[rl] = m;      // only meaningful (and only used) in the tail threads
+							q += qstep[rl];
 						}
-					}
-					uint32_t q = qb[rl];
-					#pragma unroll
-					for (int j = 0; j < J; j++) {
-						float sn, cs;
-						lo3_sincos(q, lo, sn, cs);
-						const float2 m = mix(raw[j], cs, sn);
-						sts64(slot32 + posMain[j], m);
-						if (j == J - 1)
-							tail[rl] = m;      // only meaningful (and only used) in the tail threads
-						q += qstep[rl];
-					}
-					qb[rl] = q;   // J * qstep = 2 * SF * step further: frame j = 0 of the next pass
-					if (mt == 0) {
-						const unsigned k0 = p * (unsigned)G::GO;
-						const unsigned nout = a.M1 > k0 ? min(a.M1 - k0, (unsigned)G::GO) : 0u;
-						asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
-								:: "r"(desc32 + slot * 16u), "r"(rx[rl]), "r"(k0), "r"(nout), "r"((unsigned)rl) : "memory");
-					}
-					if (lastPass) {
-						// carried state: the last N1-1 mixed frames of [history | block], NCO phase
-						bar_sync(kV3BarMix, NMT);
-						const unsigned fp = a.F - p * (unsigned)G::SF;          // frames of this pass, 1..SF
-						if (mt < (unsigned)(N1 - 1)) {
-							const unsigned vv = (unsigned)G::HF + fp - (unsigned)(N1 - 1) + mt;
-							a.hist_out[(size_t)rx[rl] * (N1 - 1) + mt] = lds64(slot32 + 8u * v3_pos<D1, G::DP>(vv));
-						}
+						qb[rl] = q;   // J * qstep = 2 * SF * step further: frame j = 0 of the next pass
 						if (mt == 0)
-							a.st_out[rx[rl]].phase = phase_at(a.st_in[rx[rl]].phase, a.conf[rx[rl]].step, a.F);
+							asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
+									:: "r"(desc32 + slot * 16u), "r"(rx[rl]), "r"(p), "r"(0u), "r"((unsigned)rl) : "memory");
+						if (lastPass) {
+							// carried state: the last N1-1 mixed frames of [history | block], NCO phase
+							bar_sync(kV3BarMix, NMT);
+							const unsigned fp = a.F - p * (unsigned)G::SF;          // frames of this pass, 1..SF
+							if (mt < (unsigned)(N1 - 1)) {
+								const unsigned vv = (unsigned)G::HF + fp - (unsigned)(N1 - 1) + mt;
+								a.hist_out[(size_t)rx[rl] * (N1 - 1) + mt] = lds64(slot32 + 8u * v3_pos<D1, G::DP>(vv));
+							}
+							if (mt == 0)
+								a.st_out[rx[rl]].phase = phase_at(a.st_in[rx[rl]].phase, a.conf[rx[rl]].step, a.F);
+						}
+						bar_arrive(kV3BarFull + (int)slot, kBarCount);
+						n++;
+						slot = (slot + 1 == S) ? 0u : slot + 1;
 					}
-					bar_arrive(kV3BarFull + (int)slot, kBarCount);
-					n++;
-					slot = (slot + 1 == S) ? 0u : slot + 1;
 				}
+				rawp += G::SF;
+			};
+
+			unsigned p = p0;
+			for (;;) {
+				do_pass(rawA, rawB, p);
+				if (++p == pend)
+					break;
+				do_pass(rawB, rawA, p);
+				if (++p == pend)
+					break;
 			}
-			havePrefetch = nextSame;
-			p++;
-			newrg = false;
-			if (p == P) {
-				p = 0;
-				rg++;
-				newrg = true;
-			}
+			unit += pend - p0;
 		}
 		// tell every FIR warp to stop, then collect the hand-backs nobody waited for
 		const unsigned N = n;
@@ -435,23 +514,28 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 	} else {
 		// ================================== FIR warps ==================================
 		const unsigned fw = (tid - NMT) >> 5, lane = tid & 31;
-		const float2 nz = make_float2(v.negzero, v.negzero);
+		const f2_t nz = f2_pack(v.negzero, v.negzero);
 		for (unsigned n = fw; ; n += C) {
 			const unsigned slot = n % S;
 			bar_sync(kV3BarFull + (int)slot, kBarCount);
-			unsigned r, k0, nout, rl;
-			asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r), "=r"(k0), "=r"(nout), "=r"(rl) : "r"(desc32 + slot * 16u));
+			unsigned r, p, unused, rl;
+			asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r), "=r"(p), "=r"(unused), "=r"(rl) : "r"(desc32 + slot * 16u));
 			if (rl == 0xFFFFFFFFu)
 				break;
+			const unsigned k0 = p * (unsigned)G::GO;
+			const unsigned nout = a.M1 > k0 ? min(a.M1 - k0, (unsigned)G::GO) : 0u;
 			const uint32_t slot32 = ring32 + slot * kSlotBytes;
 			const uint32_t t32 = taps32 + rl * G::kTapsStride;
 			#pragma unroll 1
 			for (int g = 0; g < G::NG; g++) {
 				const unsigned o = (unsigned)g * 32u + lane;
 				if ((unsigned)g * 32u < nout) {     // warp-uniform
-					const float2 acc = fir3<N1, D1, G::DP>(slot32 + 8u * o * (unsigned)G::DP, t32, nz);
-					if (o < nout)
-						a.chan[(size_t)r * a.chan_stride + k0 + o] = acc;
+					const f2_t acc = fir3<N1, D1, G::DP>(slot32 + 8u * o * (unsigned)G::DP, t32, nz);
+					if (o < nout) {
+						float2 y;
+						f2_unpack(acc, y.x, y.y);
+						a.chan[(size_t)r * a.chan_stride + k0 + o] = y;
+					}
 				}
 			}
 			bar_arrive(kV3BarEmpty + (int)slot, kBarCount);
