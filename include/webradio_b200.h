@@ -180,6 +180,11 @@ int wr_bank_kernel_times(wr_bank *b, double *ms2_total, unsigned long long *nblo
 /* --------------------------------------------- strict single-stage blocks ---- */
 /* One kernel per process() call on host buffers: what each reference block does on its own.
  * Used by the DspBlock drop-ins when a chain cannot be fused, and by stage-by-stage parity. */
+/* The FM discriminator's atan2f (reference src/dsp/demodulator.cxx:97 calls the host libm):
+ * host twin of the routine the kernels run (webradio_b200/csrc/wr_atan2f.h, a restatement of
+ * glibc's e_atan2f.c / s_atanf.c).  Exists so that tests can pin it against the installed libm. */
+void wr_atan2f_host(const float *y, const float *x, size_t n, float *out);
+
 typedef struct wr_stage wr_stage;
 
 wr_stage *wr_stage_create(int device);
@@ -194,6 +199,8 @@ int wr_stage_fir_reset(wr_stage *s);
 /* Demodulator::process (reference demodulator.cxx:77-115). prev[2] read and updated. */
 int wr_stage_demod(wr_stage *s, int mode, float *prev, const float *iq_host, unsigned nframes,
 		float *out_host);
+/* Test hook: the device's atan2f over host arrays (one kernel). */
+int wr_stage_atan2f(wr_stage *s, const float *y_host, const float *x_host, unsigned n, float *out_host);
 
 /* ----------------------------------------------------------- spectrum ---- */
 /* SpectrumSink (reference src/io/spectrumsink.cxx:60-142): Hamming window, forward complex

@@ -181,6 +181,14 @@ void wro_fir_destroy(wro_fir *f)
 	free(f);
 }
 
+/* the libm routine reference demodulator.cxx:97 calls, exposed so that tests can pin the
+ * product's restatement of it against the C library installed on the box */
+void wro_libm_atan2f(const float *y, const float *x, size_t n, float *out)
+{
+	for (size_t i = 0; i < n; i++)
+		out[i] = atan2f(y[i], x[i]);
+}
+
 /* reference demodulator.cxx:77-115 */
 int wro_demod(int mode, float *prev, const float *in, size_t nframes, float *out)
 {

@@ -48,6 +48,8 @@ void wro_fir_destroy(wro_fir *f);
 
 /* reference demodulator.cxx:77-115; prev[2] = {prev_i, prev_q} is read and updated */
 int wro_demod(int mode, float *prev, const float *iq, size_t nframes, float *out);
+/* the host libm's atan2f over arrays: what reference demodulator.cxx:97 calls on this box */
+void wro_libm_atan2f(const float *y, const float *x, size_t n, float *out);
 
 /* ---- one whole receiver (reference radio.cxx:62-90 chain) ---- */
 typedef struct wro_rx wro_rx;

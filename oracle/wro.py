@@ -46,6 +46,8 @@ def lib():
         L.wro_fir_process.argtypes = [C.c_void_p, _fp, C.c_size_t, _fp]
         L.wro_fir_destroy.argtypes = [C.c_void_p]
         L.wro_demod.argtypes = [C.c_int, _fp, _fp, C.c_size_t, _fp]
+        L.wro_libm_atan2f.argtypes = [_fp, _fp, C.c_size_t, _fp]
+        L.wro_libm_atan2f.restype = None
         L.wro_rx_create.restype = C.c_void_p
         L.wro_rx_create.argtypes = [C.c_uint, C.c_int, _fp, C.c_uint, C.c_uint, C.c_int,
                                     _fp, C.c_uint, C.c_uint]
@@ -128,6 +130,16 @@ class Fir:
         if getattr(self, "h", None):
             lib().wro_fir_destroy(self.h)
             self.h = None
+
+
+def libm_atan2f(y, x):
+    """atan2f of the C library installed on this box (what reference demodulator.cxx:97 calls)."""
+    ya, yp = _f(y)
+    xa, xp = _f(x)
+    assert ya.size == xa.size
+    out = np.empty(ya.size, np.float32)
+    lib().wro_libm_atan2f(yp, xp, ya.size, out.ctypes.data_as(_fp))
+    return out
 
 
 def demod(mode, prev, iq):

@@ -43,3 +43,42 @@ def golden_events(g):
     for b, kind, val in g["events"]:
         ev.setdefault(int(b), []).append(("if" if kind == 0 else "mode", int(val)))
     return ev
+
+
+_FM_EXACT = None
+
+
+def fm_exact():
+    """True when the C library's atan2f on this box is the glibc routine the kernels restate
+    (webradio_b200/csrc/wr_atan2f.h; pinned in depth by tests/test_atan2f.py).  The FM parity checks
+    are then bit-exact; on a box with another libm they fall back to the ULP tolerance."""
+    global _FM_EXACT
+    if _FM_EXACT is None:
+        from oracle import wro
+        from webradio_b200 import capi
+        rng = np.random.default_rng(5)
+        y = rng.uniform(-1, 1, 200000).astype(np.float32)
+        x = rng.uniform(-1, 1, 200000).astype(np.float32)
+        _FM_EXACT = bool(np.array_equal(bits(capi.atan2f_host(y, x)), bits(wro.libm_atan2f(y, x))))
+    return _FM_EXACT
+
+
+FM_MAX_ULP = 2          # fallback tolerance on the demodulated sample (foreign libm only)
+FM_AUDIO_TOL = 3e-7     # fallback tolerance on FM audio (foreign libm only)
+
+
+def assert_fm(got, want, what="", audio=False):
+    """FM samples against the reference chain: bit-exact on a glibc box, see fm_exact()."""
+    if fm_exact():
+        assert_biteq(got, want, what)
+        return
+    got = np.asarray(got, np.float32).ravel()
+    want = np.asarray(want, np.float32).ravel()
+    assert got.shape == want.shape, what
+    if got.size == 0:
+        return
+    if audio:
+        assert np.max(np.abs(got - want)) <= FM_AUDIO_TOL, what
+    else:
+        d = ulp_distance(got, want)
+        assert d.max() <= FM_MAX_ULP, f"{what}: FM demod off by {d.max()} ULP"

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 import graphlib as G
-from helpers import assert_biteq, ulp_distance
+from helpers import assert_biteq, assert_fm
 from webradio_b200 import synth
 
 pytestmark = [pytest.mark.gpu,
@@ -24,7 +24,7 @@ FS, F = 2400000, 20000
 
 def compare_audio(mode, got, want, what):
     if mode == "FM":
-        assert np.max(np.abs(got - want)) <= 3e-7, what
+        assert_fm(got, want, what, audio=True)
     else:
         assert_biteq(got, want, what)
 
@@ -66,7 +66,7 @@ def test_strict_stage_blocks_match_reference():
                 assert_biteq(g.get(i, "mixed"), r.get(i, "mixed"), f"strict rx{i} mixed b{b}")
                 assert_biteq(g.get(i, "channel"), r.get(i, "channel"), f"strict rx{i} channel b{b}")
                 if m == "FM":
-                    assert ulp_distance(g.get(i, "demod"), r.get(i, "demod")).max() <= 2
+                    assert_fm(g.get(i, "demod"), r.get(i, "demod"), f"strict rx{i} demod b{b}")
                 else:
                     assert_biteq(g.get(i, "demod"), r.get(i, "demod"), f"strict rx{i} demod b{b}")
                 compare_audio(m, g.get(i, "audio"), r.get(i, "audio"), f"strict rx{i} audio b{b}")

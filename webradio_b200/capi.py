@@ -22,7 +22,7 @@ _fp = C.POINTER(C.c_float)
 # every symbol include/webradio_b200.h declares (tests/test_abi.py checks the export list)
 SYMBOLS = [
     "wr_version", "wr_last_error", "wr_device_count", "wr_phase_step", "wr_build_sintable",
-    "wr_lowpass_design", "wr_lo_compress_check", "wr_lo3_compress_check",
+    "wr_lowpass_design", "wr_lo_compress_check", "wr_lo3_compress_check", "wr_atan2f_host",
     "wr_bank_create", "wr_bank_destroy", "wr_bank_set_sintable", "wr_rx_set_stream",
     "wr_rx_set_phase_step", "wr_rx_set_taps", "wr_rx_set_mode", "wr_rx_reset", "wr_rx_set_phase", "wr_rx_get_phase",
     "wr_bank_process", "wr_bank_process_device", "wr_bank_submit", "wr_bank_wait",
@@ -30,7 +30,7 @@ SYMBOLS = [
     "wr_bank_read_stage", "wr_bank_set_variant", "wr_bank_variant_in_use", "wr_bank_launch_count", "wr_bank_set_timing",
     "wr_bank_kernel_times",
     "wr_stage_create", "wr_stage_destroy", "wr_stage_mix", "wr_stage_fir_config", "wr_stage_fir",
-    "wr_stage_fir_reset", "wr_stage_demod",
+    "wr_stage_fir_reset", "wr_stage_demod", "wr_stage_atan2f",
     "wr_spectrum_create", "wr_spectrum_destroy", "wr_spectrum_process", "wr_spectrum_process_device",
     "wr_spectrum_get", "wr_spectrum_launch_count", "wr_spectrum_sync",
 ]
@@ -98,6 +98,9 @@ def lib():
     L.wr_stage_fir.argtypes = [vp, _fp, u, u, _fp]
     L.wr_stage_fir_reset.argtypes = [vp]
     L.wr_stage_demod.argtypes = [vp, i, _fp, _fp, u, _fp]
+    L.wr_stage_atan2f.argtypes = [vp, _fp, _fp, u, _fp]
+    L.wr_atan2f_host.argtypes = [_fp, _fp, sz, _fp]
+    L.wr_atan2f_host.restype = None
     L.wr_spectrum_create.restype = vp
     L.wr_spectrum_create.argtypes = [i, u, u, u, u]
     L.wr_spectrum_destroy.argtypes = [vp]
@@ -324,6 +327,24 @@ class Stage:
         _check(self.L.wr_stage_demod(self.h, MODES.get(mode, mode), prev.ctypes.data_as(_fp), ap, a.size // 2,
                                      out.ctypes.data_as(_fp)), "wr_stage_demod")
         return out[:a.size // 2]
+
+    def atan2f(self, y, x):
+        ya, yp = _f32(y)
+        xa, xp = _f32(x)
+        assert ya.size == xa.size
+        out = np.empty(max(1, ya.size), np.float32)
+        _check(self.L.wr_stage_atan2f(self.h, yp, xp, ya.size, out.ctypes.data_as(_fp)), "wr_stage_atan2f")
+        return out[:ya.size]
+
+
+def atan2f_host(y, x):
+    """Host twin of the kernels' atan2f (restatement of glibc's, webradio_b200/csrc/wr_atan2f.h)."""
+    ya, yp = _f32(y)
+    xa, xp = _f32(x)
+    assert ya.size == xa.size
+    out = np.empty(ya.size, np.float32)
+    lib().wr_atan2f_host(yp, xp, ya.size, out.ctypes.data_as(_fp))
+    return out
 
 
 class Spectrum:

@@ -286,7 +286,17 @@ int launch_block(wr_bank *b, const float *iq_dev, size_t stream_stride, unsigned
 		size_t lmax = (size_t)da.TK * b->d2 + b->n2 - 1;
 		size_t smem = sizeof(float) * (((lmax + 3) & ~(size_t)3) + b->n2);
 		dim3 grid(da.ntiles + 1, b->R);
-		wrd::demod_audio_kernel_v2<kThreadsV1><<<grid, kThreadsV1, smem, st>>>(da);
+		cudaLaunchConfig_t cfg = {};
+		cudaLaunchAttribute attr[1];
+		cfg.gridDim = grid;
+		cfg.blockDim = dim3(kThreadsV1);
+		cfg.dynamicSmemBytes = smem;
+		cfg.stream = st;
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = attr;
+		cfg.numAttrs = (useV3 && b->v3.pdl) ? 1 : 0;   // the v3 channel kernel releases its dependents early
+		WR_CUDA(cudaLaunchKernelEx(&cfg, wrd::demod_audio_kernel_v2<kThreadsV1>, (const wrd::DemodAudioArgs)da));
 		b->launches++;
 	} else {
 		wrd::AudioArgs aa;

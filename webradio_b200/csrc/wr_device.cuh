@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "wr_atan2f.h"
+
 namespace wrd {
 
 constexpr uint32_t kPhaseMask = 0x7FFFFFFFu;   // PHASE_BITS = 31 (reference downconverter.cxx:35)
@@ -57,13 +59,13 @@ __device__ __forceinline__ void tap1(float &acc, float c, float x)
 	acc = __fadd_rn(acc, __fmul_rn(c, x));
 }
 
-// Correctly rounded single-precision atan2 via the double routine.  The reference calls
-// glibc's atan2f (demodulator.cxx:97), which is within 1 ULP of this value (it equals it for
-// ~84% of arguments); no device routine can be bit-identical to an unspecified
-// host libm, so FM parity is "<= 1 ULP on the angle", stated in tests/test_parity_gpu.py.
-__device__ __forceinline__ float atan2f_cr(float y, float x)
+// The reference calls the host libm's atan2f (demodulator.cxx:97).  wr_atan2f.h restates the
+// glibc routine operation for operation (same constants, same rounding order), so the FM
+// discriminator is bit-identical to the reference on a glibc box; tests/test_atan2f.py pins the
+// restatement against the installed libm.
+__device__ __forceinline__ float atan2f_ref(float y, float x)
 {
-	return (float)atan2((double)y, (double)x);
+	return wrat::atan2f_glibc(y, x);
 }
 
 // reference demodulator.cxx:83-112.  prev is the previous channel-rate sample.
@@ -79,8 +81,9 @@ __device__ __forceinline__ float demod(int mode, float2 cur, float2 prev)
 		//   (float)((double)atan2f(ii, qq) / M_PI / 2.0)
 		float ii = __fadd_rn(__fmul_rn(cur.x, prev.x), __fmul_rn(cur.y, prev.y));
 		float qq = __fsub_rn(__fmul_rn(cur.y, prev.x), __fmul_rn(cur.x, prev.y));
-		double a = (double)atan2f_cr(ii, qq);
-		return (float)(__ddiv_rn(__ddiv_rn(a, 3.14159265358979323846), 2.0));
+		const double a = (double)atan2f_ref(ii, qq);
+		// x / 2.0 == x * 0.5 exactly (a power of two, no double underflow in this range)
+		return (float)__dmul_rn(__ddiv_rn(a, 3.14159265358979323846), 0.5);
 	}
 	case WR_MODE_USB:
 		return __fadd_rn(cur.x, cur.y);

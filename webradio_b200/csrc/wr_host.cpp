@@ -4,6 +4,7 @@
 #include "wr_common.h"
 #include "wr_lo.h"
 #include "wr_lo3.h"
+#include "wr_atan2f.h"
 
 #include <cmath>
 #include <cstdlib>
@@ -169,6 +170,12 @@ extern "C" {
 const char *wr_version(void) { return "webradio_b200 0.1 (sm_100a)"; }
 
 const char *wr_last_error(void) { return wr::get_error(); }
+
+void wr_atan2f_host(const float *y, const float *x, size_t n, float *out)
+{
+	for (size_t i = 0; i < n; i++)
+		out[i] = wrat::atan2f_glibc(y[i], x[i]);
+}
 
 int wr_device_count(void)
 {

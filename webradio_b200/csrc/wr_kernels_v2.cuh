@@ -405,6 +405,11 @@ __global__ void __launch_bounds__(kThreads) demod_audio_kernel_v2(const DemodAud
 	extern __shared__ float4 wr_smem_da[];
 	const unsigned r = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
 	const unsigned n2 = a.n2, d2 = a.d2;
+	// Programmatic dependent launch, both ways: this grid may have been launched while the channel
+	// kernel that feeds it was still running (wait for it), and the next block's channel kernel may
+	// start its prologue now.  Both are no-ops for a plain launch.
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 	const RxConf cf = a.conf[r];
 	const RxState st = a.st_in[r];
 	const float2 prev0 = make_float2(st.prev_i, st.prev_q);

@@ -46,10 +46,7 @@ constexpr int kV3Threads = kV3Mixers + 32 * kV3Fir;
 constexpr unsigned kV3TableBytes = (((unsigned)(WR_LO3_SLOT_MAX - WR_LO3_SLOT_MIN + 1) * 2u) + 15u) & ~15u;
 constexpr unsigned kV3MidOffset = (unsigned)(-(WR_LO3_SLOT_MIN)) * 2u;   // byte offset of slot 0
 
-// named barriers (0 is __syncthreads): full 1..S, empty S+1..2S, mixers-only 2S+1
-constexpr int kV3BarFull = 1;
-constexpr int kV3BarEmpty = 1 + kV3Slots;
-constexpr int kV3BarMix = 1 + 2 * kV3Slots;
+constexpr int kV3BarMix = 1;   // named barrier of the mixer warps (0 is __syncthreads)
 
 constexpr int v3_pad_period(int d)
 {
@@ -128,6 +125,29 @@ __device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b)
 	return r;
 }
 
+// ---- mbarrier hand-over ---------------------------------------------------------------------
+// Slots change hands through mbarriers rather than named barriers: a named barrier makes every
+// mixer warp wait for the slowest one at each slot, an mbarrier lets each warp run up to a ring
+// ahead of the others (a phase completes when all expected arrivals are in; waiting does not
+// arrive).  Arrive is a release, a successful wait an acquire (PTX defaults, CTA scope).
+__device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity)
+{
+	asm volatile("{\n\t.reg .pred p;\n"
+			"WR_MBAR_WAIT%=:\n\t"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+			"@!p bra WR_MBAR_WAIT%=;\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+
 // Packed constants of the table reconstruction, built once per thread.
 struct Lo3Regs {
 	f2_t tscale, tbias, slotk, slotm, neg1, one, eps, c0, c1, c2, c3;
@@ -182,6 +202,65 @@ __device__ __forceinline__ void lo3_sincos(uint32_t qb, const Lo3Regs &k, float 
 	asm("ld.shared.s16 %0, [%1];" : "=r"(dc) : "r"(k.cbase + 2u * __float_as_uint(slc)));
 	sn = __int_as_float(__float_as_int(bs) + ds);
 	cs = __int_as_float(__float_as_int(bc) + dc);
+}
+
+// The same for J independent phases, written stage by stage across the J frames so that the
+// instruction stream offers J independent dependency chains to the scheduler (a mixer SMSP holds
+// only three or four warps; per-frame code interleaves two chains at best).
+template <int J>
+__device__ __forceinline__ void lo3_sincos_n(const uint32_t (&qb)[J], const Lo3Regs &k, float (&sn)[J], float (&cs)[J])
+{
+	f2_t F[J], T[J], Y[J], W[J], P[J];
+	uint32_t as[J], ac[J];
+	int ds[J], dc[J];
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		uint32_t fs, fc;
+		const uint32_t qc = qb[j] + 0x40000000u;      // + a quarter turn
+		asm("prmt.b32 %0, %1, %2, 0x5432;" : "=r"(fs) : "r"(qb[j]), "r"(k.hi));
+		asm("prmt.b32 %0, %1, %2, 0x5432;" : "=r"(fc) : "r"(qc), "r"(k.hi));
+		F[j] = f2_pack(__uint_as_float(fs), __uint_as_float(fc));
+	}
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		float sls, slc;
+		f2_unpack(f2_fma(F[j], k.slotk, k.slotm), sls, slc);
+		as[j] = k.cbase + 2u * __float_as_uint(sls);
+		ac[j] = k.cbase + 2u * __float_as_uint(slc);
+	}
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		asm volatile("ld.shared.s16 %0, [%1];" : "=r"(ds[j]) : "r"(as[j]));
+		asm volatile("ld.shared.s16 %0, [%1];" : "=r"(dc[j]) : "r"(ac[j]));
+	}
+	#pragma unroll
+	for (int j = 0; j < J; j++)
+		T[j] = f2_fma(F[j], k.tscale, k.tbias);
+	#pragma unroll
+	for (int j = 0; j < J; j++)
+		Y[j] = f2_mul(T[j], T[j]);
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		W[j] = f2_fma(Y[j], k.neg1, k.one);
+		P[j] = f2_fma(Y[j], k.c3, k.c2);
+	}
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		W[j] = f2_add(W[j], k.eps);
+		P[j] = f2_fma(Y[j], P[j], k.c1);
+	}
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		W[j] = f2_mul(T[j], W[j]);
+		P[j] = f2_fma(Y[j], P[j], k.c0);
+	}
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		float bs, bc;
+		f2_unpack(f2_mul(W[j], P[j]), bs, bc);
+		sn[j] = __int_as_float(__float_as_int(bs) + ds[j]);
+		cs[j] = __int_as_float(__float_as_int(bc) + dc[j]);
+	}
 }
 
 __device__ __forceinline__ void sts64(uint32_t addr, float2 v)
@@ -291,17 +370,23 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 	using G = V3Geo<N1, D1>;
 	constexpr int NMT = kV3Mixers, J = G::J, S = kV3Slots, C = kV3Fir;
 	constexpr unsigned kSlotBytes = (unsigned)G::SLOT * 8u;
-	constexpr unsigned kBarCount = NMT + 32;
 	extern __shared__ __align__(16) unsigned char wr_smem_v3[];
 	const unsigned tid = threadIdx.x;
+	// let the demodulator kernel behind this one be scheduled as SMs drain (it waits for this grid)
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
 	// Stage the correction table once per CTA: one thread issues bulk copies (TMA, no tensor map
 	// needed for a contiguous range) that complete on an mbarrier, so the 132 KiB transfer runs
 	// behind the first group's set-up and raw loads instead of in front of them.
-	__shared__ __align__(8) unsigned long long wr_table_bar;
-	const uint32_t bar32 = (uint32_t)__cvta_generic_to_shared(&wr_table_bar);
+	__shared__ __align__(8) unsigned long long wr_bars[1 + 2 * S];   // table | full[S] | empty[S]
+	const uint32_t bar32 = (uint32_t)__cvta_generic_to_shared(wr_bars);
+	const uint32_t full32 = bar32 + 8u, empty32 = bar32 + 8u + 8u * S;
 	if (tid == 0) {
-		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar32) : "memory");
+		mbar_init(bar32, 1);
+		for (int i = 0; i < S; i++) {
+			mbar_init(full32 + 8u * i, NMT / 32);    // one arrival per mixer warp
+			mbar_init(empty32 + 8u * i, 1);          // one arrival by the slot's FIR warp
+		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
@@ -354,17 +439,19 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 			qb[rl] = 0; qstep[rl] = 0; rx[rl] = 0;
 		}
 
-		unsigned n = 0, base = 0, slot = 0;
+		const bool lane0 = (mt & 31) == 0;
+		unsigned n = 0, slot = 0;    // slot uses so far; n = kuse * S + slot
+		unsigned kuse = 0;           // how many times the ring has wrapped
 		unsigned unit = u0;
 		bool tableReady = false;
 		while (unit < u1) {
 			// ---- a run of consecutive passes [p0, pend) of one receiver group ----
 			const unsigned rg = unit / P, p0 = unit - rg * P;
 			const unsigned pend = min(P, p0 + (u1 - unit));
-			// the FIR warps may still read the previous group's taps: drain the ring
-			for (unsigned m = (n > base + S ? n - S : base); m < n; m++)
-				bar_sync(kV3BarEmpty + (int)(m % S), kBarCount);
-			base = n;
+			// the FIR warps may still read the previous group's taps: wait until every slot filled so
+			// far has been handed back (all mixer warps had arrived on it, so nobody is behind)
+			for (unsigned m = (n > S ? n - S : 0u); m < n; m++)
+				mbar_wait(empty32 + 8u * (m % S), (m / S) & 1u);
 			const int4 grp = __ldg(v.groups + rg);
 			const int cnt = grp.y;
 			const float2 *__restrict__ src = a.iq + (size_t)(unsigned)grp.z * a.stream_stride;
@@ -398,12 +485,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 			}
 			if (!tableReady) {
 				// first use of the NCO table: the bulk copies must have landed
-				uint32_t done;
-				do {
-					asm volatile("{\n\t.reg .pred p;\n\t"
-							"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
-							"selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar32) : "memory");
-				} while (!done);
+				mbar_wait(bar32, 0);
 				tableReady = true;
 			}
 			if (isTail && p0 != 0) {
@@ -430,8 +512,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 				#pragma unroll
 				for (int rl = 0; rl < RB; rl++) {
 					if (rl < cnt) {
-						if (n >= base + S)
-							bar_sync(kV3BarEmpty + (int)slot, kBarCount);      // the FIR warp is done with this slot
+						if (kuse)
+							mbar_wait(empty32 + 8u * slot, (kuse - 1u) & 1u);  // the FIR warp is done with this slot
 						const uint32_t slot32 = ring32 + slot * kSlotBytes;
 						if (isTail)
 							sts64(slot32 + posHalo, tail[rl]);
@@ -449,21 +531,24 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 								}
 							}
 						}
-						uint32_t q = qb[rl];
+						uint32_t q[J];
+						float sn[J], cs[J];
+						#pragma unroll
+						for (int j = 0; j < J; j++)
+							q[j] = qb[rl] + (uint32_t)j * qstep[rl];
+						lo3_sincos_n<J>(q, lo, sn, cs);
 						#pragma unroll
 						for (int j = 0; j < J; j++) {
 							// downconverter.cxx:109-110:  I' = i*cos + q*sin ;  Q' = q*cos - i*sin
-							float sn, cs, ic, qc, is, qs;
-							lo3_sincos(q, lo, sn, cs);
-							f2_unpack(f2_fma(cur[j], f2_pack(cs, cs), nzp), ic, qc);
-							f2_unpack(f2_fma(cur[j], f2_pack(sn, sn), nzp), is, qs);
+							float ic, qc, is, qs;
+							f2_unpack(f2_fma(cur[j], f2_pack(cs[j], cs[j]), nzp), ic, qc);
+							f2_unpack(f2_fma(cur[j], f2_pack(sn[j], sn[j]), nzp), is, qs);
 							const float2 m = make_float2(__fadd_rn(ic, qs), __fsub_rn(qc, is));
 							sts64(slot32 + posMain[j], m);
 							if (j == J - 1)
 								tail[rl] = m;      // only meaningful (and only used) in the tail threads
-							q += qstep[rl];
 						}
-						qb[rl] = q;   // J * qstep = 2 * SF * step further: frame j = 0 of the next pass
+						qb[rl] += (uint32_t)J * qstep[rl];   // 2 * SF * step further: frame j = 0 of the next pass
 						if (mt == 0)
 							asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
 									:: "r"(desc32 + slot * 16u), "r"(rx[rl]), "r"(p), "r"(0u), "r"((unsigned)rl) : "memory");
@@ -478,9 +563,14 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 							if (mt == 0)
 								a.st_out[rx[rl]].phase = phase_at(a.st_in[rx[rl]].phase, a.conf[rx[rl]].step, a.F);
 						}
-						bar_arrive(kV3BarFull + (int)slot, kBarCount);
+						__syncwarp();
+						if (lane0)
+							mbar_arrive(full32 + 8u * slot);
 						n++;
-						slot = (slot + 1 == S) ? 0u : slot + 1;
+						if (++slot == S) {
+							slot = 0;
+							kuse++;
+						}
 					}
 				}
 				rawp += G::SF;
@@ -497,27 +587,32 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 			}
 			unit += pend - p0;
 		}
-		// tell every FIR warp to stop, then collect the hand-backs nobody waited for
-		const unsigned N = n;
+		// tell every FIR warp to stop
 		for (int i = 0; i < C; i++) {
-			if (n >= base + S)
-				bar_sync(kV3BarEmpty + (int)slot, kBarCount);
+			if (kuse)
+				mbar_wait(empty32 + 8u * slot, (kuse - 1u) & 1u);
 			if (mt == 0)
 				asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
 						:: "r"(desc32 + slot * 16u), "r"(0u), "r"(0u), "r"(0u), "r"(0xFFFFFFFFu) : "memory");
-			bar_arrive(kV3BarFull + (int)slot, kBarCount);
+			__syncwarp();
+			if (lane0)
+				mbar_arrive(full32 + 8u * slot);
 			n++;
-			slot = (slot + 1 == S) ? 0u : slot + 1;
+			if (++slot == S) {
+				slot = 0;
+				kuse++;
+			}
 		}
-		for (unsigned m = (n > base + S ? n - S : base); m < N; m++)
-			bar_sync(kV3BarEmpty + (int)(m % S), kBarCount);
 	} else {
 		// ================================== FIR warps ==================================
 		const unsigned fw = (tid - NMT) >> 5, lane = tid & 31;
 		const f2_t nz = f2_pack(v.negzero, v.negzero);
-		for (unsigned n = fw; ; n += C) {
-			const unsigned slot = n % S;
-			bar_sync(kV3BarFull + (int)slot, kBarCount);
+		static_assert(C == S, "FIR warp w owns slot w");
+		const unsigned slot = fw;
+		// the demodulator of the previous block may still be reading the channel-rate buffer
+		asm volatile("griddepcontrol.wait;" ::: "memory");
+		for (unsigned kuse = 0; ; kuse++) {
+			mbar_wait(full32 + 8u * slot, kuse & 1u);
 			unsigned r, p, unused, rl;
 			asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r), "=r"(p), "=r"(unused), "=r"(rl) : "r"(desc32 + slot * 16u));
 			if (rl == 0xFFFFFFFFu)
@@ -538,7 +633,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 					}
 				}
 			}
-			bar_arrive(kV3BarEmpty + (int)slot, kBarCount);
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(empty32 + 8u * slot);
 		}
 	}
 }
@@ -561,6 +658,7 @@ struct V3Plan {
 	int4 *d_groups = nullptr;
 	unsigned nGroups = 0;
 	unsigned capR = 0;
+	bool pdl = true;          // WR_V3_PDL=0 turns programmatic dependent launch off
 };
 
 template <int N1, int D1, int RB>
@@ -593,6 +691,8 @@ inline int v3_init(V3Plan &p, int device, unsigned n1, unsigned d1)
 	p.d1 = d1;
 	p.ok = false;
 	p.kernel = nullptr;
+	if (const char *e = getenv("WR_V3_PDL"))
+		p.pdl = atoi(e) != 0;
 	if (n1 == 64 && d1 == 10) v3_fill<64, 10, 4>(p);
 	else if (n1 == 127 && d1 == 50) v3_fill<127, 50, 4>(p);
 	else if (n1 == 255 && d1 == 50) v3_fill<255, 50, 2>(p);
@@ -676,9 +776,24 @@ inline int v3_launch_chan(V3Plan &p, ChanArgs &ca, cudaStream_t st, unsigned lon
 	v.prmtHi = 0x4B00u;
 	const unsigned long long units = (unsigned long long)v.nGroups * v.P;
 	const unsigned grid = (unsigned)std::min<unsigned long long>(units, (unsigned long long)p.numSMs);
-	p.kernel<<<grid, kV3Threads, p.smemBytes, st>>>(ca, v);
+	// Programmatic dependent launch: this grid may start while the previous kernel in the stream
+	// (the demodulator of the block before) is still draining; everything up to the first store
+	// of channel-rate IQ -- table staging, group set-up, mixing -- is independent of it, and the
+	// FIR warps execute griddepcontrol.wait before that store.
+	cudaLaunchConfig_t cfg = {};
+	cudaLaunchAttribute attr[1];
+	cfg.gridDim = dim3(grid);
+	cfg.blockDim = dim3(kV3Threads);
+	cfg.dynamicSmemBytes = p.smemBytes;
+	cfg.stream = st;
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = p.pdl ? 1 : 0;
+	cudaError_t e = cudaLaunchKernelEx(&cfg, p.kernel, (const ChanArgs)ca, (const V3Args)v);
 	(*launches)++;
-	const cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess)
+		e = cudaGetLastError();
 	if (e != cudaSuccess) {
 		wr::set_error("chan_kernel_v3 launch (grid %u, %d threads, %zu bytes of shared memory): %s",
 				grid, kV3Threads, p.smemBytes, cudaGetErrorString(e));

@@ -55,6 +55,13 @@ __global__ void stage_demod_kernel(const float2 *__restrict__ in, float *__restr
 		out[k] = wrd::demod(mode, in[k], k ? in[k - 1] : prev0);
 }
 
+// test hook: the device's atan2f (wr_atan2f.h) over arrays
+__global__ void stage_atan2f_kernel(const float *__restrict__ y, const float *__restrict__ x, float *__restrict__ out, unsigned n)
+{
+	for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+		out[k] = wrd::atan2f_ref(y[k], x[k]);
+}
+
 } // namespace
 
 struct wr_stage {
@@ -279,6 +286,27 @@ int wr_stage_demod(wr_stage *s, int mode, float *prev, const float *iq_host, uns
 	WR_CUDA(cudaStreamSynchronize(s->st));
 	prev[0] = iq_host[2 * (size_t)(nframes - 1)];     // demodulator.cxx:110-111
 	prev[1] = iq_host[2 * (size_t)(nframes - 1) + 1];
+	return WR_OK;
+}
+
+int wr_stage_atan2f(wr_stage *s, const float *y_host, const float *x_host, unsigned n, float *out_host)
+{
+	WR_REQUIRE(s, WR_EINVAL, "wr_stage_atan2f: null stage");
+	if (n == 0)
+		return WR_OK;
+	WR_REQUIRE(y_host && x_host && out_host, WR_EINVAL, "wr_stage_atan2f: null buffer");
+	if (!wr::use_device(s->device))
+		return WR_ENODEV;
+	int rc;
+	if ((rc = grow(&s->d_in, &s->capIn, 2 * (size_t)n)) != WR_OK) return rc;
+	if ((rc = grow(&s->d_out, &s->capOut, (size_t)n)) != WR_OK) return rc;
+	WR_CUDA(cudaMemcpyAsync(s->d_in, y_host, sizeof(float) * n, cudaMemcpyHostToDevice, s->st));
+	WR_CUDA(cudaMemcpyAsync(s->d_in + n, x_host, sizeof(float) * n, cudaMemcpyHostToDevice, s->st));
+	stage_atan2f_kernel<<<grid_for(n, 256), 256, 0, s->st>>>(s->d_in, s->d_in + n, s->d_out, n);
+	s->launches++;
+	WR_CUDA(cudaGetLastError());
+	WR_CUDA(cudaMemcpyAsync(out_host, s->d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, s->st));
+	WR_CUDA(cudaStreamSynchronize(s->st));
 	return WR_OK;
 }
 
