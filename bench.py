@@ -42,6 +42,9 @@ def parse_args():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--workload", default="cfg2", choices=sorted(synth.WORKLOADS) + ["cfg4"])
     p.add_argument("--variant", type=int, default=0, help="kernel family: 0 auto, 1 v1, 2 v2, 3 v3")
+    p.add_argument("--input", default="f32", choices=["f32", "u8"],
+                   help="tuner block format: interleaved float IQ (the DspBlock convention) or raw RTL-SDR bytes "
+                        "converted inside the channel kernel's load (SURVEY.md 8f-1)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU baseline sample")
     return p.parse_args()
@@ -64,17 +67,18 @@ def workload_taps(w):
     return t1, t2
 
 
-def algorithmic_bytes(w):
-    """B_alg = 8*F*T + 4*R*F/(D1*D2) per block (T = unique input streams)."""
+def algorithmic_bytes(w, frame_bytes=8):
+    """B_alg = 8*F*T + 4*R*F/(D1*D2) per block (T = unique input streams); 2 bytes per
+    frame instead of 8 when the tuner block arrives as raw RTL-SDR bytes."""
     F, T, R = w["frames"], w["n_streams"], w["n_rx"]
-    return 8 * F * T + 4 * R * (F // w["d1"] // w["d2"])
+    return frame_bytes * F * T + 4 * R * (F // w["d1"] // w["d2"])
 
 
-def chan_kernel_bytes(w, variant):
+def chan_kernel_bytes(w, variant, frame_bytes=8):
     """The dominant kernel alone: reads the tuner block(s) once and writes, per channel-rate
-    sample per receiver, the demodulated float (v1: demod fused in) or the IQ pair (v2)."""
+    sample per receiver, the demodulated float (v1: demod fused in) or the IQ pair (v2, v3)."""
     F, T, R = w["frames"], w["n_streams"], w["n_rx"]
-    return 8 * F * T + (8 if variant >= 2 else 4) * R * (F // w["d1"])
+    return frame_bytes * F * T + (8 if variant >= 2 else 4) * R * (F // w["d1"])
 
 
 # ------------------------------------------------------------------ clocks ----
@@ -242,8 +246,10 @@ def reference_arm(args, w, wname):
     print(json.dumps(line), flush=True)
 
 
-def bench_config(w, wname, l2_note):
-    c = {"workload": f"{wname}: {w['desc']}", "sample_rate": w["fs"], "frames_per_step": w["frames"],
+def bench_config(w, wname, l2_note, input_format="f32"):
+    c = {"workload": f"{wname}: {w['desc']}", "input": "interleaved float IQ" if input_format == "f32" else
+         "raw RTL-SDR bytes (u8 IQ, converted in the channel kernel's load)",
+         "sample_rate": w["fs"], "frames_per_step": w["frames"],
          "n_receivers": w["n_rx"], "n_streams": w["n_streams"], "channel_fir": [w["n1"], w["d1"]],
          "audio_fir": [w["n2"], w["d2"]], "modes": w["modes"], "parallelism": "receivers sharded by tuner, no collective"}
     if l2_note:
@@ -288,7 +294,9 @@ def gpu_arm(args, w, wname):
 
     # synthetic tuner blocks on the RTL-SDR sample lattice (b-128)/128, generated in HBM; a
     # rotating set larger than L2 so that no step finds its input cached
-    block_bytes = 8 * F * T
+    u8 = args.input == "u8"
+    frame_bytes = 2 if u8 else 8
+    block_bytes = frame_bytes * F * T
     nbuf = max(2, -(-int(1.25 * L2_BYTES) // block_bytes))
     nbuf = min(nbuf, max(2, steps + warmup))
     # weak scaling: this rank owns its own copy of the workload's tuners and receivers
@@ -297,8 +305,9 @@ def gpu_arm(args, w, wname):
     gen.manual_seed(0xB200 + mine.tuners[0])
     inputs = []
     for _ in range(nbuf):
-        u8 = torch.randint(0, 256, (T, F, 2), generator=gen, device="cuda", dtype=torch.int32)
-        inputs.append(((u8.float() - 128.0) / 128.0).contiguous())
+        raw = torch.randint(0, 256, (T, F, 2), generator=gen, device="cuda", dtype=torch.int32)
+        inputs.append(raw.to(torch.uint8).contiguous() if u8 else ((raw.float() - 128.0) / 128.0).contiguous())
+        del raw
     audio = [torch.zeros(R, max(M2, 1), device="cuda") for _ in range(min(nbuf, 8))]
     l2_note = f"rotating set of {nbuf} distinct input blocks ({nbuf * block_bytes / 2**20:.0f} MiB > L2 126 MiB)" \
         if nbuf * block_bytes > L2_BYTES else \
@@ -310,7 +319,7 @@ def gpu_arm(args, w, wname):
 
     def run_steps(first, n):
         # n calls of wr_bank_process_device, looped on the C side of the ABI
-        bank.run_device_steps(in_ptrs, F, F, out_ptrs, max(M2, 1), first, n)
+        bank.run_device_steps(in_ptrs, F, F, out_ptrs, max(M2, 1), first, n, u8=u8)
 
     def barrier():
         torch.cuda.synchronize()
@@ -359,10 +368,10 @@ def gpu_arm(args, w, wname):
     pin_out_ptrs = [y.data_ptr() for y in pin_out]
 
     def e2e_pipelined(n):
-        bank.run_host_steps(pin_in_ptrs, F, pin_out_ptrs, max(M2, 1), 0, n, pipelined=True)
+        bank.run_host_steps(pin_in_ptrs, F, pin_out_ptrs, max(M2, 1), 0, n, pipelined=True, u8=u8)
 
     def e2e_sync(n):
-        bank.run_host_steps(pin_in_ptrs, F, pin_out_ptrs, max(M2, 1), 0, n, pipelined=False)
+        bank.run_host_steps(pin_in_ptrs, F, pin_out_ptrs, max(M2, 1), 0, n, pipelined=False, u8=u8)
 
     e2e_pipelined(min(3, esteps))
     barrier()
@@ -392,12 +401,12 @@ def gpu_arm(args, w, wname):
     else:
         peak, peak_src = HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
     variant_used = bank.variant_in_use()
-    kb = chan_kernel_bytes(w, variant_used)
+    kb = chan_kernel_bytes(w, variant_used, frame_bytes)
     achieved = kb / (chan_ms_avg * 1e-3) / 1e9 if chan_ms_avg > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(wname, {}).get("chan_kernel_dram_bytes_per_launch")
+        traffic = json.load(open(tpath)).get(wname + ("_u8" if u8 else ""), {}).get("chan_kernel_dram_bytes_per_launch")
     roofline = {
         "bound": "hbm",
         "kernel": f"chan_kernel_v{variant_used}: fused NCO mix + channel FIR" if variant_used >= 2 else "chan_kernel_v1: fused NCO mix + channel FIR + demod",
@@ -422,7 +431,7 @@ def gpu_arm(args, w, wname):
             "metric": METRIC, "value": value, "unit": "MSamples/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": bench_config(w, wname, l2_note),
+            "config": bench_config(w, wname, l2_note, args.input),
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "MSamples/s", "h2d_bytes_per_step": block_bytes,
                     "d2h_bytes_per_step": 4 * R * M2, "steps": esteps, "mode": f"pipelined depth {depth}",
@@ -430,7 +439,7 @@ def gpu_arm(args, w, wname):
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "hbm_gbs_algorithmic_whole_step": algorithmic_bytes(w) * steps / (ms * 1e-3) / 1e9,
+            "hbm_gbs_algorithmic_whole_step": algorithmic_bytes(w, frame_bytes) * steps / (ms * 1e-3) / 1e9,
             "tuner_msamples_per_s": world * T * F * steps / (ms * 1e-3) / 1e6,
             "kernel_variant": variant_used,
         }

@@ -150,6 +150,24 @@ int wr_bank_run_device_steps(wr_bank *b, const float *const *iq_dev, unsigned n_
 int wr_bank_run_host_steps(wr_bank *b, const float *const *iq_pinned, unsigned n_iq, unsigned nframes,
 		float *const *audio_pinned, unsigned n_audio, size_t audio_stride,
 		unsigned first, unsigned steps, int pipelined);
+/* Raw RTL-SDR bytes instead of floats: the same five calls with the tuner
+ * block as interleaved unsigned 8-bit I/Q, [n_streams][nframes][2] bytes.  The tuner's sample
+ * conversion ((float)b - 128.0) / 128.0 (reference src/io/rtlsdrtuner.cxx:104-108) runs inside
+ * the channel kernel's load, so a frame costs 2 bytes of PCIe and HBM traffic instead of 8;
+ * results are bit-identical to converting on the host and calling the float entry points.
+ * stream_stride_frames is in FRAMES (2 bytes each). */
+int wr_bank_process_u8(wr_bank *b, const uint8_t *iq_host, unsigned nframes,
+		float *audio_host, size_t audio_stride);
+int wr_bank_process_device_u8(wr_bank *b, const uint8_t *iq_dev, size_t stream_stride_frames,
+		unsigned nframes, float *audio_dev, size_t audio_stride, void *cuda_stream);
+int wr_bank_submit_u8(wr_bank *b, const uint8_t *iq_pinned, unsigned nframes,
+		float *audio_pinned, size_t audio_stride);
+int wr_bank_run_device_steps_u8(wr_bank *b, const uint8_t *const *iq_dev, unsigned n_iq, size_t stream_stride_frames,
+		unsigned nframes, float *const *audio_dev, unsigned n_audio, size_t audio_stride,
+		unsigned first, unsigned steps);
+int wr_bank_run_host_steps_u8(wr_bank *b, const uint8_t *const *iq_pinned, unsigned n_iq, unsigned nframes,
+		float *const *audio_pinned, unsigned n_audio, size_t audio_stride,
+		unsigned first, unsigned steps, int pipelined);
 void *wr_bank_stream(wr_bank *b);   /* cudaStream_t of the bank */
 int wr_bank_sync(wr_bank *b);
 

@@ -372,3 +372,59 @@ def test_spectrum_before_first_frame():
     sp = capi.Spectrum(512)
     assert np.all(np.isneginf(sp.get(0)))  # reference: outbuf is zero before the first transform
     assert sp.process(np.zeros((1, 100, 2), np.float32), rows=False) == 0
+
+
+# ------------------------------------------------------------------ raw RTL-SDR bytes ----
+
+U8_CASES = [
+    # (n1, d1, n2, d2, frames, streams, receivers): v3 geometries (conversion inside the channel kernel's
+    # load, full and partial passes), a block too short for v3 and a geometry only v1/v2 serve (conversion
+    # kernel in front)
+    (127, 50, 64, 1, 20000, 2, 8),
+    (255, 50, 64, 1, 4800, 3, 3),
+    (64, 10, 64, 5, 10240, 1, 4),
+    (64, 10, 64, 5, 1000, 1, 4),
+    (33, 7, 16, 3, 7003, 2, 5),
+]
+
+
+@pytest.mark.parametrize("case", U8_CASES)
+def test_bank_u8_ingest_matches_the_tuner_conversion(wro, case):
+    """Raw bytes through wr_bank_process_u8 == the reference chain fed RtlSdrTuner's floats
+    ((b - 128) / 128, rtlsdrtuner.cxx:106), bit for bit, over 3 blocks (carried state) -- and
+    == the float entry point of a second bank."""
+    n1, d1, n2, d2, F, T, R = case
+    fs = 2400000
+    rng = np.random.default_rng(n1 * 1000 + d1)
+    ifs = synth.receiver_ifs(R, fs)
+    modes = [r % 4 for r in range(R)]
+    taps1 = [(rng.uniform(-1, 1, n1) / n1 * 4).astype(np.float32) for _ in range(R)]
+    taps2 = [(rng.uniform(-1, 1, n2) / n2 * 4).astype(np.float32) for _ in range(R)]
+    banks = [capi.Bank(T, R, F, n1, d1, n2, d2) for _ in range(2)]
+    try:
+        for bank in banks:
+            for r in range(R):
+                bank.set_taps(r, 0, taps1[r])
+                bank.set_taps(r, 1, taps2[r])
+                bank.set_if(r, int(ifs[r]), fs)
+                bank.set_mode(r, modes[r])
+                bank.set_stream(r, r % T)
+        orx = [wro.Rx(fs, int(ifs[r]), taps1[r], d1, modes[r], taps2[r], d2) for r in range(R)]
+        for b in range(3):
+            u8 = rng.integers(0, 256, (T, F, 2), dtype=np.uint8)
+            if b == 1:
+                u8[:, :64] = 0          # the lattice's corners too
+                u8[:, 64:128] = 255
+            iq = u8_to_iq(u8)
+            got = banks[0].process_u8(u8)
+            twin = banks[1].process(iq)
+            assert_biteq(got, twin, f"u8 vs float entry point, block {b}")
+            for r in range(R):
+                want = orx[r].process(iq[r % T].ravel())
+                if modes[r] == capi.FM:
+                    assert_fm(got[r], want, f"u8 rx{r} b{b}", audio=True)
+                else:
+                    assert_biteq(got[r], want, f"u8 rx{r} b{b}")
+    finally:
+        for bank in banks:
+            bank.close()

@@ -26,6 +26,8 @@ SYMBOLS = [
     "wr_bank_create", "wr_bank_destroy", "wr_bank_set_sintable", "wr_rx_set_stream",
     "wr_rx_set_phase_step", "wr_rx_set_taps", "wr_rx_set_mode", "wr_rx_reset", "wr_rx_set_phase", "wr_rx_get_phase",
     "wr_bank_process", "wr_bank_process_device", "wr_bank_submit", "wr_bank_wait",
+    "wr_bank_process_u8", "wr_bank_process_device_u8", "wr_bank_submit_u8",
+    "wr_bank_run_device_steps_u8", "wr_bank_run_host_steps_u8",
     "wr_bank_pipeline_depth", "wr_bank_run_device_steps", "wr_bank_run_host_steps", "wr_bank_stream", "wr_bank_sync", "wr_bank_keep_channel",
     "wr_bank_read_stage", "wr_bank_set_variant", "wr_bank_variant_in_use", "wr_bank_launch_count", "wr_bank_set_timing",
     "wr_bank_kernel_times",
@@ -78,6 +80,11 @@ def lib():
     pp = C.POINTER(C.c_void_p)
     L.wr_bank_run_device_steps.argtypes = [vp, pp, u, sz, u, pp, u, sz, u, u]
     L.wr_bank_run_host_steps.argtypes = [vp, pp, u, u, pp, u, sz, u, u, i]
+    L.wr_bank_process_u8.argtypes = L.wr_bank_process.argtypes
+    L.wr_bank_process_device_u8.argtypes = L.wr_bank_process_device.argtypes
+    L.wr_bank_submit_u8.argtypes = L.wr_bank_submit.argtypes
+    L.wr_bank_run_device_steps_u8.argtypes = L.wr_bank_run_device_steps.argtypes
+    L.wr_bank_run_host_steps_u8.argtypes = L.wr_bank_run_host_steps.argtypes
     L.wr_bank_stream.restype = vp
     L.wr_bank_stream.argtypes = [vp]
     L.wr_bank_sync.argtypes = [vp]
@@ -217,27 +224,42 @@ class Bank:
                "wr_bank_process")
         return out[:, :m2]
 
-    def process_device(self, iq_ptr, stream_stride, nframes, audio_ptr, audio_stride, cuda_stream=None):
-        _check(self.L.wr_bank_process_device(self.h, iq_ptr, stream_stride, nframes, audio_ptr,
-                                             audio_stride, cuda_stream), "wr_bank_process_device")
+    def process_u8(self, iq_u8, nframes=None):
+        """iq_u8: uint8 [n_streams, nframes, 2], raw RTL-SDR bytes (reference rtlsdrtuner.cxx:104-108)."""
+        a = np.ascontiguousarray(iq_u8, dtype=np.uint8)
+        if nframes is None:
+            nframes = a.size // (2 * self.T)
+        assert a.size == 2 * self.T * nframes
+        m2 = self.out_frames(nframes)
+        out = np.zeros((self.R, max(m2, 1)), np.float32)
+        _check(self.L.wr_bank_process_u8(self.h, a.ctypes.data, nframes, out.ctypes.data, out.shape[1]),
+               "wr_bank_process_u8")
+        return out[:, :m2]
 
-    def submit(self, iq_ptr, nframes, audio_ptr, audio_stride):
-        _check(self.L.wr_bank_submit(self.h, iq_ptr, nframes, audio_ptr, audio_stride), "wr_bank_submit")
+    def process_device(self, iq_ptr, stream_stride, nframes, audio_ptr, audio_stride, cuda_stream=None, u8=False):
+        f = self.L.wr_bank_process_device_u8 if u8 else self.L.wr_bank_process_device
+        _check(f(self.h, iq_ptr, stream_stride, nframes, audio_ptr, audio_stride, cuda_stream), "wr_bank_process_device")
+
+    def submit(self, iq_ptr, nframes, audio_ptr, audio_stride, u8=False):
+        f = self.L.wr_bank_submit_u8 if u8 else self.L.wr_bank_submit
+        _check(f(self.h, iq_ptr, nframes, audio_ptr, audio_stride), "wr_bank_submit")
 
     def wait(self):
         _check(self.L.wr_bank_wait(self.h), "wr_bank_wait")
 
-    def run_device_steps(self, iq_ptrs, stride, nframes, audio_ptrs, audio_stride, first, steps):
+    def run_device_steps(self, iq_ptrs, stride, nframes, audio_ptrs, audio_stride, first, steps, u8=False):
         a = (C.c_void_p * len(iq_ptrs))(*iq_ptrs)
         o = (C.c_void_p * len(audio_ptrs))(*audio_ptrs)
-        _check(self.L.wr_bank_run_device_steps(self.h, a, len(iq_ptrs), stride, nframes, o, len(audio_ptrs),
-                                               audio_stride, first, steps), "wr_bank_run_device_steps")
+        f = self.L.wr_bank_run_device_steps_u8 if u8 else self.L.wr_bank_run_device_steps
+        _check(f(self.h, a, len(iq_ptrs), stride, nframes, o, len(audio_ptrs), audio_stride, first, steps),
+               "wr_bank_run_device_steps")
 
-    def run_host_steps(self, iq_ptrs, nframes, audio_ptrs, audio_stride, first, steps, pipelined=True):
+    def run_host_steps(self, iq_ptrs, nframes, audio_ptrs, audio_stride, first, steps, pipelined=True, u8=False):
         a = (C.c_void_p * len(iq_ptrs))(*iq_ptrs)
         o = (C.c_void_p * len(audio_ptrs))(*audio_ptrs)
-        _check(self.L.wr_bank_run_host_steps(self.h, a, len(iq_ptrs), nframes, o, len(audio_ptrs), audio_stride,
-                                             first, steps, int(pipelined)), "wr_bank_run_host_steps")
+        f = self.L.wr_bank_run_host_steps_u8 if u8 else self.L.wr_bank_run_host_steps
+        _check(f(self.h, a, len(iq_ptrs), nframes, o, len(audio_ptrs), audio_stride, first, steps, int(pipelined)),
+               "wr_bank_run_host_steps")
 
     def pipeline_depth(self):
         return self.L.wr_bank_pipeline_depth(self.h)

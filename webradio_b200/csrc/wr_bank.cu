@@ -43,8 +43,19 @@ __global__ void reset_kernel(RxState *st, float2 *hist1, float *demod_hist, unsi
 			demod_hist[(size_t)rx * dstride + i] = 0.0f;
 }
 
+// RtlSdrTuner's sample conversion (reference src/io/rtlsdrtuner.cxx:106) as a kernel of its own:
+// only for geometries the v3 channel kernel (which converts in its load path) does not serve.
+__global__ void u8_to_f32_kernel(const unsigned char *__restrict__ in, float *__restrict__ out,
+		size_t in_stride, size_t out_stride, unsigned nfloats)
+{
+	const unsigned char *src = in + (size_t)blockIdx.y * in_stride;
+	float *dst = out + (size_t)blockIdx.y * out_stride;
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nfloats; i += gridDim.x * blockDim.x)
+		dst[i] = __fdiv_rn(__fsub_rn((float)src[i], 128.0f), 128.0f);
+}
+
 struct Slot {
-	float *d_iq = nullptr;      // [T][maxF][2]
+	float *d_iq = nullptr;      // [T][maxF][2] (float blocks) or the same bytes holding raw u8 blocks
 	float *d_audio = nullptr;   // [R][maxM2]
 	cudaEvent_t in_ready = nullptr, done = nullptr, out_ready = nullptr;
 	bool busy = false;
@@ -67,6 +78,7 @@ struct wr_bank {
 	float2 *d_hist1[2] = { nullptr, nullptr };
 	float *d_demod[2] = { nullptr, nullptr };
 	float2 *d_chan = nullptr;
+	float *d_iqf = nullptr;     // scratch: a u8 tuner block converted for the v1/v2 kernels
 	int cur = 0;
 	unsigned lastM1 = 0, lastM2 = 0;
 	bool keepChan = false;
@@ -191,7 +203,7 @@ unsigned pick_tk_v1(unsigned n1, unsigned d1)
 	return tk;
 }
 
-int launch_block(wr_bank *b, const float *iq_dev, size_t stream_stride, unsigned F,
+int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, unsigned F,
 		float *audio_dev, size_t audio_stride, cudaStream_t st)
 {
 	int rc = apply_pending(b, st);
@@ -221,6 +233,19 @@ int launch_block(wr_bank *b, const float *iq_dev, size_t stream_stride, unsigned
 	}
 	if (useV2 && !b->d_chan)
 		WR_CUDA(cudaMalloc(&b->d_chan, sizeof(float2) * (size_t)b->R * std::max(1u, b->maxM1)));
+	if (u8 && !useV3) {
+		// the older kernel families read float blocks: convert once into a scratch block
+		if (!b->d_iqf)
+			WR_CUDA(cudaMalloc(&b->d_iqf, sizeof(float) * 2 * (size_t)b->T * b->maxF));
+		dim3 grid(std::max(1u, std::min(64u, (2 * F + 1023) / 1024)), b->T);
+		u8_to_f32_kernel<<<grid, 256, 0, st>>>(static_cast<const unsigned char*>(iq_dev), b->d_iqf,
+				2 * stream_stride, 2 * (size_t)b->maxF, 2 * F);
+		b->launches++;
+		WR_CUDA(cudaGetLastError());
+		iq_dev = b->d_iqf;
+		stream_stride = b->maxF;
+		u8 = false;
+	}
 
 	wrd::ChanArgs ca;
 	ca.iq = reinterpret_cast<const float2*>(iq_dev);
@@ -243,7 +268,7 @@ int launch_block(wr_bank *b, const float *iq_dev, size_t stream_stride, unsigned
 	ca.d1 = b->d1;
 
 	if (useV3) {
-		rc = wrd::v3_launch_chan(b->v3, ca, st, &b->launches);
+		rc = wrd::v3_launch_chan(b->v3, ca, u8, st, &b->launches);
 		if (rc != WR_OK)
 			return rc;
 	} else if (useV2) {
@@ -355,6 +380,7 @@ void free_bank(wr_bank *b)
 		cudaFree(b->d_demod[i]);
 	}
 	cudaFree(b->d_chan);
+	cudaFree(b->d_iqf);
 	cudaFreeHost(b->p_conf);
 	cudaFreeHost(b->p_taps1);
 	cudaFreeHost(b->p_taps2);
@@ -545,7 +571,7 @@ int wr_rx_get_phase(wr_bank *b, unsigned rx, uint32_t *phase)
 	return WR_OK;
 }
 
-int wr_bank_process_device(wr_bank *b, const float *iq_dev, size_t stream_stride_frames,
+static int process_device_any(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride_frames,
 		unsigned nframes, float *audio_dev, size_t audio_stride, void *cuda_stream)
 {
 	WR_REQUIRE(b && iq_dev && audio_dev, WR_EINVAL, "wr_bank_process_device: null argument");
@@ -553,10 +579,22 @@ int wr_bank_process_device(wr_bank *b, const float *iq_dev, size_t stream_stride
 	if (!wr::use_device(b->device))
 		return WR_ENODEV;
 	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->compute;
-	return launch_block(b, iq_dev, stream_stride_frames, nframes, audio_dev, audio_stride, st);
+	return launch_block(b, iq_dev, u8, stream_stride_frames, nframes, audio_dev, audio_stride, st);
 }
 
-int wr_bank_submit(wr_bank *b, const float *iq_host, unsigned nframes, float *audio_host, size_t audio_stride)
+int wr_bank_process_device(wr_bank *b, const float *iq_dev, size_t stream_stride_frames,
+		unsigned nframes, float *audio_dev, size_t audio_stride, void *cuda_stream)
+{
+	return process_device_any(b, iq_dev, false, stream_stride_frames, nframes, audio_dev, audio_stride, cuda_stream);
+}
+
+int wr_bank_process_device_u8(wr_bank *b, const uint8_t *iq_dev, size_t stream_stride_frames,
+		unsigned nframes, float *audio_dev, size_t audio_stride, void *cuda_stream)
+{
+	return process_device_any(b, iq_dev, true, stream_stride_frames, nframes, audio_dev, audio_stride, cuda_stream);
+}
+
+static int submit_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframes, float *audio_host, size_t audio_stride)
 {
 	WR_REQUIRE(b && iq_host && audio_host, WR_EINVAL, "wr_bank_submit: null argument");
 	WR_REQUIRE(nframes <= b->maxF, WR_EINVAL, "wr_bank_submit: %u frames > max_frames %u", nframes, b->maxF);
@@ -569,18 +607,18 @@ int wr_bank_submit(wr_bank *b, const float *iq_host, unsigned nframes, float *au
 		WR_CUDA(cudaMalloc(&s.d_audio, sizeof(float) * (size_t)b->R * std::max(1u, b->maxM2)));
 	}
 	const unsigned M2 = nframes / b->d1 / b->d2;
+	const size_t fb = u8 ? 2 : sizeof(float) * 2;   // bytes per frame on the wire and in HBM
 	// H2D: must not overwrite the slot's tuner block before the kernels of its previous use ran
 	if (s.used)
 		WR_CUDA(cudaStreamWaitEvent(b->h2d, s.done, 0));
-	WR_CUDA(cudaMemcpy2DAsync(s.d_iq, sizeof(float) * 2 * (size_t)b->maxF,
-			iq_host, sizeof(float) * 2 * (size_t)nframes,
-			sizeof(float) * 2 * (size_t)nframes, b->T, cudaMemcpyHostToDevice, b->h2d));
+	WR_CUDA(cudaMemcpy2DAsync(s.d_iq, fb * (size_t)b->maxF, iq_host, fb * (size_t)nframes,
+			fb * (size_t)nframes, b->T, cudaMemcpyHostToDevice, b->h2d));
 	WR_CUDA(cudaEventRecord(s.in_ready, b->h2d));
 	// compute: after the copy in, and after the previous read-out of this slot's audio buffer
 	WR_CUDA(cudaStreamWaitEvent(b->compute, s.in_ready, 0));
 	if (s.used)
 		WR_CUDA(cudaStreamWaitEvent(b->compute, s.out_ready, 0));
-	int rc = launch_block(b, s.d_iq, b->maxF, nframes, s.d_audio, std::max(1u, b->maxM2), b->compute);
+	int rc = launch_block(b, s.d_iq, u8, b->maxF, nframes, s.d_audio, std::max(1u, b->maxM2), b->compute);
 	if (rc != WR_OK)
 		return rc;
 	WR_CUDA(cudaEventRecord(s.done, b->compute));
@@ -596,6 +634,16 @@ int wr_bank_submit(wr_bank *b, const float *iq_host, unsigned nframes, float *au
 	b->head = (b->head + 1) % kSlots;
 	b->inflight++;
 	return WR_OK;
+}
+
+int wr_bank_submit(wr_bank *b, const float *iq_host, unsigned nframes, float *audio_host, size_t audio_stride)
+{
+	return submit_any(b, iq_host, false, nframes, audio_host, audio_stride);
+}
+
+int wr_bank_submit_u8(wr_bank *b, const uint8_t *iq_host, unsigned nframes, float *audio_host, size_t audio_stride)
+{
+	return submit_any(b, iq_host, true, nframes, audio_host, audio_stride);
 }
 
 int wr_bank_wait(wr_bank *b)
@@ -614,23 +662,33 @@ int wr_bank_wait(wr_bank *b)
 
 int wr_bank_pipeline_depth(const wr_bank *) { return kSlots; }
 
-int wr_bank_process(wr_bank *b, const float *iq_host, unsigned nframes, float *audio_host, size_t audio_stride)
+static int process_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframes, float *audio_host, size_t audio_stride)
 {
 	WR_REQUIRE(b, WR_EINVAL, "wr_bank_process: null bank");
 	WR_REQUIRE(b->inflight == 0, WR_ESTATE, "wr_bank_process: pipelined blocks still in flight");
-	int rc = wr_bank_submit(b, iq_host, nframes, audio_host, audio_stride);
+	int rc = submit_any(b, iq_host, u8, nframes, audio_host, audio_stride);
 	if (rc != WR_OK)
 		return rc;
 	return wr_bank_wait(b);
 }
 
-int wr_bank_run_device_steps(wr_bank *b, const float *const *iq_dev, unsigned n_iq, size_t stream_stride_frames,
+int wr_bank_process(wr_bank *b, const float *iq_host, unsigned nframes, float *audio_host, size_t audio_stride)
+{
+	return process_any(b, iq_host, false, nframes, audio_host, audio_stride);
+}
+
+int wr_bank_process_u8(wr_bank *b, const uint8_t *iq_host, unsigned nframes, float *audio_host, size_t audio_stride)
+{
+	return process_any(b, iq_host, true, nframes, audio_host, audio_stride);
+}
+
+static int run_device_steps_any(wr_bank *b, const void *const *iq_dev, bool u8, unsigned n_iq, size_t stream_stride_frames,
 		unsigned nframes, float *const *audio_dev, unsigned n_audio, size_t audio_stride,
 		unsigned first, unsigned steps)
 {
 	WR_REQUIRE(b && iq_dev && audio_dev && n_iq && n_audio, WR_EINVAL, "wr_bank_run_device_steps: bad argument");
 	for (unsigned i = 0; i < steps; i++) {
-		int rc = wr_bank_process_device(b, iq_dev[(first + i) % n_iq], stream_stride_frames, nframes,
+		int rc = process_device_any(b, iq_dev[(first + i) % n_iq], u8, stream_stride_frames, nframes,
 				audio_dev[(first + i) % n_audio], audio_stride, nullptr);
 		if (rc != WR_OK)
 			return rc;
@@ -638,7 +696,23 @@ int wr_bank_run_device_steps(wr_bank *b, const float *const *iq_dev, unsigned n_
 	return WR_OK;
 }
 
-int wr_bank_run_host_steps(wr_bank *b, const float *const *iq_pinned, unsigned n_iq, unsigned nframes,
+int wr_bank_run_device_steps(wr_bank *b, const float *const *iq_dev, unsigned n_iq, size_t stream_stride_frames,
+		unsigned nframes, float *const *audio_dev, unsigned n_audio, size_t audio_stride,
+		unsigned first, unsigned steps)
+{
+	return run_device_steps_any(b, reinterpret_cast<const void *const *>(iq_dev), false, n_iq, stream_stride_frames,
+			nframes, audio_dev, n_audio, audio_stride, first, steps);
+}
+
+int wr_bank_run_device_steps_u8(wr_bank *b, const uint8_t *const *iq_dev, unsigned n_iq, size_t stream_stride_frames,
+		unsigned nframes, float *const *audio_dev, unsigned n_audio, size_t audio_stride,
+		unsigned first, unsigned steps)
+{
+	return run_device_steps_any(b, reinterpret_cast<const void *const *>(iq_dev), true, n_iq, stream_stride_frames,
+			nframes, audio_dev, n_audio, audio_stride, first, steps);
+}
+
+static int run_host_steps_any(wr_bank *b, const void *const *iq_pinned, bool u8, unsigned n_iq, unsigned nframes,
 		float *const *audio_pinned, unsigned n_audio, size_t audio_stride,
 		unsigned first, unsigned steps, int pipelined)
 {
@@ -649,7 +723,7 @@ int wr_bank_run_host_steps(wr_bank *b, const float *const *iq_pinned, unsigned n
 	for (unsigned i = 0; i < steps; i++) {
 		if (b->inflight == depth && (rc = wr_bank_wait(b)) != WR_OK)
 			return rc;
-		rc = wr_bank_submit(b, iq_pinned[(first + i) % n_iq], nframes, audio_pinned[(first + i) % n_audio], audio_stride);
+		rc = submit_any(b, iq_pinned[(first + i) % n_iq], u8, nframes, audio_pinned[(first + i) % n_audio], audio_stride);
 		if (rc != WR_OK)
 			return rc;
 	}
@@ -657,6 +731,22 @@ int wr_bank_run_host_steps(wr_bank *b, const float *const *iq_pinned, unsigned n
 		if ((rc = wr_bank_wait(b)) != WR_OK)
 			return rc;
 	return WR_OK;
+}
+
+int wr_bank_run_host_steps(wr_bank *b, const float *const *iq_pinned, unsigned n_iq, unsigned nframes,
+		float *const *audio_pinned, unsigned n_audio, size_t audio_stride,
+		unsigned first, unsigned steps, int pipelined)
+{
+	return run_host_steps_any(b, reinterpret_cast<const void *const *>(iq_pinned), false, n_iq, nframes,
+			audio_pinned, n_audio, audio_stride, first, steps, pipelined);
+}
+
+int wr_bank_run_host_steps_u8(wr_bank *b, const uint8_t *const *iq_pinned, unsigned n_iq, unsigned nframes,
+		float *const *audio_pinned, unsigned n_audio, size_t audio_stride,
+		unsigned first, unsigned steps, int pipelined)
+{
+	return run_host_steps_any(b, reinterpret_cast<const void *const *>(iq_pinned), true, n_iq, nframes,
+			audio_pinned, n_audio, audio_stride, first, steps, pipelined);
 }
 
 void *wr_bank_stream(wr_bank *b) { return b ? (void*)b->compute : nullptr; }

@@ -364,10 +364,49 @@ __device__ __forceinline__ f2_t fir3(uint32_t base32, uint32_t taps32, f2_t nz)
 	return acc;
 }
 
-template <int N1, int D1, int RB>
+// ---- tuner-block formats ---------------------------------------------------------------------
+// F32: interleaved float IQ, as DspBlock buffers carry it (dspblock.h:45).
+// U8 : raw RTL-SDR bytes; the tuner's conversion ((float)b - 128.0) / 128.0 (reference
+//      src/io/rtlsdrtuner.cxx:106) runs here, in the load path, so a frame costs 2 bytes of HBM
+//      and PCIe traffic instead of 8.  Built as 2^23 + b in the mantissa (one byte permute per
+//      component), then one packed fma: (2^23 + b) * 2^-7 - 65537 = (b - 128) / 128, exact.
+template <bool U8> struct RawIO;
+
+template <> struct RawIO<false> {
+	typedef f2_t T;
+	static constexpr unsigned FB = 8;    // bytes per frame
+	__device__ __forceinline__ static T zero() { return 0ull; }
+	__device__ __forceinline__ static T load(const char *p) { return ldg64p(reinterpret_cast<const float2*>(p)); }
+	__device__ __forceinline__ static f2_t cvt(T v, uint32_t) { return v; }
+};
+
+template <> struct RawIO<true> {
+	typedef uint32_t T;
+	static constexpr unsigned FB = 2;
+	__device__ __forceinline__ static T zero() { return 0x8080u; }   // (128, 128) -> (0.0, 0.0)
+	__device__ __forceinline__ static T load(const char *p)
+	{
+		unsigned short v;
+		asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
+		return v;
+	}
+	__device__ __forceinline__ static f2_t cvt(T v, uint32_t hi)     // hi = 0x4B00
+	{
+		uint32_t fi, fq;
+		asm("prmt.b32 %0, %1, %2, 0x5440;" : "=r"(fi) : "r"(v), "r"(hi));
+		asm("prmt.b32 %0, %1, %2, 0x5441;" : "=r"(fq) : "r"(v), "r"(hi));
+		return f2_fma(f2_pack(__uint_as_float(fi), __uint_as_float(fq)), f2_pack(0.0078125f, 0.0078125f),
+				f2_pack(-65537.0f, -65537.0f));
+	}
+};
+
+template <int N1, int D1, int RB, bool U8>
 __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a, const V3Args v)
 {
 	using G = V3Geo<N1, D1>;
+	using IO = RawIO<U8>;
+	typedef typename IO::T raw_t;
+	constexpr unsigned FB = IO::FB;
 	constexpr int NMT = kV3Mixers, J = G::J, S = kV3Slots, C = kV3Fir;
 	constexpr unsigned kSlotBytes = (unsigned)G::SLOT * 8u;
 	extern __shared__ __align__(16) unsigned char wr_smem_v3[];
@@ -425,10 +464,10 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 		const unsigned ti = mt - (unsigned)(NMT - G::HF);          // halo frame this thread carries
 		const uint32_t posHalo = 8u * v3_pos<D1, G::DP>(isTail ? ti : 0u);
 		const unsigned Pfull = a.F / (unsigned)G::SF;              // passes that lie entirely inside the block
-		const bool pfLine = mt < (unsigned)(G::SF / 16);           // this thread prefetches line mt of a pass
-		const unsigned pfOff = 4u * (unsigned)G::SF + 15u * mt;    // float2 units from this thread's frame j = 0
+		const bool pfLine = mt < (unsigned)G::SF * FB / 128u;      // this thread prefetches line mt of a pass
+		const unsigned pfOff = 4u * (unsigned)G::SF * FB + (128u - FB) * mt;   // bytes from this thread's frame j = 0
 
-		f2_t rawA[J], rawB[J];    // raw IQ of the current / the next pass, {i, q} packed (ping-pong)
+		raw_t rawA[J], rawB[J];   // raw IQ of the current / the next pass (ping-pong): {i, q} packed, or the two bytes
 		float2 tail[RB];
 		uint32_t qb[RB];          // biased doubled phase of this thread's frame j = 0 of the current pass
 		uint32_t qstep[RB];       // 2 * NMT * step
@@ -454,13 +493,13 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 				mbar_wait(empty32 + 8u * (m % S), (m / S) & 1u);
 			const int4 grp = __ldg(v.groups + rg);
 			const int cnt = grp.y;
-			const float2 *__restrict__ src = a.iq + (size_t)(unsigned)grp.z * a.stream_stride;
+			const char *__restrict__ src = reinterpret_cast<const char*>(a.iq) + (size_t)(unsigned)grp.z * a.stream_stride * FB;
 			// this thread's frame j = 0 of the current pass; frames past the block read as zero
-			const float2 *rawp = src + (size_t)p0 * G::SF + mt;
+			const char *rawp = src + ((size_t)p0 * G::SF + mt) * FB;
 			#pragma unroll
 			for (int j = 0; j < J; j++) {
 				const unsigned f = p0 * (unsigned)G::SF + mt + (unsigned)j * NMT;
-				rawA[j] = f < a.F ? ldg64p(src + f) : 0ull;
+				rawA[j] = f < a.F ? IO::load(src + (size_t)f * FB) : IO::zero();
 			}
 			uint32_t ph0[RB];
 			int32_t step[RB];
@@ -496,16 +535,22 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 						const unsigned f = p0 * (unsigned)G::SF - (unsigned)G::HF + ti;
 						float sn, cs;
 						lo3_sincos(((ph0[rl] + f * (uint32_t)step[rl]) << 1) + 0x80000000u, lo, sn, cs);
-						tail[rl] = mix(__ldg(src + f), cs, sn);
+						float2 x;
+						f2_unpack(IO::cvt(IO::load(src + (size_t)f * FB), lo.hi), x.x, x.y);
+						tail[rl] = mix(x, cs, sn);
 					}
 				}
 			}
 
 			// One pass: `cur` holds its raw IQ, `nxt` receives the next one's while the last
 			// receiver of the group is mixed.
-			auto do_pass = [&](f2_t (&cur)[J], f2_t (&nxt)[J], const unsigned p) {
+			auto do_pass = [&](raw_t (&curRaw)[J], raw_t (&nxt)[J], const unsigned p) {
 				const bool lastPass = (p + 1 == P);
 				const bool more = (p + 1 < pend);
+				f2_t cur[J];
+				#pragma unroll
+				for (int j = 0; j < J; j++)
+					cur[j] = IO::cvt(curRaw[j], lo.hi);
 				// pull the pass four ahead into L2 while this one is mixed: one 128-byte line per thread
 				if (pfLine && p + 4 < Pfull)
 					asm volatile("prefetch.global.L2 [%0];" :: "l"(rawp + pfOff));
@@ -522,12 +567,12 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 							if (p + 1 < Pfull) {
 								#pragma unroll
 								for (int j = 0; j < J; j++)
-									nxt[j] = ldg64p(rawp + G::SF + j * NMT);
+									nxt[j] = IO::load(rawp + (G::SF + j * NMT) * FB);
 							} else {
 								#pragma unroll
 								for (int j = 0; j < J; j++) {
 									const unsigned f = (p + 1) * (unsigned)G::SF + mt + (unsigned)j * NMT;
-									nxt[j] = f < a.F ? ldg64p(src + f) : 0ull;
+									nxt[j] = f < a.F ? IO::load(src + (size_t)f * FB) : IO::zero();
 								}
 							}
 						}
@@ -573,7 +618,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 						}
 					}
 				}
-				rawp += G::SF;
+				rawp += G::SF * FB;
 			};
 
 			unsigned p = p0;
@@ -646,7 +691,8 @@ typedef void (*V3Kernel)(const ChanArgs, const V3Args);
 
 struct V3Plan {
 	bool ok = false;
-	V3Kernel kernel = nullptr;
+	V3Kernel kernel = nullptr;     // float tuner blocks
+	V3Kernel kernel8 = nullptr;    // raw RTL-SDR bytes
 	int device = 0;
 	int numSMs = 0;
 	unsigned n1 = 0, d1 = 0;
@@ -665,7 +711,8 @@ template <int N1, int D1, int RB>
 inline void v3_fill(V3Plan &p)
 {
 	using G = V3Geo<N1, D1>;
-	p.kernel = chan_kernel_v3<N1, D1, RB>;
+	p.kernel = chan_kernel_v3<N1, D1, RB, false>;
+	p.kernel8 = chan_kernel_v3<N1, D1, RB, true>;
 	p.SF = G::SF;
 	p.RB = RB;
 	p.smemBytes = kV3TableBytes + (size_t)kV3Slots * G::SLOT * 8 + (size_t)RB * G::kTapsStride + (size_t)kV3Slots * 16;
@@ -704,6 +751,7 @@ inline int v3_init(V3Plan &p, int device, unsigned n1, unsigned d1)
 	if (p.smemBytes > (size_t)prop.sharedMemPerBlockOptin)
 		return WR_OK;
 	WR_CUDA(cudaFuncSetAttribute(p.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
+	WR_CUDA(cudaFuncSetAttribute(p.kernel8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
 	WR_CUDA(cudaMalloc(&p.d_delta, kV3TableBytes));
 	p.ok = true;
 	return WR_OK;
@@ -763,7 +811,7 @@ inline int v3_set_groups(V3Plan &p, const RxConf *h_conf, unsigned R, cudaStream
 	return WR_OK;
 }
 
-inline int v3_launch_chan(V3Plan &p, ChanArgs &ca, cudaStream_t st, unsigned long long *launches)
+inline int v3_launch_chan(V3Plan &p, ChanArgs &ca, bool u8, cudaStream_t st, unsigned long long *launches)
 {
 	V3Args v;
 	v.delta = p.d_delta;
@@ -790,7 +838,7 @@ inline int v3_launch_chan(V3Plan &p, ChanArgs &ca, cudaStream_t st, unsigned lon
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = p.pdl ? 1 : 0;
-	cudaError_t e = cudaLaunchKernelEx(&cfg, p.kernel, (const ChanArgs)ca, (const V3Args)v);
+	cudaError_t e = cudaLaunchKernelEx(&cfg, u8 ? p.kernel8 : p.kernel, (const ChanArgs)ca, (const V3Args)v);
 	(*launches)++;
 	if (e == cudaSuccess)
 		e = cudaGetLastError();
