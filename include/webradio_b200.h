@@ -178,6 +178,14 @@ int wr_bank_keep_channel(wr_bank *b, int keep);
  * number of floats written, or a negative error. */
 long wr_bank_read_stage(wr_bank *b, unsigned rx, int stage, float *out_host, size_t cap_floats);
 
+/* Audio sample format of every later block: WR_AUDIO_FLOAT (default) is the
+ * DspBlock convention, WR_AUDIO_LAME multiplies by 32768 in the audio kernel's store -- the
+ * "LAME wants +/-32768" conversion MP3Encoder::encode does per sample before
+ * lame_encode_buffer_float (reference src/web/mp3encoder.cxx:66-73). */
+#define WR_AUDIO_FLOAT 0
+#define WR_AUDIO_LAME  1
+int wr_bank_set_audio_format(wr_bank *b, int format);
+
 /* Selects the kernel family: 0 = auto (default: the newest one that supports the geometry and
  * the block length), 1 = v1 generic kernels (NCO table read from L2), 2 = v2 kernels (NCO table
  * resident in shared memory, tile per work item), 3 = v3 kernels (streaming ring of mixed
@@ -217,6 +225,8 @@ int wr_stage_fir_reset(wr_stage *s);
 /* Demodulator::process (reference demodulator.cxx:77-115). prev[2] read and updated. */
 int wr_stage_demod(wr_stage *s, int mode, float *prev, const float *iq_host, unsigned nframes,
 		float *out_host);
+/* The waterfall palette map of wr_spectrum_get_palette over an arbitrary host array of dB values. */
+int wr_stage_palette(wr_stage *s, const float *db_host, unsigned n, uint8_t *index_host);
 /* Test hook: the device's atan2f over host arrays (one kernel). */
 int wr_stage_atan2f(wr_stage *s, const float *y_host, const float *x_host, unsigned n, float *out_host);
 
@@ -242,6 +252,12 @@ long wr_spectrum_process_device(wr_spectrum *s, const float *iq_dev, size_t stre
 /* SpectrumSink::getSpectrum (reference spectrumsink.cxx:125-142): dB of the most recent
  * transform of one stream; fft_size floats. */
 int wr_spectrum_get(wr_spectrum *s, unsigned stream, float *db_host);
+/* The same row as the 256-entry palette index the browser computes for it:
+ * WaterfallHandler::doGet replaces non-finite bins by -10000.0 (reference
+ * src/web/waterfallhandler.cxx:59-69) and Waterfall.update maps
+ *   floor(((dB + 50.0) / 25.0) * 255.0) clamped to [0, 255]     (html/waterfall.js:92-109)
+ * in double arithmetic; one byte per bin leaves the GPU instead of a float. */
+int wr_spectrum_get_palette(wr_spectrum *s, unsigned stream, uint8_t *index_host);
 unsigned long long wr_spectrum_launch_count(const wr_spectrum *s);
 int wr_spectrum_sync(wr_spectrum *s);
 

@@ -181,6 +181,37 @@ void wro_fir_destroy(wro_fir *f)
 	free(f);
 }
 
+/* What a waterfall bin becomes on the way to the screen.  WaterfallHandler::doGet (reference
+ * src/web/waterfallhandler.cxx:62-68) sends finite values as they are and anything else as
+ * -10000.0; Waterfall.update (reference html/waterfall.js:92-109) computes, in JavaScript numbers
+ * (doubles): val = (series[bin] + 50.0) / 25.0; val = val * 255.0; floor; clamp to [0, 255]. */
+void wro_waterfall_index(const float *db, size_t n, unsigned char *out)
+{
+	for (size_t i = 0; i < n; i++) {
+		double v = isfinite(db[i]) ? (double)db[i] : -10000.0;
+		double val = (v + 50.0) / 25.0;
+		val = val * 255.0;
+		val = floor(val);
+		if (val < 0) val = 0;
+		if (val > 255) val = 255;
+		out[i] = (unsigned char)val;
+	}
+}
+
+/* reference src/web/mp3encoder.cxx:66-73: left[n] = (*ptr++) * 32768.0 (double product, stored to float) */
+void wro_lame_scale(const float *x, size_t n, float *out)
+{
+	for (size_t i = 0; i < n; i++)
+		out[i] = x[i] * 32768.0;
+}
+
+/* reference src/io/rtlsdrtuner.cxx:106: buffer->push_back(((float)(*buf++) - 128.0) / 128.0) */
+void wro_rtlsdr_convert(const unsigned char *buf, size_t n, float *out)
+{
+	for (size_t i = 0; i < n; i++)
+		out[i] = ((float)buf[i] - 128.0) / 128.0;
+}
+
 /* the libm routine reference demodulator.cxx:97 calls, exposed so that tests can pin the
  * product's restatement of it against the C library installed on the box */
 void wro_libm_atan2f(const float *y, const float *x, size_t n, float *out)

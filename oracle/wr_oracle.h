@@ -48,6 +48,12 @@ void wro_fir_destroy(wro_fir *f);
 
 /* reference demodulator.cxx:77-115; prev[2] = {prev_i, prev_q} is read and updated */
 int wro_demod(int mode, float *prev, const float *iq, size_t nframes, float *out);
+/* reference src/web/waterfallhandler.cxx:62-68 + html/waterfall.js:92-109: palette index of a dB row */
+void wro_waterfall_index(const float *db, size_t n, unsigned char *out);
+/* reference src/web/mp3encoder.cxx:66-73: the encoder's +/-32768 sample format */
+void wro_lame_scale(const float *x, size_t n, float *out);
+/* reference src/io/rtlsdrtuner.cxx:104-108: raw bytes to samples */
+void wro_rtlsdr_convert(const unsigned char *buf, size_t n, float *out);
 /* the host libm's atan2f over arrays: what reference demodulator.cxx:97 calls on this box */
 void wro_libm_atan2f(const float *y, const float *x, size_t n, float *out);
 

@@ -48,6 +48,12 @@ def lib():
         L.wro_demod.argtypes = [C.c_int, _fp, _fp, C.c_size_t, _fp]
         L.wro_libm_atan2f.argtypes = [_fp, _fp, C.c_size_t, _fp]
         L.wro_libm_atan2f.restype = None
+        L.wro_waterfall_index.argtypes = [_fp, C.c_size_t, C.c_void_p]
+        L.wro_waterfall_index.restype = None
+        L.wro_lame_scale.argtypes = [_fp, C.c_size_t, _fp]
+        L.wro_lame_scale.restype = None
+        L.wro_rtlsdr_convert.argtypes = [C.c_void_p, C.c_size_t, _fp]
+        L.wro_rtlsdr_convert.restype = None
         L.wro_rx_create.restype = C.c_void_p
         L.wro_rx_create.argtypes = [C.c_uint, C.c_int, _fp, C.c_uint, C.c_uint, C.c_int,
                                     _fp, C.c_uint, C.c_uint]
@@ -130,6 +136,30 @@ class Fir:
         if getattr(self, "h", None):
             lib().wro_fir_destroy(self.h)
             self.h = None
+
+
+def waterfall_index(db):
+    """Palette index per bin as the browser computes it (waterfallhandler.cxx:62-68, waterfall.js:92-109)."""
+    a, ap = _f(db)
+    out = np.empty(a.size, np.uint8)
+    lib().wro_waterfall_index(ap, a.size, out.ctypes.data)
+    return out
+
+
+def lame_scale(x):
+    """MP3Encoder::encode's sample conversion (mp3encoder.cxx:66-73)."""
+    a, ap = _f(x)
+    out = np.empty(a.size, np.float32)
+    lib().wro_lame_scale(ap, a.size, out.ctypes.data_as(_fp))
+    return out.reshape(np.shape(x))
+
+
+def rtlsdr_convert(u8):
+    """RtlSdrTuner's byte-to-sample conversion (rtlsdrtuner.cxx:106)."""
+    b = np.ascontiguousarray(u8, dtype=np.uint8)
+    out = np.empty(b.size, np.float32)
+    lib().wro_rtlsdr_convert(b.ctypes.data, b.size, out.ctypes.data_as(_fp))
+    return out.reshape(b.shape)
 
 
 def libm_atan2f(y, x):

@@ -428,3 +428,60 @@ def test_bank_u8_ingest_matches_the_tuner_conversion(wro, case):
     finally:
         for bank in banks:
             bank.close()
+
+
+# ------------------------------------------------------------------ the steps behind the path ----
+
+def test_waterfall_palette_index(wro):
+    """dB row -> palette index exactly as the handler + browser compute it (waterfallhandler.cxx:62-68,
+    waterfall.js:92-109): every index boundary +-2 ULP, the clamps, and the non-finite -> -10000 rule."""
+    st = capi.Stage()
+    try:
+        edges = (np.float64(-50.0) + np.float64(25.0) * np.arange(0, 257, dtype=np.float64) / np.float64(255.0)).astype(np.float32)
+        around = np.concatenate([(edges.view(np.int32) + d).view(np.float32) for d in (-2, -1, 0, 1, 2)])
+        special = np.float32([-np.inf, np.inf, np.nan, -10000.0, -50.0, -25.0, 0.0, -0.0, 1e30, -1e30, -49.999996, -25.000002])
+        rng = np.random.default_rng(3)
+        db = np.concatenate([around, special, rng.uniform(-80, 10, 100000).astype(np.float32)])
+        got = st.palette(db)
+        want = wro.waterfall_index(db)
+        assert np.array_equal(got, want), np.nonzero(got != want)[0][:10]
+        assert got[around.size] == 0 and got[around.size + 1] == 0 and got[around.size + 2] == 0   # -inf, +inf, nan -> -10000 -> 0
+    finally:
+        st.close()
+
+
+def test_spectrum_palette_of_latest_row(wro):
+    sp = capi.Spectrum(512, max_frames=4096)
+    try:
+        assert np.array_equal(sp.get_palette(0), np.zeros(512, np.uint8))     # nothing transformed yet: all -inf
+        iq = synth.structured(4096, 2400000, [100000, -345678], [0, 1])
+        sp.process(iq[None], rows=False)
+        assert np.array_equal(sp.get_palette(0), wro.waterfall_index(sp.get(0)))
+    finally:
+        sp.close()
+
+
+@pytest.mark.parametrize("variant", [1, 3])
+def test_audio_format_for_the_encoder(wro, variant):
+    """WR_AUDIO_LAME: the audio kernel's store applies MP3Encoder::encode's x * 32768.0
+    (mp3encoder.cxx:66-73); everything else about the block is unchanged."""
+    fs, F, R = 2400000, 20480, 4
+    t1 = capi.lowpass_design(64, 80000, fs)
+    t2 = capi.lowpass_design(64, 8000, 240000)
+    banks = [make_bank(variant, 1, R, F, 64, 10, 64, 5) for _ in range(2)]
+    try:
+        banks[1].set_audio_format(capi.AUDIO_LAME)
+        for bank in banks:
+            for r in range(R):
+                bank.set_taps(r, 0, t1)
+                bank.set_taps(r, 1, t2)
+                bank.set_if(r, 100000 * (r - 1), fs)
+                bank.set_mode(r, r)
+        for b in range(2):
+            iq = synth.structured(F, fs, [100000 * (r - 1) for r in range(R)], list(range(R)), start=b * F)
+            plain = banks[0].process(iq[None])
+            scaled = banks[1].process(iq[None])
+            assert_biteq(scaled, wro.lame_scale(plain), f"v{variant} block {b}")
+    finally:
+        for bank in banks:
+            bank.close()

@@ -16,6 +16,7 @@ AM, FM, USB, LSB = 0, 1, 2, 3
 MODES = {"AM": AM, "FM": FM, "USB": USB, "LSB": LSB}
 RESET_PHASE, RESET_CHANNEL, RESET_DEMOD, RESET_AUDIO = 1, 2, 4, 8
 STAGE_CHANNEL, STAGE_DEMOD = 1, 2
+AUDIO_FLOAT, AUDIO_LAME = 0, 1
 
 _fp = C.POINTER(C.c_float)
 
@@ -29,12 +30,12 @@ SYMBOLS = [
     "wr_bank_process_u8", "wr_bank_process_device_u8", "wr_bank_submit_u8",
     "wr_bank_run_device_steps_u8", "wr_bank_run_host_steps_u8",
     "wr_bank_pipeline_depth", "wr_bank_run_device_steps", "wr_bank_run_host_steps", "wr_bank_stream", "wr_bank_sync", "wr_bank_keep_channel",
-    "wr_bank_read_stage", "wr_bank_set_variant", "wr_bank_variant_in_use", "wr_bank_launch_count", "wr_bank_set_timing",
+    "wr_bank_read_stage", "wr_bank_set_audio_format", "wr_bank_set_variant", "wr_bank_variant_in_use", "wr_bank_launch_count", "wr_bank_set_timing",
     "wr_bank_kernel_times",
     "wr_stage_create", "wr_stage_destroy", "wr_stage_mix", "wr_stage_fir_config", "wr_stage_fir",
-    "wr_stage_fir_reset", "wr_stage_demod", "wr_stage_atan2f",
+    "wr_stage_fir_reset", "wr_stage_demod", "wr_stage_atan2f", "wr_stage_palette",
     "wr_spectrum_create", "wr_spectrum_destroy", "wr_spectrum_process", "wr_spectrum_process_device",
-    "wr_spectrum_get", "wr_spectrum_launch_count", "wr_spectrum_sync",
+    "wr_spectrum_get", "wr_spectrum_get_palette", "wr_spectrum_launch_count", "wr_spectrum_sync",
 ]
 
 _lib = None
@@ -106,6 +107,9 @@ def lib():
     L.wr_stage_fir_reset.argtypes = [vp]
     L.wr_stage_demod.argtypes = [vp, i, _fp, _fp, u, _fp]
     L.wr_stage_atan2f.argtypes = [vp, _fp, _fp, u, _fp]
+    L.wr_stage_palette.argtypes = [vp, _fp, u, vp]
+    L.wr_spectrum_get_palette.argtypes = [vp, u, vp]
+    L.wr_bank_set_audio_format.argtypes = [vp, i]
     L.wr_atan2f_host.argtypes = [_fp, _fp, sz, _fp]
     L.wr_atan2f_host.restype = None
     L.wr_spectrum_create.restype = vp
@@ -280,6 +284,9 @@ class Bank:
         got = _check(self.L.wr_bank_read_stage(self.h, rx, stage, out.ctypes.data_as(_fp), n), "wr_bank_read_stage")
         return out[:got]
 
+    def set_audio_format(self, fmt):
+        _check(self.L.wr_bank_set_audio_format(self.h, fmt), "wr_bank_set_audio_format")
+
     def set_variant(self, v):
         _check(self.L.wr_bank_set_variant(self.h, v), "wr_bank_set_variant")
 
@@ -350,6 +357,12 @@ class Stage:
                                      out.ctypes.data_as(_fp)), "wr_stage_demod")
         return out[:a.size // 2]
 
+    def palette(self, db):
+        a, ap = _f32(db)
+        out = np.empty(max(1, a.size), np.uint8)
+        _check(self.L.wr_stage_palette(self.h, ap, a.size, out.ctypes.data), "wr_stage_palette")
+        return out[:a.size]
+
     def atan2f(self, y, x):
         ya, yp = _f32(y)
         xa, xp = _f32(x)
@@ -403,6 +416,12 @@ class Spectrum:
     def get(self, stream=0):
         out = np.empty(self.N, np.float32)
         _check(self.L.wr_spectrum_get(self.h, stream, out.ctypes.data_as(_fp)), "wr_spectrum_get")
+        return out
+
+    def get_palette(self, stream=0):
+        """The latest row as the browser's 256-entry palette index (waterfall.js:92-109)."""
+        out = np.empty(self.N, np.uint8)
+        _check(self.L.wr_spectrum_get_palette(self.h, stream, out.ctypes.data), "wr_spectrum_get_palette")
         return out
 
     def launch_count(self):

@@ -82,6 +82,7 @@ struct wr_bank {
 	int cur = 0;
 	unsigned lastM1 = 0, lastM2 = 0;
 	bool keepChan = false;
+	float outScale = 1.0f;      // audio sample format: 1 = DspBlock floats, 32768 = what the MP3 encoder feeds LAME
 
 	// host shadows of the per-receiver configuration; setters touch only these (any thread)
 	std::mutex mu;
@@ -308,6 +309,7 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 		da.d2 = b->d2;
 		da.TK = 128;
 		da.ntiles = (M2 + da.TK - 1) / da.TK;
+		da.out_scale = b->outScale;
 		size_t lmax = (size_t)da.TK * b->d2 + b->n2 - 1;
 		size_t smem = sizeof(float) * (((lmax + 3) & ~(size_t)3) + b->n2);
 		dim3 grid(da.ntiles + 1, b->R);
@@ -337,6 +339,7 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 		aa.d2 = b->d2;
 		aa.TK = 128;
 		aa.ntiles = (M2 + aa.TK - 1) / aa.TK;
+		aa.out_scale = b->outScale;
 		size_t lmax = (size_t)(aa.TK - 1) * b->d2 + b->n2;
 		size_t smem = sizeof(float) * (((lmax + 3) & ~(size_t)3) + b->n2);
 		dim3 grid(aa.ntiles + 1, b->R);
@@ -793,6 +796,13 @@ long wr_bank_read_stage(wr_bank *b, unsigned rx, int stage, float *out, size_t c
 	}
 	wr::set_error("wr_bank_read_stage: unknown stage %d", stage);
 	return WR_EINVAL;
+}
+
+int wr_bank_set_audio_format(wr_bank *b, int format)
+{
+	WR_REQUIRE(b && (format == WR_AUDIO_FLOAT || format == WR_AUDIO_LAME), WR_EINVAL, "wr_bank_set_audio_format: bad format %d", format);
+	b->outScale = format == WR_AUDIO_LAME ? 32768.0f : 1.0f;
+	return WR_OK;
 }
 
 int wr_bank_set_variant(wr_bank *b, int variant)

@@ -62,6 +62,7 @@ struct AudioArgs {
 	size_t audio_stride;
 	unsigned M1, M2, n2, d2;
 	unsigned TK, ntiles;
+	float out_scale;         // 1, or 32768 for the encoder's sample format (reference mp3encoder.cxx:66-73)
 };
 
 } // namespace wrd

@@ -92,4 +92,15 @@ __device__ __forceinline__ float demod(int mode, float2 cur, float2 prev)
 	}
 }
 
+// What the browser does with one waterfall bin: WaterfallHandler::doGet sends non-finite values as
+// -10000.0 (reference src/web/waterfallhandler.cxx:62-68), Waterfall.update computes
+// (dB + 50.0) / 25.0, times 255.0, floor, clamp to [0, 255] -- JavaScript numbers, i.e. doubles
+// (reference html/waterfall.js:92-109).
+__device__ __forceinline__ unsigned char waterfall_index(float db)
+{
+	const double v = isfinite(db) ? (double)db : -10000.0;
+	const double val = floor(__dmul_rn(__ddiv_rn(__dadd_rn(v, 50.0), 25.0), 255.0));
+	return (unsigned char)(val < 0.0 ? 0.0 : (val > 255.0 ? 255.0 : val));
+}
+
 } // namespace wrd

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kThreads) audio_kernel_v1(const AudioArgs a)
 		const float *p = s + (size_t)o * d2;
 		for (unsigned j = 0; j < n2; j++)
 			tap1(acc, rt[j], p[j]);
-		a.audio[(size_t)r * a.audio_stride + m0 + o] = acc;
+		a.audio[(size_t)r * a.audio_stride + m0 + o] = __fmul_rn(acc, a.out_scale);
 	}
 }
 

@@ -387,6 +387,7 @@ struct DemodAudioArgs {
 	size_t audio_stride;
 	unsigned M1, M2, n2, d2;
 	unsigned TK, ntiles;
+	float out_scale;         // 1, or 32768 for the encoder's sample format (reference mp3encoder.cxx:66-73)
 };
 
 // sample i of [history | demod(chan)] for receiver r
@@ -456,7 +457,7 @@ __global__ void __launch_bounds__(kThreads) demod_audio_kernel_v2(const DemodAud
 		const float *p = s + (size_t)o * d2;
 		for (unsigned j = 0; j < n2; j++)
 			tap1(acc, rt[j], p[j]);
-		a.audio[(size_t)r * a.audio_stride + m0 + o] = acc;
+		a.audio[(size_t)r * a.audio_stride + m0 + o] = __fmul_rn(acc, a.out_scale);
 	}
 }
 

@@ -8,10 +8,12 @@
 // two-segment view instead of first concatenating them in HBM.
 #include "wr_common.h"
 #include "wr_fft.cuh"
+#include "wr_device.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #ifndef M_PI
@@ -219,6 +221,13 @@ __global__ void __launch_bounds__(256, 2) spectrum_kernel_v2(const SpecArgs a)
 	}
 }
 
+// the browser's palette index for one row (wr_device.cuh: waterfall_index)
+__global__ void spectrum_palette_kernel(const float *__restrict__ db, unsigned char *__restrict__ out, unsigned n)
+{
+	for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+		out[k] = wrd::waterfall_index(db[k]);
+}
+
 // leftover frames of [carry | in] starting at `from` become the next call's carry
 __global__ void spectrum_carry_kernel(const SpecArgs a, float2 *next, size_t from, unsigned count)
 {
@@ -242,6 +251,7 @@ struct wr_spectrum {
 	float *d_rows = nullptr;   // host-path staging [T][maxRows][N]
 	unsigned maxRows = 0;
 	float *d_last = nullptr;   // [T][N]
+	unsigned char *d_palette = nullptr;   // [N] scratch of wr_spectrum_get_palette
 	bool haveLast = false;
 	cudaStream_t lastStream = nullptr; // stream of the most recent launch
 	bool forceV1 = false;              // env WR_FFT_V1=1: radix-4 shared-memory kernel for every size
@@ -264,6 +274,7 @@ void free_spectrum(wr_spectrum *s)
 	cudaFree(s->d_in);
 	cudaFree(s->d_rows);
 	cudaFree(s->d_last);
+	cudaFree(s->d_palette);
 	if (s->st)
 		cudaStreamDestroy(s->st);
 	cudaGetLastError();
@@ -445,6 +456,29 @@ int wr_spectrum_get(wr_spectrum *s, unsigned stream, float *db_host)
 		return WR_OK;
 	}
 	WR_CUDA(cudaMemcpy(db_host, s->d_last + (size_t)stream * s->N, sizeof(float) * s->N, cudaMemcpyDeviceToHost));
+	return WR_OK;
+}
+
+int wr_spectrum_get_palette(wr_spectrum *s, unsigned stream, uint8_t *index_host)
+{
+	WR_REQUIRE(s && index_host && stream < s->T, WR_EINVAL, "wr_spectrum_get_palette: bad argument");
+	if (!wr::use_device(s->device))
+		return WR_ENODEV;
+	WR_CUDA(cudaStreamSynchronize(s->st));
+	if (s->lastStream && s->lastStream != s->st)
+		WR_CUDA(cudaStreamSynchronize(s->lastStream));
+	if (!s->haveLast) {
+		// no transform yet: every bin is -inf, which the handler sends as -10000.0 -> index 0
+		memset(index_host, 0, s->N);
+		return WR_OK;
+	}
+	if (!s->d_palette)
+		WR_CUDA(cudaMalloc(&s->d_palette, s->N));
+	spectrum_palette_kernel<<<(s->N + 255) / 256, 256, 0, s->st>>>(s->d_last + (size_t)stream * s->N, s->d_palette, s->N);
+	s->launches++;
+	WR_CUDA(cudaGetLastError());
+	WR_CUDA(cudaMemcpyAsync(index_host, s->d_palette, s->N, cudaMemcpyDeviceToHost, s->st));
+	WR_CUDA(cudaStreamSynchronize(s->st));
 	return WR_OK;
 }
 

@@ -55,6 +55,12 @@ __global__ void stage_demod_kernel(const float2 *__restrict__ in, float *__restr
 		out[k] = wrd::demod(mode, in[k], k ? in[k - 1] : prev0);
 }
 
+__global__ void stage_palette_kernel(const float *__restrict__ db, unsigned char *__restrict__ out, unsigned n)
+{
+	for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+		out[k] = wrd::waterfall_index(db[k]);
+}
+
 // test hook: the device's atan2f (wr_atan2f.h) over arrays
 __global__ void stage_atan2f_kernel(const float *__restrict__ y, const float *__restrict__ x, float *__restrict__ out, unsigned n)
 {
@@ -286,6 +292,26 @@ int wr_stage_demod(wr_stage *s, int mode, float *prev, const float *iq_host, uns
 	WR_CUDA(cudaStreamSynchronize(s->st));
 	prev[0] = iq_host[2 * (size_t)(nframes - 1)];     // demodulator.cxx:110-111
 	prev[1] = iq_host[2 * (size_t)(nframes - 1) + 1];
+	return WR_OK;
+}
+
+int wr_stage_palette(wr_stage *s, const float *db_host, unsigned n, uint8_t *index_host)
+{
+	WR_REQUIRE(s, WR_EINVAL, "wr_stage_palette: null stage");
+	if (n == 0)
+		return WR_OK;
+	WR_REQUIRE(db_host && index_host, WR_EINVAL, "wr_stage_palette: null buffer");
+	if (!wr::use_device(s->device))
+		return WR_ENODEV;
+	int rc;
+	if ((rc = grow(&s->d_in, &s->capIn, (size_t)n)) != WR_OK) return rc;
+	if ((rc = grow(&s->d_out, &s->capOut, ((size_t)n + 3) / 4)) != WR_OK) return rc;
+	WR_CUDA(cudaMemcpyAsync(s->d_in, db_host, sizeof(float) * n, cudaMemcpyHostToDevice, s->st));
+	stage_palette_kernel<<<grid_for(n, 256), 256, 0, s->st>>>(s->d_in, reinterpret_cast<unsigned char*>(s->d_out), n);
+	s->launches++;
+	WR_CUDA(cudaGetLastError());
+	WR_CUDA(cudaMemcpyAsync(index_host, s->d_out, n, cudaMemcpyDeviceToHost, s->st));
+	WR_CUDA(cudaStreamSynchronize(s->st));
 	return WR_OK;
 }
 
