@@ -403,17 +403,26 @@ def gpu_arm(args, w, wname):
     variant_used = bank.variant_in_use()
     kb = chan_kernel_bytes(w, variant_used, frame_bytes)
     achieved = kb / (chan_ms_avg * 1e-3) / 1e9 if chan_ms_avg > 0 else 0.0
-    traffic = None
+    traffic, ncu = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(wname + ("_u8" if u8 else ""), {}).get("chan_kernel_dram_bytes_per_launch")
+        rec = json.load(open(tpath)).get(wname + ("_u8" if u8 else ""), {})
+        traffic = rec.get("chan_kernel_dram_bytes_per_launch")
+        if rec:
+            # what binds the kernel when it is not HBM (one ncu --set full capture, profiles/)
+            ncu = {k: rec[k] for k in ("issue_active_pct", "l1tex_throughput_pct", "fma_pipe_cycles_active_pct",
+                                       "warp_instructions_per_launch", "kernel", "source") if k in rec}
     roofline = {
         "bound": "hbm",
         "kernel": f"chan_kernel_v{variant_used}: fused NCO mix + channel FIR" if variant_used >= 2 else "chan_kernel_v1: fused NCO mix + channel FIR + demod",
         "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": kb, "kernel_ms": chan_ms_avg, "audio_kernel_ms": audio_ms_avg,
+        # serialised kernel times (CUDA events around each kernel); in the timed region above the
+        # next block's channel kernel starts under this block's demodulator kernel (programmatic
+        # dependent launch), so ms_per_step < kernel_ms + audio_kernel_ms
         "kernel_share_of_step": chan_ms_avg / max(chan_ms_avg + audio_ms_avg, 1e-12),
+        "ncu": ncu,
         "receiver_frames_per_s": R * F / (chan_ms_avg * 1e-3) if chan_ms_avg > 0 else 0.0,
         "note": ("shared-tuner workload: every receiver re-uses the one tuner block from L2/shared memory, "
                  "so DRAM traffic is small by construction and the kernel is FP32-issue bound, not HBM bound "

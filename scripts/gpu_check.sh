@@ -18,6 +18,14 @@ for w in cfg1 cfg3 cfg5 cfg4; do
   echo "== bench $w"
   timeout 900 python bench.py --workload $w --no-cpu-baseline 2>$OUT/bench_$w.err | tee $OUT/bench_$w.json | cut -c1-200
 done
+echo "== bench cfg3 / cfg2 fed raw RTL-SDR bytes"
+for w in cfg3 cfg2; do
+  timeout 900 python bench.py --workload $w --input u8 --no-cpu-baseline 2>/dev/null | tee $OUT/bench_${w}_u8.json | cut -c1-200
+done
+echo "== bench cfg2, v2 kernels (for the record)"
+timeout 900 python bench.py --variant 2 --no-cpu-baseline 2>/dev/null | tee $OUT/bench_cfg2_v2.json | cut -c1-200
+echo "== bench cfg3, v2 kernels (for the record)"
+timeout 900 python bench.py --workload cfg3 --variant 2 --no-cpu-baseline 2>/dev/null | tee $OUT/bench_cfg3_v2.json | cut -c1-200
 echo "== bench cfg2, v1 kernels (for the record)"
 timeout 900 python bench.py --variant 1 --no-cpu-baseline 2>/dev/null | tee $OUT/bench_cfg2_v1.json | cut -c1-200
 echo "== ncu launch list (cfg2, short)"
