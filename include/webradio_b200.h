@@ -107,6 +107,13 @@ int wr_rx_set_phase_step(wr_bank *b, unsigned rx, int32_t step);
  * i.e. coeff[0] multiplies the NEWEST sample.  stage 0 = channel filter, 1 = audio filter;
  * ntaps must equal the bank geometry. */
 int wr_rx_set_taps(wr_bank *b, unsigned rx, int stage, const float *coeff, unsigned ntaps);
+/* LowPass::setPassband for EVERY receiver of the bank at once: the design of
+ * wr_lowpass_design (LowPass::recalculate, reference lowpass.cxx:164-189) runs on the device,
+ * one CTA per receiver, and leaves the taps where the kernels read them; passband_hz has
+ * n_receivers entries.  Bit-identical to calling wr_lowpass_design + wr_rx_set_taps per receiver.
+ * wr_rx_get_taps reads a receiver's current coefficients back (reference order, coeff[0] newest). */
+int wr_bank_design_taps(wr_bank *b, int stage, const unsigned *passband_hz, unsigned sample_rate);
+int wr_rx_get_taps(wr_bank *b, unsigned rx, int stage, float *coeff, unsigned ntaps);
 /* Demodulator::setMode (reference demodulator.h:49). */
 int wr_rx_set_mode(wr_bank *b, unsigned rx, int mode);
 /* Clear carried state (OR of WR_RESET_*); mirrors what ctor/deinit do in the reference. */

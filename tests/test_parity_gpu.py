@@ -485,3 +485,41 @@ def test_audio_format_for_the_encoder(wro, variant):
     finally:
         for bank in banks:
             bank.close()
+
+
+@pytest.mark.parametrize("geom", [(64, 10, 64, 5), (127, 50, 64, 1), (255, 50, 16, 2)])
+def test_bank_design_on_device_equals_host_design(wro, geom):
+    """wr_bank_design_taps (SURVEY.md 8f-3): LowPass::recalculate (lowpass.cxx:164-189) for every receiver
+    at once on the device == the host design == the oracle's restatement, bit for bit, and a bank set up
+    that way produces the same audio as one fed the host-designed coefficients."""
+    n1, d1, n2, d2 = geom
+    fs, F, R = 2400000, 8000, 12
+    pb1 = [80000, 0, 12500, 300000, 1200000, 2399999, 37500, 75000, 150000, 600000, 1, 999999]
+    pb2 = [8000, 3000, 0, 24000, 100000, 15000, 500, 12000, 20000, 1000, 6000, 4000]
+    fs2 = fs // d1
+    banks = [capi.Bank(1, R, F, n1, d1, n2, d2) for _ in range(2)]
+    try:
+        banks[0].design_taps(0, pb1, fs)
+        banks[0].design_taps(1, pb2, fs2)
+        for r in range(R):
+            h1 = capi.lowpass_design(n1, pb1[r], fs)
+            h2 = capi.lowpass_design(n2, pb2[r], fs2)
+            assert_biteq(banks[0].get_taps(r, 0), h1, f"rx{r} channel taps, passband {pb1[r]}")
+            assert_biteq(banks[0].get_taps(r, 1), h2, f"rx{r} audio taps, passband {pb2[r]}")
+            if n1 & (n1 - 1) == 0:
+                assert_biteq(h1, wro.lowpass_design(n1, pb1[r], fs), "host design vs oracle")
+            banks[1].set_taps(r, 0, h1)
+            banks[1].set_taps(r, 1, h2)
+        for bank in banks:
+            for r in range(R):
+                bank.set_if(r, 50000 * (r - 6), fs)
+                bank.set_mode(r, r % 4)
+        # a later per-receiver setter must not disturb the device-designed neighbours
+        banks[0].set_taps(3, 0, capi.lowpass_design(n1, 55555, fs))
+        banks[1].set_taps(3, 0, capi.lowpass_design(n1, 55555, fs))
+        for b in range(2):
+            iq = synth.lattice_noise(F, stream=9, start=b * F)
+            assert_biteq(banks[0].process(iq[None]), banks[1].process(iq[None]), f"block {b}")
+    finally:
+        for bank in banks:
+            bank.close()

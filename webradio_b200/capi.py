@@ -25,7 +25,7 @@ SYMBOLS = [
     "wr_version", "wr_last_error", "wr_device_count", "wr_phase_step", "wr_build_sintable",
     "wr_lowpass_design", "wr_lo_compress_check", "wr_lo3_compress_check", "wr_atan2f_host",
     "wr_bank_create", "wr_bank_destroy", "wr_bank_set_sintable", "wr_rx_set_stream",
-    "wr_rx_set_phase_step", "wr_rx_set_taps", "wr_rx_set_mode", "wr_rx_reset", "wr_rx_set_phase", "wr_rx_get_phase",
+    "wr_rx_set_phase_step", "wr_rx_set_taps", "wr_bank_design_taps", "wr_rx_get_taps", "wr_rx_set_mode", "wr_rx_reset", "wr_rx_set_phase", "wr_rx_get_phase",
     "wr_bank_process", "wr_bank_process_device", "wr_bank_submit", "wr_bank_wait",
     "wr_bank_process_u8", "wr_bank_process_device_u8", "wr_bank_submit_u8",
     "wr_bank_run_device_steps_u8", "wr_bank_run_host_steps_u8",
@@ -70,6 +70,8 @@ def lib():
     L.wr_rx_set_phase_step.argtypes = [vp, u, C.c_int32]
     L.wr_rx_set_taps.argtypes = [vp, u, i, _fp, u]
     L.wr_rx_set_mode.argtypes = [vp, u, i]
+    L.wr_bank_design_taps.argtypes = [vp, i, C.POINTER(C.c_uint), u]
+    L.wr_rx_get_taps.argtypes = [vp, u, i, _fp, u]
     L.wr_rx_reset.argtypes = [vp, u, u]
     L.wr_rx_set_phase.argtypes = [vp, u, C.c_uint32]
     L.wr_rx_get_phase.argtypes = [vp, u, C.POINTER(C.c_uint32)]
@@ -198,6 +200,19 @@ class Bank:
     def set_taps(self, rx, stage, coeff):
         c, p = _f32(coeff)
         _check(self.L.wr_rx_set_taps(self.h, rx, stage, p, c.size), "wr_rx_set_taps")
+
+    def design_taps(self, stage, passbands_hz, fs):
+        """LowPass::setPassband for every receiver at once, designed on the device."""
+        pb = np.ascontiguousarray(passbands_hz, dtype=np.uint32)
+        assert pb.size == self.R
+        _check(self.L.wr_bank_design_taps(self.h, stage, pb.ctypes.data_as(C.POINTER(C.c_uint)), int(fs)),
+               "wr_bank_design_taps")
+
+    def get_taps(self, rx, stage):
+        n = self.n2 if stage else self.n1
+        out = np.empty(n, np.float32)
+        _check(self.L.wr_rx_get_taps(self.h, rx, stage, out.ctypes.data_as(_fp), n), "wr_rx_get_taps")
+        return out
 
     def set_mode(self, rx, mode):
         _check(self.L.wr_rx_set_mode(self.h, rx, MODES.get(mode, mode)), "wr_rx_set_mode")

@@ -7,9 +7,14 @@
 #include "wr_kernels_v3.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <vector>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
 
 using wrd::RxConf;
 using wrd::RxState;
@@ -52,6 +57,27 @@ __global__ void u8_to_f32_kernel(const unsigned char *__restrict__ in, float *__
 	float *dst = out + (size_t)blockIdx.y * out_stride;
 	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nfloats; i += gridDim.x * blockDim.x)
 		dst[i] = __fdiv_rn(__fsub_rn((float)src[i], 128.0f), 128.0f);
+}
+
+// LowPass::recalculate for every receiver of a bank at once (reference lowpass.cxx:164-189; the
+// arithmetic is wr_lowpass_design's, term for term: same mask, same summation order in double,
+// one rounding to float, same window).  cos(2 pi idx / n) and the window come from the HOST libm
+// in two small tables, so host and device designs are bit-identical.
+__global__ void design_kernel(const double *__restrict__ costab, const float *__restrict__ window,
+		const unsigned *__restrict__ passband, unsigned fs, unsigned n, float *__restrict__ taps_rev)
+{
+	const unsigned r = blockIdx.x;
+	const unsigned maxbin = n * passband[r] / fs / 2;          // lowpass.cxx:167, unsigned arithmetic
+	for (unsigned k = threadIdx.x; k < n; k += blockDim.x) {
+		const unsigned bin = (k + n / 2) % n;                  // lowpass.cxx:184
+		double re = 0.0;
+		for (unsigned m = 0; m < n; m++) {
+			const double mask = (min(m, n - m) < maxbin) ? 1.0 : 0.0;
+			const unsigned idx = (unsigned)(((unsigned long long)bin * m) % n);
+			re = __dadd_rn(re, __dmul_rn(mask, costab[idx]));
+		}
+		taps_rev[(size_t)r * n + (n - 1 - k)] = __fmul_rn((float)re, window[k]);
+	}
 }
 
 struct Slot {
@@ -530,6 +556,74 @@ int wr_rx_set_taps(wr_bank *b, unsigned rx, int stage, const float *coeff, unsig
 	for (unsigned j = 0; j < n; j++)
 		dst[j] = coeff[n - 1 - j]; // the kernels walk taps in sample order (lowpass.cxx:152-156)
 	(stage ? b->taps2Dirty : b->taps1Dirty) = true;
+	return WR_OK;
+}
+
+int wr_bank_design_taps(wr_bank *b, int stage, const unsigned *passband_hz, unsigned sample_rate)
+{
+	WR_REQUIRE(b && passband_hz && sample_rate > 0 && (stage == 0 || stage == 1), WR_EINVAL, "wr_bank_design_taps: bad argument");
+	if (!wr::use_device(b->device))
+		return WR_ENODEV;
+	const unsigned n = stage ? b->n2 : b->n1;
+	WR_REQUIRE(n >= 2, WR_EINVAL, "wr_bank_design_taps: %u taps", n);
+	// pending setter changes first, so that the copy back below leaves host and device identical
+	int rc = apply_pending(b, b->compute);
+	if (rc != WR_OK)
+		return rc;
+	std::vector<double> costab(n);
+	std::vector<float> window(n);
+	const double two_pi = 6.283185307179586476925286766559;
+	for (unsigned i = 0; i < n; i++) {
+		costab[i] = cos(two_pi * (double)i / (double)n);
+		// lowpass.cxx:108-109: Hamming window, then the 1/N of the unnormalised transform
+		float w = (float)(0.54 - 0.46 * cosf((float)(2 * M_PI * (float)i / (float)(n - 1))));
+		w /= (float)n;
+		window[i] = w;
+	}
+	double *d_cos = nullptr;
+	float *d_win = nullptr;
+	unsigned *d_pb = nullptr;
+	cudaError_t e = cudaMalloc(&d_cos, sizeof(double) * n);
+	if (e == cudaSuccess) e = cudaMalloc(&d_win, sizeof(float) * n);
+	if (e == cudaSuccess) e = cudaMalloc(&d_pb, sizeof(unsigned) * b->R);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_cos, costab.data(), sizeof(double) * n, cudaMemcpyHostToDevice, b->compute);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_win, window.data(), sizeof(float) * n, cudaMemcpyHostToDevice, b->compute);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_pb, passband_hz, sizeof(unsigned) * b->R, cudaMemcpyHostToDevice, b->compute);
+	float *d_taps = stage ? b->d_taps2 : b->d_taps1;
+	std::vector<float> &h_taps = stage ? b->h_taps2 : b->h_taps1;
+	if (e == cudaSuccess) {
+		design_kernel<<<b->R, 128, 0, b->compute>>>(d_cos, d_win, d_pb, sample_rate, n, d_taps);
+		b->launches++;
+		e = cudaGetLastError();
+	}
+	{
+		std::lock_guard<std::mutex> lk(b->mu);
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(h_taps.data(), d_taps, sizeof(float) * h_taps.size(), cudaMemcpyDeviceToHost, b->compute);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(b->compute);
+		(stage ? b->taps2Dirty : b->taps1Dirty) = false;
+	}
+	cudaFree(d_cos);
+	cudaFree(d_win);
+	cudaFree(d_pb);
+	if (e != cudaSuccess) {
+		wr::set_error("wr_bank_design_taps: %s", cudaGetErrorString(e));
+		cudaGetLastError();
+		return WR_ECUDA;
+	}
+	return WR_OK;
+}
+
+int wr_rx_get_taps(wr_bank *b, unsigned rx, int stage, float *coeff, unsigned ntaps)
+{
+	WR_REQUIRE(b && coeff && rx < b->R && (stage == 0 || stage == 1), WR_EINVAL, "wr_rx_get_taps: bad argument");
+	const unsigned n = stage ? b->n2 : b->n1;
+	WR_REQUIRE(ntaps == n, WR_EINVAL, "wr_rx_get_taps: %u taps asked, bank geometry has %u", ntaps, n);
+	std::lock_guard<std::mutex> lk(b->mu);
+	const float *src = (stage ? b->h_taps2.data() : b->h_taps1.data()) + (size_t)rx * n;
+	for (unsigned j = 0; j < n; j++)
+		coeff[j] = src[n - 1 - j];
 	return WR_OK;
 }
 
