@@ -40,8 +40,9 @@
 namespace wrd {
 
 constexpr int kV3Mixers = 320;                 // mixer threads (10 warps)
-constexpr int kV3Slots = 6;                    // ring slots
-constexpr int kV3Fir = kV3Slots;               // FIR warps: warp w owns slot w (so no barrier is ever shared by two waiters)
+constexpr int kV3Slots = 3;                    // ring slots
+constexpr int kV3FirPerSlot = 2;               // FIR warps that share a slot (each takes every second group of 32 outputs)
+constexpr int kV3Fir = kV3Slots * kV3FirPerSlot;
 constexpr int kV3Threads = kV3Mixers + 32 * kV3Fir;
 constexpr unsigned kV3TableBytes = (((unsigned)(WR_LO3_SLOT_MAX - WR_LO3_SLOT_MIN + 1) * 2u) + 15u) & ~15u;
 constexpr unsigned kV3MidOffset = (unsigned)(-(WR_LO3_SLOT_MIN)) * 2u;   // byte offset of slot 0
@@ -63,7 +64,10 @@ struct V3Geo {
 	static constexpr int A = (N1 - 1 + D1 - 1) / D1;       // periods of halo
 	static constexpr int OFF = A * D1 - (N1 - 1);          // offset of an output's first tap in its period
 	static constexpr int DP = v3_pad_period(D1);
-	static constexpr int NG = (32 * D1 >= 1280) ? 1 : 1280 / (32 * D1);   // output groups per slot
+	// output groups (of 32) per slot: passes of ~3200 frames, so that a mixer thread owns 8-10
+	// frames per pass and the per-pass bookkeeping is spread over twice as many frames as with
+	// one group per slot
+	static constexpr int NG = (32 * D1 >= 3200) ? 1 : 3200 / (32 * D1);
 	static constexpr int GO = 32 * NG;                     // outputs per slot
 	static constexpr int SF = GO * D1;                     // frames per pass
 	static constexpr int J = SF / kV3Mixers;               // frames per mixer thread
@@ -76,6 +80,8 @@ struct V3Geo {
 	static_assert(HF <= kV3Mixers, "halo must fit the last frame of each mixer thread");
 	static_assert(HF <= SF, "a pass must be at least as long as the halo");
 	static_assert(N1 <= kV3Mixers, "taps are staged one per mixer thread");
+	static_assert(J % 2 == 0, "a pass is mixed in two halves");
+	static_assert(NG % kV3FirPerSlot == 0, "the FIR warps of a slot split its groups evenly");
 };
 
 struct V3Args {
@@ -407,7 +413,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 	using IO = RawIO<U8>;
 	typedef typename IO::T raw_t;
 	constexpr unsigned FB = IO::FB;
-	constexpr int NMT = kV3Mixers, J = G::J, S = kV3Slots, C = kV3Fir;
+	constexpr int NMT = kV3Mixers, J = G::J, JH = G::J / 2, S = kV3Slots, FW = kV3FirPerSlot;
 	constexpr unsigned kSlotBytes = (unsigned)G::SLOT * 8u;
 	extern __shared__ __align__(16) unsigned char wr_smem_v3[];
 	const unsigned tid = threadIdx.x;
@@ -424,7 +430,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 		mbar_init(bar32, 1);
 		for (int i = 0; i < S; i++) {
 			mbar_init(full32 + 8u * i, NMT / 32);    // one arrival per mixer warp
-			mbar_init(empty32 + 8u * i, 1);          // one arrival by the slot's FIR warp
+			mbar_init(empty32 + 8u * i, FW);         // one arrival per FIR warp of the slot
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
@@ -467,7 +473,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 		const bool pfLine = mt < (unsigned)G::SF * FB / 128u;      // this thread prefetches line mt of a pass
 		const unsigned pfOff = 4u * (unsigned)G::SF * FB + (128u - FB) * mt;   // bytes from this thread's frame j = 0
 
-		raw_t rawA[J], rawB[J];   // raw IQ of the current / the next pass (ping-pong): {i, q} packed, or the two bytes
+		raw_t raw[J];             // raw IQ of the current pass: {i, q} packed, or the two bytes
 		float2 tail[RB];
 		uint32_t qb[RB];          // biased doubled phase of this thread's frame j = 0 of the current pass
 		uint32_t qstep[RB];       // 2 * NMT * step
@@ -499,7 +505,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 			#pragma unroll
 			for (int j = 0; j < J; j++) {
 				const unsigned f = p0 * (unsigned)G::SF + mt + (unsigned)j * NMT;
-				rawA[j] = f < a.F ? IO::load(src + (size_t)f * FB) : IO::zero();
+				raw[j] = f < a.F ? IO::load(src + (size_t)f * FB) : IO::zero();
 			}
 			uint32_t ph0[RB];
 			int32_t step[RB];
@@ -542,56 +548,72 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 				}
 			}
 
-			// One pass: `cur` holds its raw IQ, `nxt` receives the next one's while the last
-			// receiver of the group is mixed.
-			auto do_pass = [&](raw_t (&curRaw)[J], raw_t (&nxt)[J], const unsigned p) {
+			// One pass per iteration.  A pass is mixed in two halves of JH frames per thread; while
+			// the LAST receiver of the group is mixed, each half's raw registers are refilled with
+			// the next pass's frames as soon as the half is done with them, so the loads fly behind
+			// the mixing without a second register set.
+			for (unsigned p = p0; p < pend; p++) {
 				const bool lastPass = (p + 1 == P);
 				const bool more = (p + 1 < pend);
-				f2_t cur[J];
-				#pragma unroll
-				for (int j = 0; j < J; j++)
-					cur[j] = IO::cvt(curRaw[j], lo.hi);
+				const bool nextFull = (p + 1 < Pfull);
 				// pull the pass four ahead into L2 while this one is mixed: one 128-byte line per thread
 				if (pfLine && p + 4 < Pfull)
 					asm volatile("prefetch.global.L2 [%0];" :: "l"(rawp + pfOff));
+				// raw bytes are converted once per pass; float blocks are used where they are
+				f2_t cur8[U8 ? J : 1];
+				if (U8) {
+					#pragma unroll
+					for (int j = 0; j < J; j++)
+						cur8[U8 ? j : 0] = IO::cvt(raw[j], lo.hi);
+				}
 				#pragma unroll
 				for (int rl = 0; rl < RB; rl++) {
 					if (rl < cnt) {
 						if (kuse)
-							mbar_wait(empty32 + 8u * slot, (kuse - 1u) & 1u);  // the FIR warp is done with this slot
+							mbar_wait(empty32 + 8u * slot, (kuse - 1u) & 1u);  // the FIR warps are done with this slot
 						const uint32_t slot32 = ring32 + slot * kSlotBytes;
 						if (isTail)
 							sts64(slot32 + posHalo, tail[rl]);
-						if (rl == cnt - 1 && more) {
-							// last receiver of the pass: fetch the next pass's raw IQ behind the mixing
-							if (p + 1 < Pfull) {
-								#pragma unroll
-								for (int j = 0; j < J; j++)
-									nxt[j] = IO::load(rawp + (G::SF + j * NMT) * FB);
-							} else {
-								#pragma unroll
-								for (int j = 0; j < J; j++) {
-									const unsigned f = (p + 1) * (unsigned)G::SF + mt + (unsigned)j * NMT;
-									nxt[j] = f < a.F ? IO::load(src + (size_t)f * FB) : IO::zero();
+						const bool refill = (rl == cnt - 1) && more;
+						#pragma unroll
+						for (int h = 0; h < 2; h++) {
+							uint32_t q[JH];
+							float sn[JH], cs[JH];
+							#pragma unroll
+							for (int jj = 0; jj < JH; jj++)
+								q[jj] = qb[rl] + (uint32_t)(h * JH + jj) * qstep[rl];
+							lo3_sincos_n<JH>(q, lo, sn, cs);
+							#pragma unroll
+							for (int jj = 0; jj < JH; jj++) {
+								const int j = h * JH + jj;
+								f2_t x;
+								if constexpr (U8)
+									x = cur8[j];
+								else
+									x = raw[j];
+								// downconverter.cxx:109-110:  I' = i*cos + q*sin ;  Q' = q*cos - i*sin
+								float ic, qc, is, qs;
+								f2_unpack(f2_fma(x, f2_pack(cs[jj], cs[jj]), nzp), ic, qc);
+								f2_unpack(f2_fma(x, f2_pack(sn[jj], sn[jj]), nzp), is, qs);
+								const float2 m = make_float2(__fadd_rn(ic, qs), __fsub_rn(qc, is));
+								sts64(slot32 + posMain[j], m);
+								if (j == J - 1)
+									tail[rl] = m;      // only meaningful (and only used) in the tail threads
+							}
+							if (refill) {
+								// this half's raw registers are free: fetch the same frames of the next pass
+								if (nextFull) {
+									#pragma unroll
+									for (int jj = 0; jj < JH; jj++)
+										raw[h * JH + jj] = IO::load(rawp + (G::SF + (h * JH + jj) * NMT) * FB);
+								} else {
+									#pragma unroll
+									for (int jj = 0; jj < JH; jj++) {
+										const unsigned f = (p + 1) * (unsigned)G::SF + mt + (unsigned)(h * JH + jj) * NMT;
+										raw[h * JH + jj] = f < a.F ? IO::load(src + (size_t)f * FB) : IO::zero();
+									}
 								}
 							}
-						}
-						uint32_t q[J];
-						float sn[J], cs[J];
-						#pragma unroll
-						for (int j = 0; j < J; j++)
-							q[j] = qb[rl] + (uint32_t)j * qstep[rl];
-						lo3_sincos_n<J>(q, lo, sn, cs);
-						#pragma unroll
-						for (int j = 0; j < J; j++) {
-							// downconverter.cxx:109-110:  I' = i*cos + q*sin ;  Q' = q*cos - i*sin
-							float ic, qc, is, qs;
-							f2_unpack(f2_fma(cur[j], f2_pack(cs[j], cs[j]), nzp), ic, qc);
-							f2_unpack(f2_fma(cur[j], f2_pack(sn[j], sn[j]), nzp), is, qs);
-							const float2 m = make_float2(__fadd_rn(ic, qs), __fsub_rn(qc, is));
-							sts64(slot32 + posMain[j], m);
-							if (j == J - 1)
-								tail[rl] = m;      // only meaningful (and only used) in the tail threads
 						}
 						qb[rl] += (uint32_t)J * qstep[rl];   // 2 * SF * step further: frame j = 0 of the next pass
 						if (mt == 0)
@@ -619,21 +641,11 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 					}
 				}
 				rawp += G::SF * FB;
-			};
-
-			unsigned p = p0;
-			for (;;) {
-				do_pass(rawA, rawB, p);
-				if (++p == pend)
-					break;
-				do_pass(rawB, rawA, p);
-				if (++p == pend)
-					break;
 			}
 			unit += pend - p0;
 		}
-		// tell every FIR warp to stop
-		for (int i = 0; i < C; i++) {
+		// tell every FIR warp to stop (one descriptor per slot reaches both of its warps)
+		for (int i = 0; i < S; i++) {
 			if (kuse)
 				mbar_wait(empty32 + 8u * slot, (kuse - 1u) & 1u);
 			if (mt == 0)
@@ -652,8 +664,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 		// ================================== FIR warps ==================================
 		const unsigned fw = (tid - NMT) >> 5, lane = tid & 31;
 		const f2_t nz = f2_pack(v.negzero, v.negzero);
-		static_assert(C == S, "FIR warp w owns slot w");
-		const unsigned slot = fw;
+		// FIR warp fw serves slot fw % S and, of its NG groups of 32 outputs, every FW-th one
+		const unsigned slot = fw % S, sub = fw / S;
 		// the demodulator of the previous block may still be reading the channel-rate buffer
 		asm volatile("griddepcontrol.wait;" ::: "memory");
 		for (unsigned kuse = 0; ; kuse++) {
@@ -667,7 +679,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 			const uint32_t slot32 = ring32 + slot * kSlotBytes;
 			const uint32_t t32 = taps32 + rl * G::kTapsStride;
 			#pragma unroll 1
-			for (int g = 0; g < G::NG; g++) {
+			for (int g = (int)sub; g < G::NG; g += FW) {
 				const unsigned o = (unsigned)g * 32u + lane;
 				if ((unsigned)g * 32u < nout) {     // warp-uniform
 					const f2_t acc = fir3<N1, D1, G::DP>(slot32 + 8u * o * (unsigned)G::DP, t32, nz);
