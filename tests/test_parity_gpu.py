@@ -523,3 +523,15 @@ def test_bank_design_on_device_equals_host_design(wro, geom):
     finally:
         for bank in banks:
             bank.close()
+
+
+@pytest.mark.parametrize("geom,F", [((127, 50, 64, 1), 20037), ((64, 10, 64, 5), 10243), ((255, 50, 16, 2), 3200),
+                                    ((127, 40, 64, 5), 2560 * 3 + 1), ((255, 50, 64, 1), 6399)])
+def test_bank_v3_ragged_block_lengths(wro, geom, F):
+    """The v3 kernel on block lengths that are not multiples of the decimation or of its pass length
+    (3200 / 2560 frames): the last pass is partial, floor(F / d1) outputs, the carried history is the
+    last n1-1 frames of the real block.  Three blocks, mixed modes, every receiver checked."""
+    n1, d1, n2, d2 = geom
+    fs = 2400000
+    R = 6
+    run_bank_vs_oracle(wro, 3, fs, F, 2, synth.receiver_ifs(R, fs), [r % 4 for r in range(R)], n1, d1, n2, d2, 3, seed=11)

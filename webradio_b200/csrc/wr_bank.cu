@@ -509,7 +509,7 @@ wr_bank *wr_bank_create(int device, unsigned n_streams, unsigned n_receivers, un
 	wr_build_sintable(b->h_table.data());
 	b->tableDirty = true;
 
-	if (wrd::v2_init(b->v2, device, n1, d1) != WR_OK || wrd::v3_init(b->v3, device, n1, d1) != WR_OK) {
+	if (wrd::v2_init(b->v2, device, n1, d1) != WR_OK || wrd::v3_init(b->v3, device, n1, d1, max_frames) != WR_OK) {
 		free_bank(b);
 		return nullptr;
 	}

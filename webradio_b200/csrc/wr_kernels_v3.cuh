@@ -717,6 +717,7 @@ struct V3Plan {
 	unsigned nGroups = 0;
 	unsigned capR = 0;
 	bool pdl = true;          // WR_V3_PDL=0 turns programmatic dependent launch off
+	unsigned maxF = 0;        // block length the bank was created for (sizes the receiver groups)
 };
 
 template <int N1, int D1, int RB>
@@ -743,9 +744,10 @@ inline void v3_destroy(V3Plan &p)
 
 // v3 is built for the geometries of the BASELINE configs and the reference's shipped point;
 // everything else stays with v2 / v1.
-inline int v3_init(V3Plan &p, int device, unsigned n1, unsigned d1)
+inline int v3_init(V3Plan &p, int device, unsigned n1, unsigned d1, unsigned maxF)
 {
 	p.device = device;
+	p.maxF = maxF;
 	p.n1 = n1;
 	p.d1 = d1;
 	p.ok = false;
@@ -799,13 +801,24 @@ inline int v3_set_groups(V3Plan &p, const RxConf *h_conf, unsigned R, cudaStream
 		order[r] = r;
 	std::stable_sort(order.begin(), order.end(),
 			[&](unsigned x, unsigned y) { return h_conf[x].stream < h_conf[y].stream; });
+	// Receivers that share a stream are mixed from one set of raw registers, up to RB at a time.
+	// A work unit is (group, pass); with few receivers and short blocks large groups leave the
+	// 148 CTAs with 3 or 4 units each (a 15% imbalance), so the group size is halved until there
+	// are enough units to spread evenly.
+	const unsigned passes = std::max(1u, (p.maxF + p.SF - 1) / p.SF);
+	unsigned cap = p.RB;
 	std::vector<int4> groups;
-	for (unsigned i = 0; i < R;) {
-		unsigned n = 1;
-		while (i + n < R && n < p.RB && h_conf[order[i + n]].stream == h_conf[order[i]].stream)
-			n++;
-		groups.push_back(make_int4((int)i, (int)n, (int)h_conf[order[i]].stream, 0));
-		i += n;
+	for (;; cap /= 2) {
+		groups.clear();
+		for (unsigned i = 0; i < R;) {
+			unsigned n = 1;
+			while (i + n < R && n < cap && h_conf[order[i + n]].stream == h_conf[order[i]].stream)
+				n++;
+			groups.push_back(make_int4((int)i, (int)n, (int)h_conf[order[i]].stream, 0));
+			i += n;
+		}
+		if (cap == 1 || (unsigned long long)groups.size() * passes >= 6ull * (unsigned)p.numSMs)
+			break;
 	}
 	if (R > p.capR) {
 		cudaFree(p.d_order);
