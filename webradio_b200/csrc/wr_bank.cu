@@ -333,7 +333,12 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 		da.M2 = M2;
 		da.n2 = b->n2;
 		da.d2 = b->d2;
+		// 128 audio outputs per CTA, fewer when that would leave most SMs without a CTA (a single
+		// receiver's block is 16 tiles of 128): the demodulator in front of the FIR is the long
+		// pole of a tile, and smaller tiles spread it over more SMs
 		da.TK = 128;
+		while (da.TK > 16 && (unsigned long long)b->R * ((M2 + da.TK - 1) / da.TK) < 296ull)
+			da.TK /= 2;
 		da.ntiles = (M2 + da.TK - 1) / da.TK;
 		da.out_scale = b->outScale;
 		size_t lmax = (size_t)da.TK * b->d2 + b->n2 - 1;
