@@ -705,6 +705,9 @@ struct V3Plan {
 	bool ok = false;
 	V3Kernel kernel = nullptr;     // float tuner blocks
 	V3Kernel kernel8 = nullptr;    // raw RTL-SDR bytes
+	V3Kernel kernelH = nullptr;    // the same two, instantiated for groups of at most RB/2 receivers:
+	V3Kernel kernel8H = nullptr;   // half the unrolled mixer code when the groups are small anyway
+	unsigned groupCap = 0;         // largest group v3_set_groups built
 	int device = 0;
 	int numSMs = 0;
 	unsigned n1 = 0, d1 = 0;
@@ -726,6 +729,8 @@ inline void v3_fill(V3Plan &p)
 	using G = V3Geo<N1, D1>;
 	p.kernel = chan_kernel_v3<N1, D1, RB, false>;
 	p.kernel8 = chan_kernel_v3<N1, D1, RB, true>;
+	p.kernelH = chan_kernel_v3<N1, D1, (RB > 1 ? RB / 2 : 1), false>;
+	p.kernel8H = chan_kernel_v3<N1, D1, (RB > 1 ? RB / 2 : 1), true>;
 	p.SF = G::SF;
 	p.RB = RB;
 	p.smemBytes = kV3TableBytes + (size_t)kV3Slots * G::SLOT * 8 + (size_t)RB * G::kTapsStride + (size_t)kV3Slots * 16;
@@ -766,6 +771,8 @@ inline int v3_init(V3Plan &p, int device, unsigned n1, unsigned d1, unsigned max
 		return WR_OK;
 	WR_CUDA(cudaFuncSetAttribute(p.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
 	WR_CUDA(cudaFuncSetAttribute(p.kernel8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
+	WR_CUDA(cudaFuncSetAttribute(p.kernelH, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
+	WR_CUDA(cudaFuncSetAttribute(p.kernel8H, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
 	WR_CUDA(cudaMalloc(&p.d_delta, kV3TableBytes));
 	p.ok = true;
 	return WR_OK;
@@ -820,6 +827,7 @@ inline int v3_set_groups(V3Plan &p, const RxConf *h_conf, unsigned R, cudaStream
 		if (cap == 1 || (unsigned long long)groups.size() * passes >= 6ull * (unsigned)p.numSMs)
 			break;
 	}
+	p.groupCap = cap;
 	if (R > p.capR) {
 		cudaFree(p.d_order);
 		cudaFree(p.d_groups);
@@ -863,7 +871,9 @@ inline int v3_launch_chan(V3Plan &p, ChanArgs &ca, bool u8, cudaStream_t st, uns
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = p.pdl ? 1 : 0;
-	cudaError_t e = cudaLaunchKernelEx(&cfg, u8 ? p.kernel8 : p.kernel, (const ChanArgs)ca, (const V3Args)v);
+	const bool half = p.RB > 1 && p.groupCap <= p.RB / 2;
+	const V3Kernel k = half ? (u8 ? p.kernel8H : p.kernelH) : (u8 ? p.kernel8 : p.kernel);
+	cudaError_t e = cudaLaunchKernelEx(&cfg, k, (const ChanArgs)ca, (const V3Args)v);
 	(*launches)++;
 	if (e == cudaSuccess)
 		e = cudaGetLastError();
