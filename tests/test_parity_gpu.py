@@ -526,7 +526,8 @@ def test_bank_design_on_device_equals_host_design(wro, geom):
 
 
 @pytest.mark.parametrize("geom,F", [((127, 50, 64, 1), 20037), ((64, 10, 64, 5), 10243), ((255, 50, 16, 2), 3200),
-                                    ((127, 40, 64, 5), 2560 * 3 + 1), ((255, 50, 64, 1), 6399)])
+                                    ((127, 40, 64, 5), 2560 * 3 + 1), ((255, 50, 64, 1), 6399),
+                                    ((64, 8, 64, 4), 2560 * 4 + 37)])
 def test_bank_v3_ragged_block_lengths(wro, geom, F):
     """The v3 kernel on block lengths that are not multiples of the decimation or of its pass length
     (3200 / 2560 frames): the last pass is partial, floor(F / d1) outputs, the carried history is the

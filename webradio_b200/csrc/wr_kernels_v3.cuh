@@ -59,6 +59,17 @@ constexpr int v3_pad_period(int d)
 	return dp;
 }
 
+// Output groups (of 32) per slot: the largest even count that keeps a pass at or below ~3200
+// frames AND gives every mixer thread an even number of frames (a pass is mixed in two halves).
+constexpr int v3_groups(int d)
+{
+	int best = 0;
+	for (int ng = 2; 32 * ng * d <= 3200; ng += 2)
+		if ((32 * ng * d) % (2 * kV3Mixers) == 0)
+			best = ng;
+	return best;
+}
+
 template <int N1, int D1>
 struct V3Geo {
 	static constexpr int A = (N1 - 1 + D1 - 1) / D1;       // periods of halo
@@ -67,7 +78,8 @@ struct V3Geo {
 	// output groups (of 32) per slot: passes of ~3200 frames, so that a mixer thread owns 8-10
 	// frames per pass and the per-pass bookkeeping is spread over twice as many frames as with
 	// one group per slot
-	static constexpr int NG = (32 * D1 >= 3200) ? 1 : 3200 / (32 * D1);
+	static constexpr int NG = v3_groups(D1);
+	static_assert(NG >= 2, "no pass length fits this decimation");
 	static constexpr int GO = 32 * NG;                     // outputs per slot
 	static constexpr int SF = GO * D1;                     // frames per pass
 	static constexpr int J = SF / kV3Mixers;               // frames per mixer thread
@@ -760,6 +772,7 @@ inline int v3_init(V3Plan &p, int device, unsigned n1, unsigned d1, unsigned max
 	if (const char *e = getenv("WR_V3_PDL"))
 		p.pdl = atoi(e) != 0;
 	if (n1 == 64 && d1 == 10) v3_fill<64, 10, 4>(p);
+	else if (n1 == 64 && d1 == 8) v3_fill<64, 8, 4>(p);     // 2.048 MSPS -> 256 k
 	else if (n1 == 127 && d1 == 50) v3_fill<127, 50, 4>(p);
 	else if (n1 == 255 && d1 == 50) v3_fill<255, 50, 2>(p);
 	else if (n1 == 127 && d1 == 40) v3_fill<127, 40, 4>(p);
