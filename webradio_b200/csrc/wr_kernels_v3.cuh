@@ -1,32 +1,38 @@
 // wr_kernels_v3.cuh -- fused NCO mix + decimating channel FIR (K1+K2 of SURVEY.md 2a), third
 // generation: a STREAMING RING of mixed slots instead of one tile per work item.
 //
-// What v2 measured (profiles/r02_v2_stalls.md): its per-item set-up was 21% of all instructions,
-// the mixers spent 21% of their time waiting for a tile buffer and 18% waiting for raw loads, and
-// the consumer's single dependent FADD2 chain per tile took ~5100 clk because the warp scheduler
-// is fair -- a latency-bound warp gets one issue slot per round like everyone else, so a role
-// that needs 5x the instructions of the others per hand-over is the critical path.
+// What v2 measured: its per-item set-up was 21% of all instructions, the mixers spent 21% of
+// their time waiting for a tile buffer and 18% waiting for raw loads, and the consumer's single
+// dependent FADD2 chain per tile took ~5100 clk because the warp scheduler is fair -- a
+// latency-bound warp gets one issue slot per round like everyone else, so a role that needs 5x
+// the instructions of the others per hand-over is the critical path.
 //
 // Shape of v3.  Persistent grid, one 512-thread CTA per SM.  A CTA owns a contiguous range of
-// "units" (receiver group, pass): a pass is SF = 32*NG*d1 consecutive frames of the block, i.e.
-// GO = 32*NG channel-rate outputs per receiver.
-//   * 10 MIXER warps (320 threads, J = SF/320 frames each).  The raw IQ of a unit is held in
-//     registers (loaded one unit ahead) and shared by the <= RB receivers of the group that
-//     listen to that stream.  Per (receiver, pass) the mixers fill one of S ring slots in shared
-//     memory: [A periods of halo | GO periods], period-major.  The halo -- the last A*d1 mixed
-//     frames of the receiver's previous pass -- never leaves the mixer threads that produced it:
-//     they keep it in registers and store it again into the next slot, so nothing is mixed twice
-//     and slots are self-contained.
-//   * S FIR warps, warp w owning slot w (every S-th pass): one thread per output over the taps in the
-//     reference's order (packed f32x2, products and sums rounded separately), samples and taps
-//     fetched two taps at a time with 128-bit loads.  With S-1 passes in flight every warp of the
-//     CTA has about the same number of instructions per pass, which is what a fair scheduler
-//     needs to keep all of them busy.
-//   * Slots are handed over with named barriers (full/empty per slot); a small descriptor per
-//     slot tells the FIR warp which receiver and which outputs it holds.
+// "units" (receiver group, pass): a pass is SF = 32*NG*d1 consecutive frames of the block
+// (~3200), i.e. GO = 32*NG channel-rate outputs per receiver.
+//   * The NCO correction table (wr_lo3.h, 132 KiB) is staged into shared memory by bulk copies
+//     (TMA) that complete on an mbarrier, behind the first group's set-up.
+//   * 10 MIXER warps (320 threads, J = SF/320 frames each).  The raw IQ of a pass is held in
+//     registers and shared by the <= RB receivers of the group that listen to that stream; a
+//     pass is mixed in two halves, and while the last receiver is mixed each half's registers
+//     are refilled with the next pass's frames.  Per (receiver, pass) the mixers fill one of S
+//     ring slots in shared memory: [A periods of halo | GO periods], period-major.  The halo --
+//     the last A*d1 mixed frames of the receiver's previous pass -- never leaves the mixer
+//     threads that produced it: they keep it in registers and store it again into the next
+//     slot, so nothing is mixed twice and slots are self-contained.
+//   * S*2 FIR warps, two per slot, each taking every second group of 32 outputs: one thread per
+//     output over the taps in the reference's order (packed f32x2, products and sums rounded
+//     separately), samples two per 128-bit load, taps four per 128-bit load and applied through
+//     the broadcast operand form.
+//   * Slots are handed over with mbarriers (full/empty per slot); a small descriptor per slot
+//     tells the FIR warps which receiver and which pass it holds.
+//   * Tuner blocks arrive as float IQ or as raw RTL-SDR bytes (converted in the load path).
+//   * Launched with programmatic stream serialization: only the FIR warps wait for the previous
+//     kernel in the stream (the demodulator of the block before).
 // NCO: the sine and cosine table entries of a frame are reconstructed TOGETHER in the two halves
 // of packed f32x2 registers (wr_lo3.h): one byte permute per entry builds the float index, ten
-// packed instructions produce both bases and both padded table positions.
+// packed instructions produce both bases and both padded table positions; written stage by stage
+// across the frames of a half pass so that the scheduler sees independent chains.
 #pragma once
 
 #include "wr_bank.cuh"
