@@ -536,3 +536,76 @@ def test_bank_v3_ragged_block_lengths(wro, geom, F):
     fs = 2400000
     R = 6
     run_bank_vs_oracle(wro, 3, fs, F, 2, synth.receiver_ifs(R, fs), [r % 4 for r in range(R)], n1, d1, n2, d2, 3, seed=11)
+
+
+# ------------------------------------------------------------------ BASELINE configs 3 and 5 at FULL size ----
+
+def _full_size_bank(w, taps_seed):
+    rng = np.random.default_rng(taps_seed)
+    R, T = w["n_rx"], w["n_streams"]
+    t1 = (rng.uniform(-1, 1, w["n1"]) / w["n1"] * 4).astype(np.float32)
+    t2 = (rng.uniform(-1, 1, w["n2"]) / w["n2"] * 4).astype(np.float32)
+    ifs, modes = synth.workload_ifs(w), synth.workload_modes(w)
+    bank = capi.Bank(T, R, w["frames"], w["n1"], w["d1"], w["n2"], w["d2"])
+    for r in range(R):
+        bank.set_taps(r, 0, t1)
+        bank.set_taps(r, 1, t2)
+        bank.set_if(r, int(ifs[r]), w["fs"])
+        bank.set_mode(r, int(modes[r]))
+        bank.set_stream(r, r % T)
+    return bank, t1, t2, ifs, modes
+
+
+def test_bank_cfg3_full_size(wro):
+    """BASELINE config 3 at FULL size: 1024 independent AM streams x 102400 frames, 255 taps, decim 50,
+    fed as raw bytes (210 MB per block on the host instead of 839 MB).  Two blocks.  Size-independent
+    property: streams 512..1023 repeat streams 0..511 and the receivers on them share IF and taps, so
+    their audio must be bit-identical; 6 receivers spread over the bank are checked against the oracle."""
+    w = synth.WORKLOADS["cfg3"]
+    R, T, F = w["n_rx"], w["n_streams"], w["frames"]
+    bank, t1, t2, ifs, modes = _full_size_bank(w, 31)
+    try:
+        for r in range(R // 2, R):
+            bank.set_if(r, int(ifs[r - R // 2]), w["fs"])
+        picks = [0, 1, 255, 511, 700, 1023]
+        orx = {r: wro.Rx(w["fs"], int(ifs[r % (R // 2)]), t1, w["d1"], int(modes[r]), t2, w["d2"]) for r in picks}
+        rng = np.random.default_rng(32)
+        for b in range(2):
+            half = rng.integers(0, 256, (T // 2, F, 2), dtype=np.uint8)
+            u8 = np.concatenate([half, half])
+            audio = bank.process_u8(u8)
+            assert audio.shape == (R, F // w["d1"] // w["d2"])
+            assert_biteq(audio[:R // 2], audio[R // 2:], f"twin streams, block {b}")
+            for r in picks:
+                assert_biteq(audio[r], orx[r].process(u8_to_iq(u8[r]).ravel()), f"cfg3 full rx{r} b{b}")
+            del u8, half
+        assert bank.variant_in_use() == 3
+    finally:
+        bank.close()
+
+
+def test_bank_cfg5_full_size(wro):
+    """BASELINE config 5, one GPU's share at FULL size: 16 tuners x 64 mixed-mode receivers, 409600-frame
+    blocks at 10 MSPS, 127 taps /40, 64 taps /5.  Two blocks; 12 receivers (all four modes, several
+    tuners) against the oracle, and the phase accumulators of all 1024 against the closed form."""
+    w = synth.WORKLOADS["cfg5"]
+    R, T, F = w["n_rx"], w["n_streams"], w["frames"]
+    bank, t1, t2, ifs, modes = _full_size_bank(w, 51)
+    try:
+        picks = [0, 1, 2, 3, 17, 130, 515, 516, 777, 1021, 1022, 1023]
+        orx = {r: wro.Rx(w["fs"], int(ifs[r]), t1, w["d1"], int(modes[r]), t2, w["d2"]) for r in picks}
+        rng = np.random.default_rng(52)
+        for b in range(2):
+            u8 = rng.integers(0, 256, (T, F, 2), dtype=np.uint8)
+            audio = bank.process_u8(u8)
+            for r in picks:
+                want = orx[r].process(u8_to_iq(u8[r % T]).ravel())
+                if int(modes[r]) == capi.FM:
+                    assert_fm(audio[r], want, f"cfg5 full rx{r} b{b}", audio=True)
+                else:
+                    assert_biteq(audio[r], want, f"cfg5 full rx{r} b{b}")
+        for r in range(0, R, 37):
+            assert bank.get_phase(r) == (capi.phase_step(int(ifs[r]), w["fs"]) * F * 2) & 0x7FFFFFFF
+        assert bank.variant_in_use() == 3
+    finally:
+        bank.close()
