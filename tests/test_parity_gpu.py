@@ -609,3 +609,29 @@ def test_bank_cfg5_full_size(wro):
         assert bank.variant_in_use() == 3
     finally:
         bank.close()
+
+
+def test_spectrum_cfg4_full_size(wro):
+    """BASELINE config 4 at FULL size: 8192-point transforms at hop 4096 over 256 streams of 528384 frames
+    (128 rows per stream, 32768 transforms, 1 GiB in, 1 GiB out).  Size-independent property: the 256
+    streams carry the same samples, so every stream's rows must be bit-identical to stream 0's; the first,
+    a middle and the last row of stream 0 are compared with the oracle at the north_star tolerance."""
+    n, hop, T = 8192, 4096, 256
+    F = hop * 129
+    base = synth.structured(F, 2400000, [300000, -700000, 15000], [0, 1, 2], noise_db=-40.0)
+    sp = capi.Spectrum(n, hop, T, max_frames=F)
+    try:
+        iq = np.ascontiguousarray(np.broadcast_to(base.reshape(1, F, 2), (T, F, 2)))
+        rows = sp.process(iq)
+        del iq
+        assert rows.shape == (T, 128, n)
+        ref0 = rows[0].view(np.uint32)
+        for t in range(1, T):
+            assert np.array_equal(rows[t].view(np.uint32), ref0), f"stream {t} differs from stream 0"
+        want = wro.Spectrum(n, hop).process(base)
+        assert want.shape[0] == 128
+        for m in (0, 63, 127):
+            spectrum_close(rows[0, m], want[m], f"cfg4 full row {m}")
+        spectrum_close(sp.get(T - 1), want[127], "getSpectrum of the last stream")
+    finally:
+        sp.close()
