@@ -44,6 +44,13 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 	return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
+{
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+
 __device__ __forceinline__ float2 view(const SpecArgs &a, unsigned t, size_t pos)
 {
 	if (pos < a.ncarry)
@@ -158,7 +165,9 @@ __global__ void __launch_bounds__(256, 2) spectrum_kernel_v2(const SpecArgs a)
 		#pragma unroll
 		for (int j = 0; j < R1; j++) {
 			const float w = __ldg(a.window + tid + 256u * j);
-			v[j] = make_float2(__fmul_rn(v[j].x, w), __fmul_rn(v[j].y, w)); // inbuf[n] *= window[n] (spectrumsink.cxx:110-113)
+			// inbuf[n] *= window[n] (spectrumsink.cxx:110-113): both components in one packed multiply
+			asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&v[j]))
+					: "l"(*reinterpret_cast<const unsigned long long*>(&v[j])), "l"(pack2(w, w)));
 		}
 		wrfft::RegDft<R1>::run(v);
 		// twiddle W_N^(tid * k1), built up from W_N^tid by repeated multiplication
@@ -210,10 +219,14 @@ __global__ void __launch_bounds__(256, 2) spectrum_kernel_v2(const SpecArgs a)
 			for (int kb = 0; kb < 16; kb++) {
 				const unsigned k = bf + R1 * 16 * kb;           // = k1 + R1 * (ka + 16 * kb)
 				const unsigned o = (k + N / 2) & (N - 1);        // fft-shift (spectrumsink.cxx:139)
-				const float p = __fadd_rn(__fmul_rn(u[kb].x, u[kb].x), __fmul_rn(u[kb].y, u[kb].y));
+				const float p = fmaf(u[kb].x, u[kb].x, u[kb].y * u[kb].y);
 				// 10*log10(p) = (10*log10(2)) * log2(p); the hardware log2 is good to ~1e-6 dB here,
-				// far inside the 1e-5 magnitude tolerance, and keeps log(0) = -inf
-				const float db = __fsub_rn(__fmul_rn(3.01029995663981195f, __log2f(p)), a.scaledb);
+				// far inside the 1e-5 magnitude tolerance, and keeps log(0) = -inf.  The .ftz form is
+				// one MUFU without the denormal rescue around it: a power below 1e-38 (-380 dB) reads
+				// as -inf, which the waterfall handler maps to its floor anyway.
+				float l2;
+				asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(p));
+				const float db = fmaf(3.01029995663981195f, l2, -a.scaledb);
 				if (rowout) rowout[o] = db;
 				if (last) last[o] = db;
 			}
