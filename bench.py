@@ -443,7 +443,8 @@ def gpu_arm(args, w, wname):
             "config": bench_config(w, wname, l2_note, args.input),
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "MSamples/s", "h2d_bytes_per_step": block_bytes,
-                    "d2h_bytes_per_step": 4 * R * M2, "steps": esteps, "mode": f"pipelined depth {depth}",
+                    "d2h_bytes_per_step": 4 * R * M2, "steps": esteps,
+                    "mode": f"pipelined depth {depth}, copy-in hand-over by a counter in HBM the channel kernel waits on",
                     "sync_value": e2e_sync_value},
             "gpu_launches": launches,
             "roofline": roofline,

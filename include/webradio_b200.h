@@ -139,11 +139,31 @@ int wr_bank_process_device(wr_bank *b, const float *iq_dev, size_t stream_stride
 
 /* Pipelined host path: enqueue one block (H2D copy, kernels, D2H copy all asynchronous, from
  * / into caller-owned PINNED buffers) and wait for the oldest outstanding one.  Up to
- * wr_bank_pipeline_depth() blocks may be in flight. */
+ * wr_bank_pipeline_depth() blocks may be in flight; a caller must not touch a block's buffers
+ * between its wr_bank_submit and the wr_bank_wait that returns it. */
 int wr_bank_submit(wr_bank *b, const float *iq_pinned, unsigned nframes,
 		float *audio_pinned, size_t audio_stride);
 int wr_bank_wait(wr_bank *b);
 int wr_bank_pipeline_depth(const wr_bank *b);
+/* How a block travels between the copy-in stream, the two kernels and the host on the pipelined
+ * path (v3 channel kernel; the v1/v2 kernels always use events):
+ *   WR_HANDOVER_FLAGS  (default) the copy-in stream raises a counter in HBM behind the tuner block
+ *                      (a stream memory operation; a 4-byte copy on drivers without them) and the
+ *                      channel kernel's loaders wait for it.  The launch stream holds nothing but
+ *                      kernels and event records, so consecutive blocks overlap as they do on the
+ *                      device-resident path (a cudaStreamWaitEvent in front of the channel kernel
+ *                      costs that overlap: measured, ~6 us per 22 us block).  The audio leaves
+ *                      through an event and a copy on the copy-out stream;
+ *   WR_HANDOVER_EVENTS CUDA events in both directions;
+ *   WR_HANDOVER_DIRECT flags in; out, the demodulator kernel stores the audio straight into the
+ *                      caller's pinned buffer and its last CTA raises a counter in mapped host
+ *                      memory that wr_bank_wait polls (no copy-out stream at all: lowest latency
+ *                      for one block at a time, but the kernel then runs at PCIe write speed).
+ * Returns the scheme, or a negative WR_E* code.  Call it with no blocks in flight. */
+#define WR_HANDOVER_EVENTS 0
+#define WR_HANDOVER_FLAGS  1
+#define WR_HANDOVER_DIRECT 2
+int wr_bank_set_handover(wr_bank *b, int scheme);
 
 /* Host-language loop helpers (what a C++ caller would write itself; they keep interpreter
  * overhead out of bench.py's timed regions).  Step i uses iq[(first + i) % n_iq] and

@@ -263,38 +263,64 @@ def test_bank_state_reset_and_retune(wro, variant):
             assert_biteq(bank.process(iq)[0], rx.process(iq), f"after reset b{b}")
 
 
-def test_bank_pipelined_submit_equals_sync(wro):
+@pytest.mark.parametrize("scheme", [1, 0, 2], ids=["flags", "events", "direct"])
+@pytest.mark.parametrize("geo", ["64/10", "127/50"])
+def test_bank_pipelined_submit_equals_sync(wro, scheme, geo):
+    """wr_bank_submit / wr_bank_wait with the pipeline kept full == one synchronous wr_bank_process per
+    block, bit for bit, under every hand-over scheme (a counter in HBM the channel kernel waits on;
+    CUDA events; audio stored by the kernel straight into the pinned buffer) and across more blocks than there are slots."""
     import torch
-    fs, F, R = 2400000, 20000, 8
+    fs, R = 2400000, 8
+    if geo == "64/10":
+        F, n1, d1, n2, d2 = 20000, 64, 10, 64, 5
+        taps1 = wro.lowpass_design(64, 80000, fs)
+        taps2 = wro.lowpass_design(64, 8000, 240000)
+        modes = [r % 4 for r in range(R)]
+    else:
+        F, n1, d1, n2, d2 = 25600, 127, 50, 64, 1
+        rng = np.random.default_rng(5)
+        taps1 = (rng.standard_normal(n1) / n1).astype(np.float32)
+        taps2 = wro.lowpass_design(64, 8000, 48000)
+        modes = [1] * R
     ifs = synth.receiver_ifs(R, fs)
-    taps1 = wro.lowpass_design(64, 80000, fs)
-    taps2 = wro.lowpass_design(64, 8000, 240000)
 
     def setup():
-        b = capi.Bank(1, R, F, 64, 10, 64, 5)
+        b = capi.Bank(1, R, F, n1, d1, n2, d2)
         for r in range(R):
             b.set_taps(r, 0, taps1)
             b.set_taps(r, 1, taps2)
             b.set_if(r, int(ifs[r]), fs)
-            b.set_mode(r, r % 4 if r % 4 != 1 else 0)
+            b.set_mode(r, modes[r])
         return b
 
-    blocks = [synth.lattice_noise(F, stream=1, start=i * F) for i in range(7)]
+    nblocks = 23
+    blocks = [synth.lattice_noise(F, stream=1, start=i * F) for i in range(nblocks)]
     with setup() as b1:
         want = [b1.process(x).copy() for x in blocks]
-    m2 = F // 10 // 5
+    m2 = F // d1 // d2
     with setup() as b2:
+        got_scheme = b2.set_handover(scheme)
+        assert got_scheme == scheme
         pin_in = [torch.from_numpy(x.copy()).pin_memory() for x in blocks]
         pin_out = [torch.zeros(R, m2).pin_memory() for _ in blocks]
         depth = b2.pipeline_depth()
+        assert depth >= 2
         for i in range(len(blocks)):
             if i >= depth:
                 b2.wait()
             b2.submit(pin_in[i].data_ptr(), F, pin_out[i].data_ptr(), m2)
         for _ in range(min(depth, len(blocks))):
             b2.wait()
+        assert b2.variant_in_use() == 3
         for i in range(len(blocks)):
-            assert_biteq(pin_out[i].numpy(), want[i], f"pipelined block {i}")
+            assert_biteq(pin_out[i].numpy(), want[i], f"pipelined block {i} (hand-over scheme {got_scheme})")
+        # the C-side loop helper takes the same path
+        outs = [torch.zeros(R, m2).pin_memory() for _ in range(depth + 1)]
+    with setup() as b3:
+        b3.set_handover(scheme)
+        b3.run_host_steps([x.data_ptr() for x in pin_in], F, [y.data_ptr() for y in outs], m2, 0, nblocks, pipelined=True)
+        last = (nblocks - 1) % len(outs)
+        assert_biteq(outs[last].numpy(), want[nblocks - 1], "run_host_steps last block")
 
 
 def test_bank_device_resident_path(wro):

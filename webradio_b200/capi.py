@@ -29,7 +29,7 @@ SYMBOLS = [
     "wr_bank_process", "wr_bank_process_device", "wr_bank_submit", "wr_bank_wait",
     "wr_bank_process_u8", "wr_bank_process_device_u8", "wr_bank_submit_u8",
     "wr_bank_run_device_steps_u8", "wr_bank_run_host_steps_u8",
-    "wr_bank_pipeline_depth", "wr_bank_run_device_steps", "wr_bank_run_host_steps", "wr_bank_stream", "wr_bank_sync", "wr_bank_keep_channel",
+    "wr_bank_pipeline_depth", "wr_bank_set_handover", "wr_bank_run_device_steps", "wr_bank_run_host_steps", "wr_bank_stream", "wr_bank_sync", "wr_bank_keep_channel",
     "wr_bank_read_stage", "wr_bank_set_audio_format", "wr_bank_set_variant", "wr_bank_variant_in_use", "wr_bank_launch_count", "wr_bank_set_timing",
     "wr_bank_kernel_times",
     "wr_stage_create", "wr_stage_destroy", "wr_stage_mix", "wr_stage_fir_config", "wr_stage_fir",
@@ -95,6 +95,7 @@ def lib():
     L.wr_bank_read_stage.restype = C.c_long
     L.wr_bank_read_stage.argtypes = [vp, u, i, _fp, sz]
     L.wr_bank_set_variant.argtypes = [vp, i]
+    L.wr_bank_set_handover.argtypes = [vp, i]
     L.wr_bank_variant_in_use.argtypes = [vp]
     L.wr_bank_launch_count.restype = C.c_ulonglong
     L.wr_bank_launch_count.argtypes = [vp]
@@ -301,6 +302,10 @@ class Bank:
 
     def set_audio_format(self, fmt):
         _check(self.L.wr_bank_set_audio_format(self.h, fmt), "wr_bank_set_audio_format")
+
+    def set_handover(self, scheme):
+        """0 = CUDA events, 1 = counter in HBM in / event out (default), 2 = counter in / audio stored by the kernel into the pinned buffer."""
+        return _check(self.L.wr_bank_set_handover(self.h, scheme), "wr_bank_set_handover")
 
     def set_variant(self, v):
         _check(self.L.wr_bank_set_variant(self.h, v), "wr_bank_set_variant")

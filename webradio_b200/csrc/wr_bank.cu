@@ -6,9 +6,13 @@
 #include "wr_kernels_v2.cuh"
 #include "wr_kernels_v3.cuh"
 
+#include <cuda.h>        // types of the two stream memory operations; the entry points are looked up at run time
+
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <vector>
 
@@ -21,7 +25,7 @@ using wrd::RxState;
 
 namespace {
 
-constexpr int kSlots = 3;        // pipeline depth of the submit/wait path
+constexpr int kSlots = 6;        // most blocks the submit/wait path keeps in flight
 constexpr int kThreadsV1 = 128;
 
 constexpr unsigned kSetPhase = 0x100u; // internal flag: overwrite the phase with a given value
@@ -80,18 +84,70 @@ __global__ void design_kernel(const double *__restrict__ costab, const float *__
 	}
 }
 
+// Stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32), fetched through the
+// runtime so that the library does not link against libcuda: the copy streams of the pipelined
+// host path signal and wait through two words in HBM instead of events on the launch stream.
+typedef CUresult (*StreamValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+
+struct StreamOps {
+	StreamValueFn write = nullptr, wait = nullptr;
+	bool ok = false;
+};
+
+const StreamOps &stream_ops()
+{
+	static const StreamOps ops = [] {
+		StreamOps o;
+		const char *e = getenv("WR_FLAG_SYNC");
+		if (e && atoi(e) == 0)
+			return o;
+		cudaDriverEntryPointQueryResult q1, q2;
+		void *w = nullptr, *a = nullptr;
+		if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &q1) == cudaSuccess
+				&& cudaGetDriverEntryPoint("cuStreamWaitValue32", &a, cudaEnableDefault, &q2) == cudaSuccess
+				&& q1 == cudaDriverEntryPointSuccess && q2 == cudaDriverEntryPointSuccess && w && a) {
+			o.write = reinterpret_cast<StreamValueFn>(w);
+			o.wait = reinterpret_cast<StreamValueFn>(a);
+			o.ok = true;
+		}
+		cudaGetLastError();
+		return o;
+	}();
+	return ops;
+}
+
+// How a block is handed from the copy-in stream to the channel kernel and from the demodulator
+// kernel to the host.
+enum { IN_EVENT = 0, IN_FLAG = 1, IN_COPYFLAG = 2 };     // event | stream write-value | a 4-byte copy behind the block
+enum { OUT_EVENT = 0, OUT_FLAG = 1, OUT_DIRECT = 2 };    // event + copy | stream wait-value + copy | the kernel stores into the pinned buffer
+
 struct Slot {
 	float *d_iq = nullptr;      // [T][maxF][2] (float blocks) or the same bytes holding raw u8 blocks
 	float *d_audio = nullptr;   // [R][maxM2]
 	cudaEvent_t in_ready = nullptr, done = nullptr, out_ready = nullptr;
 	bool busy = false;
 	bool used = false;
+	unsigned seq = 0;
+	int outMode = OUT_EVENT;
 };
+
+inline unsigned long long host_ns()
+{
+	timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
+
+constexpr unsigned kTraceBlocks = 4096;
+// WR_TRACE_CTA=<file>: {start, end} of every CTA of both kernels for a few blocks
+constexpr unsigned kCtaTraceBlocks = 6, kCtaTraceChan = 256, kCtaTraceDemod = 4096;
+constexpr int kSeqRing = 64;
 
 } // namespace
 
 struct wr_bank {
 	int device = 0;
+	int numSMs = 148;
 	unsigned T = 0, R = 0, maxF = 0, n1 = 0, d1 = 0, n2 = 0, d2 = 0;
 	unsigned maxM1 = 0, maxM2 = 0;
 	size_t dstride = 0;
@@ -103,7 +159,8 @@ struct wr_bank {
 	RxState *d_state[2] = { nullptr, nullptr };
 	float2 *d_hist1[2] = { nullptr, nullptr };
 	float *d_demod[2] = { nullptr, nullptr };
-	float2 *d_chan = nullptr;
+	float2 *d_chan = nullptr;   // [2][R][maxM1]: consecutive blocks alternate, so that a block's channel kernel can run under the previous block's demodulator
+	int chanSide = 0;           // side the last block wrote
 	float *d_iqf = nullptr;     // scratch: a u8 tuner block converted for the v1/v2 kernels
 	int cur = 0;
 	unsigned lastM1 = 0, lastM2 = 0;
@@ -126,7 +183,26 @@ struct wr_bank {
 	cudaEvent_t stagingFree = nullptr;
 
 	Slot slot[kSlots];
+	int depth = kSlots;         // slots in use: as many as fit a few GB of HBM
 	int head = 0, tail = 0, inflight = 0;
+	// hand-over of the pipelined host path: d_sync = {blocks copied in, blocks demodulated, CTA count}
+	unsigned *d_sync = nullptr;
+	unsigned *h_err = nullptr;  // mapped host words: [0] a missed hand-over reported by the kernels, [1] blocks whose audio the demodulator kernel stored into host memory
+	unsigned *p_seq = nullptr;  // pinned ring of sequence numbers (source of the IN_COPYFLAG copies)
+	unsigned seq = 0;           // blocks submitted through wr_bank_submit
+	int handIn = IN_EVENT, handOut = OUT_EVENT;
+	unsigned pollNs = 1000;     // WR_POLL_NS: pause between two looks of the channel kernel at the copy-in counter
+	int waitLate = 1;           // WR_WAIT_LATE: the channel kernel runs under the previous block's demodulator kernel
+	// the device address of a pinned output buffer (OUT_DIRECT): small cache of the runtime's answer
+	struct HostMap { const void *host; void *dev; size_t bytes; } hostMap[8] = {};
+	int hostMapNext = 0;
+	// WR_TRACE=<file>: per-block device and host timestamps, dumped when the bank is destroyed
+	const char *tracePath = nullptr;
+	unsigned long long *d_ts = nullptr;
+	unsigned long long *d_cta = nullptr;
+	const char *ctaPath = nullptr;
+	unsigned ctaFirst = 300;    // WR_TRACE_CTA_FIRST: first traced block
+	std::vector<unsigned long long> hostTs;   // {submit entered, submit returned, wait returned} per block
 
 	int variant = 0;
 	int variantInUse = 0;
@@ -230,8 +306,53 @@ unsigned pick_tk_v1(unsigned n1, unsigned d1)
 	return tk;
 }
 
+// The hand-over scheme a bank starts with (WR_HAND_IN / WR_HAND_OUT override it, for experiments).
+void default_handover(wr_bank *b)
+{
+	b->handIn = stream_ops().ok ? IN_FLAG : IN_COPYFLAG;
+	b->handOut = OUT_EVENT;
+	if (const char *e = getenv("WR_HAND_IN"))
+		b->handIn = std::min(std::max(atoi(e), 0), 2);
+	if (const char *e = getenv("WR_HAND_OUT"))
+		b->handOut = std::min(std::max(atoi(e), 0), 2);
+	if (!stream_ops().ok) {
+		if (b->handIn == IN_FLAG) b->handIn = IN_COPYFLAG;
+		if (b->handOut == OUT_FLAG) b->handOut = OUT_EVENT;
+	}
+}
+
+// device address of a caller's pinned buffer, or nullptr if the device cannot address it
+void *device_view(wr_bank *b, const void *host, size_t bytes)
+{
+	for (auto &m : b->hostMap)
+		if (m.host == host && m.bytes >= bytes)
+			return m.dev;
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, host) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	// the whole range must be pinned: ask about its last byte too
+	cudaPointerAttributes at2;
+	if (bytes > 1 && (cudaPointerGetAttributes(&at2, static_cast<const char*>(host) + bytes - 1) != cudaSuccess
+			|| at2.type != cudaMemoryTypeHost || !at2.devicePointer)) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	auto &m = b->hostMap[b->hostMapNext];
+	b->hostMapNext = (b->hostMapNext + 1) % 8;
+	m.host = host; m.dev = at.devicePointer; m.bytes = bytes;
+	return m.dev;
+}
+
+// can this block go through the v3 channel kernel (the one that knows the flag hand-over)?
+bool block_uses_v3(const wr_bank *b, unsigned F)
+{
+	return (b->variant == 3 || b->variant == 0) && wrd::v3_supported(b->v3, F);
+}
+
 int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, unsigned F,
-		float *audio_dev, size_t audio_stride, cudaStream_t st)
+		float *audio_dev, size_t audio_stride, cudaStream_t st, unsigned seq = 0, int handIn = IN_EVENT, int handOut = OUT_EVENT)
 {
 	int rc = apply_pending(b, st);
 	if (rc != WR_OK)
@@ -248,7 +369,7 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 		WR_CUDA(cudaEventRecord(tev[0], st));
 	}
 
-	const bool useV3 = (b->variant == 3 || b->variant == 0) && wrd::v3_supported(b->v3, F);
+	const bool useV3 = block_uses_v3(b, F);
 	if (b->variant == 3 && !useV3) {
 		wr::set_error("v3 kernels do not support this geometry (n1=%u d1=%u, %u frames)", b->n1, b->d1, F);
 		return WR_EINVAL;
@@ -259,7 +380,8 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 		return WR_EINVAL;
 	}
 	if (useV2 && !b->d_chan)
-		WR_CUDA(cudaMalloc(&b->d_chan, sizeof(float2) * (size_t)b->R * std::max(1u, b->maxM1)));
+		WR_CUDA(cudaMalloc(&b->d_chan, 2 * sizeof(float2) * (size_t)b->R * std::max(1u, b->maxM1)));
+	float2 *const chanBuf = b->d_chan ? b->d_chan + (size_t)cur * b->R * std::max(1u, b->maxM1) : nullptr;
 	if (u8 && !useV3) {
 		// the older kernel families read float blocks: convert once into a scratch block
 		if (!b->d_iqf)
@@ -287,12 +409,22 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 	ca.demod = b->d_demod[cur];
 	ca.dstride = b->dstride;
 	ca.demod_off = b->n2 - 1;
-	ca.chan = (b->keepChan || useV2) ? b->d_chan : nullptr; // v2 always materialises the channel stream
+	ca.chan = (b->keepChan || useV2) ? chanBuf : nullptr; // v2 always materialises the channel stream
 	ca.chan_stride = b->maxM1;
 	ca.F = F;
 	ca.M1 = M1;
 	ca.n1 = b->n1;
 	ca.d1 = b->d1;
+	ca.in_flag = handIn != IN_EVENT ? b->d_sync + 0 : nullptr;
+	ca.in_seq = seq;
+	ca.err = b->h_err;
+	unsigned long long *ts = (b->d_ts && seq && seq <= kTraceBlocks) ? b->d_ts + (size_t)(seq - 1) * wrd::kTsWords : nullptr;
+	ca.ts = ts;
+	unsigned long long *cta_ts = (b->d_cta && seq >= b->ctaFirst && seq < b->ctaFirst + kCtaTraceBlocks)
+			? b->d_cta + (size_t)(seq - b->ctaFirst) * 2 * (kCtaTraceChan + kCtaTraceDemod) : nullptr;
+	ca.cta_ts = cta_ts;
+	ca.wait_late = b->waitLate;
+	ca.poll_ns = b->pollNs;
 
 	if (useV3) {
 		rc = wrd::v3_launch_chan(b->v3, ca, u8, st, &b->launches);
@@ -318,7 +450,7 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 	if (useV2) {
 		// demodulator + audio FIR over the channel-rate IQ the v2 kernel wrote
 		wrd::DemodAudioArgs da;
-		da.chan = b->d_chan;
+		da.chan = chanBuf;
 		da.chan_stride = b->maxM1;
 		da.conf = b->d_conf;
 		da.st_in = b->d_state[cur];
@@ -341,20 +473,28 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 			da.TK /= 2;
 		da.ntiles = (M2 + da.TK - 1) / da.TK;
 		da.out_scale = b->outScale;
+		da.done_count = (handOut != OUT_EVENT || ts) ? b->d_sync + 2 : nullptr;
+		da.done_flag = handOut == OUT_FLAG ? b->d_sync + 1 : nullptr;
+		da.host_done = handOut == OUT_DIRECT ? b->h_err + 1 : nullptr;
+		da.done_seq = seq;
+		da.ts = ts;
+		da.cta_ts = cta_ts ? cta_ts + 2 * kCtaTraceChan : nullptr;
 		size_t lmax = (size_t)da.TK * b->d2 + b->n2 - 1;
 		size_t smem = sizeof(float) * (((lmax + 3) & ~(size_t)3) + b->n2);
 		dim3 grid(da.ntiles + 1, b->R);
+		if (cta_ts && (size_t)grid.x * grid.y > kCtaTraceDemod)
+			da.cta_ts = nullptr;
 		cudaLaunchConfig_t cfg = {};
 		cudaLaunchAttribute attr[1];
 		cfg.gridDim = grid;
-		cfg.blockDim = dim3(kThreadsV1);
+		cfg.blockDim = dim3(wrd::kDemodThreads);
 		cfg.dynamicSmemBytes = smem;
 		cfg.stream = st;
 		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 		attr[0].val.programmaticStreamSerializationAllowed = 1;
 		cfg.attrs = attr;
 		cfg.numAttrs = (useV3 && b->v3.pdl) ? 1 : 0;   // the v3 channel kernel releases its dependents early
-		WR_CUDA(cudaLaunchKernelEx(&cfg, wrd::demod_audio_kernel_v2<kThreadsV1>, (const wrd::DemodAudioArgs)da));
+		WR_CUDA(cudaLaunchKernelEx(&cfg, wrd::demod_audio_kernel_v2<wrd::kDemodThreads>, (const wrd::DemodAudioArgs)da));
 		b->launches++;
 	} else {
 		wrd::AudioArgs aa;
@@ -385,6 +525,7 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 	}
 
 	b->variantInUse = useV3 ? 3 : useV2 ? 2 : 1;
+	b->chanSide = cur;
 	b->cur = nxt;
 	b->lastM1 = M1;
 	b->lastM2 = M2;
@@ -415,6 +556,44 @@ void free_bank(wr_bank *b)
 	}
 	cudaFree(b->d_chan);
 	cudaFree(b->d_iqf);
+	if (b->tracePath && b->d_ts) {
+		const unsigned n = std::min(b->seq, kTraceBlocks);
+		std::vector<unsigned long long> dev((size_t)n * wrd::kTsWords);
+		if (n && cudaMemcpy(dev.data(), b->d_ts, dev.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+			if (FILE *f = fopen(b->tracePath, "a")) {
+				fprintf(f, "# bank R=%u T=%u F=%u in=%d out=%d depth=%d\n", b->R, b->T, b->maxF, b->handIn, b->handOut, b->depth);
+				fprintf(f, "seq,host_submit,host_submitted,host_waited,chan_start,chan_input,chan_end,demod_start,demod_end\n");
+				for (unsigned i = 0; i < n; i++) {
+					const unsigned long long *d = dev.data() + (size_t)i * wrd::kTsWords;
+					fprintf(f, "%u,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu\n", i + 1, b->hostTs[3 * i], b->hostTs[3 * i + 1], b->hostTs[3 * i + 2],
+							d[wrd::kTsChanStart], d[wrd::kTsChanInput], d[wrd::kTsChanEnd], d[wrd::kTsDemodStart], d[wrd::kTsDemodEnd]);
+				}
+				fclose(f);
+			}
+		}
+	}
+	if (b->ctaPath && b->d_cta) {
+		const size_t words = (size_t)2 * (kCtaTraceChan + kCtaTraceDemod) * kCtaTraceBlocks;
+		std::vector<unsigned long long> dev(words);
+		if (cudaMemcpy(dev.data(), b->d_cta, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+			if (FILE *f = fopen(b->ctaPath, "a")) {
+				fprintf(f, "# bank R=%u T=%u F=%u\nblock,kernel,cta,start,end\n", b->R, b->T, b->maxF);
+				for (unsigned blk = 0; blk < kCtaTraceBlocks; blk++) {
+					const unsigned long long *d = dev.data() + (size_t)blk * 2 * (kCtaTraceChan + kCtaTraceDemod);
+					for (unsigned c = 0; c < kCtaTraceChan + kCtaTraceDemod; c++)
+						if (d[2 * c])
+							fprintf(f, "%u,%s,%u,%llu,%llu\n", b->ctaFirst + blk, c < kCtaTraceChan ? "chan" : "demod",
+									c < kCtaTraceChan ? c : c - kCtaTraceChan, d[2 * c], d[2 * c + 1]);
+				}
+				fclose(f);
+			}
+		}
+	}
+	cudaFree(b->d_cta);
+	cudaFree(b->d_ts);
+	cudaFree(b->d_sync);
+	cudaFreeHost(b->h_err);
+	cudaFreeHost(b->p_seq);
 	cudaFreeHost(b->p_conf);
 	cudaFreeHost(b->p_taps1);
 	cudaFreeHost(b->p_taps2);
@@ -471,6 +650,7 @@ wr_bank *wr_bank_create(int device, unsigned n_streams, unsigned n_receivers, un
 	b->dstride = ((size_t)(n2 - 1) + b->maxM1 + 3) & ~(size_t)3;
 	const unsigned R = n_receivers;
 
+	WR_BANK_ALLOC(cudaDeviceGetAttribute(&b->numSMs, cudaDevAttrMultiProcessorCount, device));
 	WR_BANK_ALLOC(cudaStreamCreateWithFlags(&b->compute, cudaStreamNonBlocking));
 	WR_BANK_ALLOC(cudaStreamCreateWithFlags(&b->h2d, cudaStreamNonBlocking));
 	WR_BANK_ALLOC(cudaStreamCreateWithFlags(&b->d2h, cudaStreamNonBlocking));
@@ -493,6 +673,35 @@ wr_bank *wr_bank_create(int device, unsigned n_streams, unsigned n_receivers, un
 	WR_BANK_ALLOC(cudaMallocHost(&b->p_taps1, sizeof(float) * (size_t)R * n1));
 	WR_BANK_ALLOC(cudaMallocHost(&b->p_taps2, sizeof(float) * (size_t)R * n2));
 	WR_BANK_ALLOC(cudaMallocHost(&b->p_table, sizeof(float) * WR_SINTABLE_SIZE));
+	WR_BANK_ALLOC(cudaMalloc(&b->d_sync, sizeof(unsigned) * 4));
+	WR_BANK_ALLOC(cudaMemset(b->d_sync, 0, sizeof(unsigned) * 4));
+	WR_BANK_ALLOC(cudaHostAlloc(&b->h_err, sizeof(unsigned) * 2, cudaHostAllocMapped));
+	b->h_err[0] = b->h_err[1] = 0;
+	WR_BANK_ALLOC(cudaMallocHost(&b->p_seq, sizeof(unsigned) * kSeqRing));
+	default_handover(b);
+	if (const char *e = getenv("WR_POLL_NS"))
+		b->pollNs = (unsigned)atoi(e);
+	if (const char *e = getenv("WR_WAIT_LATE"))
+		b->waitLate = atoi(e) != 0;
+	if ((b->tracePath = getenv("WR_TRACE")) != nullptr) {
+		WR_BANK_ALLOC(cudaMalloc(&b->d_ts, sizeof(unsigned long long) * wrd::kTsWords * kTraceBlocks));
+		WR_BANK_ALLOC(cudaMemset(b->d_ts, 0, sizeof(unsigned long long) * wrd::kTsWords * kTraceBlocks));
+		b->hostTs.assign((size_t)3 * kTraceBlocks, 0);
+		if (const char *e = getenv("WR_TRACE_CTA_FIRST"))
+			b->ctaFirst = (unsigned)atoi(e);
+		if ((b->ctaPath = getenv("WR_TRACE_CTA")) != nullptr) {
+			const size_t n = sizeof(unsigned long long) * 2 * (kCtaTraceChan + kCtaTraceDemod) * kCtaTraceBlocks;
+			WR_BANK_ALLOC(cudaMalloc(&b->d_cta, n));
+			WR_BANK_ALLOC(cudaMemset(b->d_cta, 0, n));
+		}
+	}
+	{
+		// pipeline depth: what the chain copy-in -> two kernels -> copy-out needs to stay full on
+		// small blocks, bounded by ~6 GB of staging for large ones
+		const size_t slotBytes = sizeof(float) * 2 * (size_t)n_streams * max_frames + sizeof(float) * (size_t)R * std::max(1u, b->maxM2);
+		const size_t fit = ((size_t)6 << 30) / std::max<size_t>(1, slotBytes);
+		b->depth = (int)std::max<size_t>(2, std::min<size_t>(kSlots, fit));
+	}
 	for (int i = 0; i < kSlots; i++) {
 		WR_BANK_ALLOC(cudaEventCreateWithFlags(&b->slot[i].in_ready, cudaEventDisableTiming));
 		WR_BANK_ALLOC(cudaEventCreateWithFlags(&b->slot[i].done, cudaEventDisableTiming));
@@ -681,7 +890,7 @@ static int process_device_any(wr_bank *b, const void *iq_dev, bool u8, size_t st
 	if (!wr::use_device(b->device))
 		return WR_ENODEV;
 	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->compute;
-	return launch_block(b, iq_dev, u8, stream_stride_frames, nframes, audio_dev, audio_stride, st);
+	return launch_block(b, iq_dev, u8, stream_stride_frames, nframes, audio_dev, audio_stride, st, b->d_ts ? ++b->seq : 0);
 }
 
 int wr_bank_process_device(wr_bank *b, const float *iq_dev, size_t stream_stride_frames,
@@ -700,41 +909,94 @@ static int submit_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframes
 {
 	WR_REQUIRE(b && iq_host && audio_host, WR_EINVAL, "wr_bank_submit: null argument");
 	WR_REQUIRE(nframes <= b->maxF, WR_EINVAL, "wr_bank_submit: %u frames > max_frames %u", nframes, b->maxF);
-	WR_REQUIRE(b->inflight < kSlots, WR_ESTATE, "wr_bank_submit: %d blocks already in flight", b->inflight);
+	WR_REQUIRE(b->inflight < b->depth, WR_ESTATE, "wr_bank_submit: %d blocks already in flight", b->inflight);
 	if (!wr::use_device(b->device))
 		return WR_ENODEV;
+	const unsigned long long t_enter = b->d_ts ? host_ns() : 0;
 	Slot &s = b->slot[b->head];
 	if (!s.d_iq) {
 		WR_CUDA(cudaMalloc(&s.d_iq, sizeof(float) * 2 * (size_t)b->T * b->maxF));
 		WR_CUDA(cudaMalloc(&s.d_audio, sizeof(float) * (size_t)b->R * std::max(1u, b->maxM2)));
 	}
 	const unsigned M2 = nframes / b->d1 / b->d2;
+	const unsigned maxM2 = std::max(1u, b->maxM2);
 	const size_t fb = u8 ? 2 : sizeof(float) * 2;   // bytes per frame on the wire and in HBM
-	// H2D: must not overwrite the slot's tuner block before the kernels of its previous use ran
-	if (s.used)
-		WR_CUDA(cudaStreamWaitEvent(b->h2d, s.done, 0));
-	WR_CUDA(cudaMemcpy2DAsync(s.d_iq, fb * (size_t)b->maxF, iq_host, fb * (size_t)nframes,
-			fb * (size_t)nframes, b->T, cudaMemcpyHostToDevice, b->h2d));
-	WR_CUDA(cudaEventRecord(s.in_ready, b->h2d));
-	// compute: after the copy in, and after the previous read-out of this slot's audio buffer
-	WR_CUDA(cudaStreamWaitEvent(b->compute, s.in_ready, 0));
-	if (s.used)
-		WR_CUDA(cudaStreamWaitEvent(b->compute, s.out_ready, 0));
-	int rc = launch_block(b, s.d_iq, u8, b->maxF, nframes, s.d_audio, std::max(1u, b->maxM2), b->compute);
+	// A slot is reused only after wr_bank_wait returned for the block that held it (inflight <
+	// depth = the number of slots), i.e. after its kernels and its copy out completed: the host's
+	// own order protects the slot buffers under every hand-over scheme below.
+	//
+	// Hand-over without events (v3 channel kernel): nothing but the two kernels goes into the
+	// launch stream, so consecutive blocks keep their programmatic overlap.
+	//   in : the copy-in stream raises a counter in HBM behind the tuner block (a stream memory
+	//        operation, or a 4-byte copy) and the channel kernel's loaders wait for it;
+	//   out: the demodulator kernel stores the audio straight into the caller's pinned buffer and
+	//        its last CTA raises a counter in mapped host memory that wr_bank_wait polls -- or it
+	//        raises a counter in HBM that the copy-out stream waits for.
+	// Hand-over by events (other kernel families): events between the three streams.
+	const bool v3 = block_uses_v3(b, nframes);
+	int handIn = v3 ? b->handIn : IN_EVENT, handOut = v3 ? b->handOut : OUT_EVENT;
+	float *audio_dev = s.d_audio;
+	size_t audio_dev_stride = maxM2;
+	if (handOut == OUT_DIRECT) {
+		void *dv = M2 ? device_view(b, audio_host, sizeof(float) * ((size_t)(b->R - 1) * audio_stride + M2)) : nullptr;
+		if (dv) {
+			audio_dev = static_cast<float*>(dv);
+			audio_dev_stride = audio_stride;
+		} else {
+			handOut = stream_ops().ok ? OUT_FLAG : OUT_EVENT;   // pageable or foreign memory: copy it out
+		}
+	}
+	const unsigned seq = ++b->seq;
+	if (nframes == b->maxF || b->T == 1)
+		WR_CUDA(cudaMemcpyAsync(s.d_iq, iq_host, fb * (size_t)nframes * b->T, cudaMemcpyHostToDevice, b->h2d));
+	else
+		WR_CUDA(cudaMemcpy2DAsync(s.d_iq, fb * (size_t)b->maxF, iq_host, fb * (size_t)nframes,
+				fb * (size_t)nframes, b->T, cudaMemcpyHostToDevice, b->h2d));
+	if (handIn == IN_FLAG) {
+		if (stream_ops().write((CUstream)b->h2d, (CUdeviceptr)(uintptr_t)(b->d_sync + 0), seq, 0) != CUDA_SUCCESS) {
+			wr::set_error("wr_bank_submit: cuStreamWriteValue32 failed");
+			return WR_ECUDA;
+		}
+	} else if (handIn == IN_COPYFLAG) {
+		// the ring entry is free again: depth < kSeqRing blocks can be in flight
+		b->p_seq[seq % kSeqRing] = seq;
+		WR_CUDA(cudaMemcpyAsync(b->d_sync + 0, b->p_seq + seq % kSeqRing, sizeof(unsigned), cudaMemcpyHostToDevice, b->h2d));
+	} else {
+		WR_CUDA(cudaEventRecord(s.in_ready, b->h2d));
+		WR_CUDA(cudaStreamWaitEvent(b->compute, s.in_ready, 0));
+	}
+	int rc = launch_block(b, s.d_iq, u8, b->maxF, nframes, audio_dev, audio_dev_stride, b->compute, seq, handIn, handOut);
 	if (rc != WR_OK)
 		return rc;
-	WR_CUDA(cudaEventRecord(s.done, b->compute));
-	// D2H
-	WR_CUDA(cudaStreamWaitEvent(b->d2h, s.done, 0));
-	if (M2 > 0)
-		WR_CUDA(cudaMemcpy2DAsync(audio_host, sizeof(float) * audio_stride,
-				s.d_audio, sizeof(float) * std::max(1u, b->maxM2),
-				sizeof(float) * M2, b->R, cudaMemcpyDeviceToHost, b->d2h));
-	WR_CUDA(cudaEventRecord(s.out_ready, b->d2h));
+	if (handOut != OUT_DIRECT) {
+		if (handOut == OUT_FLAG) {
+			if (stream_ops().wait((CUstream)b->d2h, (CUdeviceptr)(uintptr_t)(b->d_sync + 1), seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) {
+				wr::set_error("wr_bank_submit: cuStreamWaitValue32 failed");
+				return WR_ECUDA;
+			}
+		} else {
+			WR_CUDA(cudaEventRecord(s.done, b->compute));
+			WR_CUDA(cudaStreamWaitEvent(b->d2h, s.done, 0));
+		}
+		if (M2 > 0) {
+			if (audio_stride == M2 && maxM2 == M2)
+				WR_CUDA(cudaMemcpyAsync(audio_host, s.d_audio, sizeof(float) * (size_t)M2 * b->R, cudaMemcpyDeviceToHost, b->d2h));
+			else
+				WR_CUDA(cudaMemcpy2DAsync(audio_host, sizeof(float) * audio_stride, s.d_audio, sizeof(float) * maxM2,
+						sizeof(float) * M2, b->R, cudaMemcpyDeviceToHost, b->d2h));
+		}
+		WR_CUDA(cudaEventRecord(s.out_ready, b->d2h));
+	}
 	s.busy = true;
 	s.used = true;
-	b->head = (b->head + 1) % kSlots;
+	s.seq = seq;
+	s.outMode = handOut;
+	b->head = (b->head + 1) % b->depth;
 	b->inflight++;
+	if (b->d_ts && seq <= kTraceBlocks) {
+		b->hostTs[3 * (size_t)(seq - 1)] = t_enter;
+		b->hostTs[3 * (size_t)(seq - 1) + 1] = host_ns();
+	}
 	return WR_OK;
 }
 
@@ -755,14 +1017,57 @@ int wr_bank_wait(wr_bank *b)
 	if (!wr::use_device(b->device))
 		return WR_ENODEV;
 	Slot &s = b->slot[b->tail];
-	WR_CUDA(cudaEventSynchronize(s.out_ready));
+	if (s.outMode == OUT_DIRECT) {
+		// the demodulator kernel's last CTA publishes the block's number behind its audio
+		volatile unsigned *done = b->h_err + 1;
+		const unsigned long long t0 = host_ns();
+		for (unsigned spins = 0; (int)(*done - s.seq) < 0; spins++) {
+			__builtin_ia32_pause();
+			if ((spins & 0xFFFu) == 0xFFFu) {
+				// a failed launch or a dead context must not spin forever
+				cudaError_t e = cudaStreamQuery(b->compute);
+				if (e != cudaSuccess && e != cudaErrorNotReady) {
+					wr::set_error("wr_bank_wait: %s", cudaGetErrorString(e));
+					return WR_ECUDA;
+				}
+				if (e == cudaSuccess && (int)(*done - s.seq) < 0 && host_ns() - t0 > 10000000000ull) {
+					wr::set_error("wr_bank_wait: the launch stream drained without the block's completion word");
+					return WR_ECUDA;
+				}
+			}
+		}
+		__atomic_thread_fence(__ATOMIC_ACQUIRE);
+	} else {
+		WR_CUDA(cudaEventSynchronize(s.out_ready));
+	}
 	s.busy = false;
-	b->tail = (b->tail + 1) % kSlots;
+	b->tail = (b->tail + 1) % b->depth;
 	b->inflight--;
+	if (b->d_ts && s.seq && s.seq <= kTraceBlocks)
+		b->hostTs[3 * (size_t)(s.seq - 1) + 2] = host_ns();
+	if (*static_cast<volatile unsigned*>(b->h_err) & wrd::kSyncTimeout) {
+		*b->h_err = 0;
+		wr::set_error("wr_bank_wait: the channel kernel gave up waiting for its tuner block (copy-in stream stalled)");
+		return WR_ECUDA;
+	}
 	return WR_OK;
 }
 
-int wr_bank_pipeline_depth(const wr_bank *) { return kSlots; }
+int wr_bank_pipeline_depth(const wr_bank *b) { return b ? b->depth : kSlots; }
+
+int wr_bank_set_handover(wr_bank *b, int scheme)
+{
+	WR_REQUIRE(b && scheme >= WR_HANDOVER_EVENTS && scheme <= WR_HANDOVER_DIRECT, WR_EINVAL, "wr_bank_set_handover: bad argument");
+	WR_REQUIRE(b->inflight == 0, WR_ESTATE, "wr_bank_set_handover: blocks in flight");
+	if (scheme == WR_HANDOVER_EVENTS) {
+		b->handIn = IN_EVENT;
+		b->handOut = OUT_EVENT;
+	} else {
+		b->handIn = stream_ops().ok ? IN_FLAG : IN_COPYFLAG;
+		b->handOut = scheme == WR_HANDOVER_DIRECT ? OUT_DIRECT : OUT_EVENT;
+	}
+	return scheme;
+}
 
 static int process_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframes, float *audio_host, size_t audio_stride)
 {
@@ -820,7 +1125,7 @@ static int run_host_steps_any(wr_bank *b, const void *const *iq_pinned, bool u8,
 {
 	WR_REQUIRE(b && iq_pinned && audio_pinned && n_iq && n_audio, WR_EINVAL, "wr_bank_run_host_steps: bad argument");
 	WR_REQUIRE(b->inflight == 0, WR_ESTATE, "wr_bank_run_host_steps: blocks already in flight");
-	const int depth = pipelined ? std::min<int>(kSlots, (int)n_audio) : 1;
+	const int depth = pipelined ? std::min<int>(b->depth, (int)n_audio) : 1;
 	int rc;
 	for (unsigned i = 0; i < steps; i++) {
 		if (b->inflight == depth && (rc = wr_bank_wait(b)) != WR_OK)
@@ -870,7 +1175,7 @@ int wr_bank_keep_channel(wr_bank *b, int keep)
 	if (!wr::use_device(b->device))
 		return WR_ENODEV;
 	if (keep && !b->d_chan)
-		WR_CUDA(cudaMalloc(&b->d_chan, sizeof(float2) * (size_t)b->R * std::max(1u, b->maxM1)));
+		WR_CUDA(cudaMalloc(&b->d_chan, 2 * sizeof(float2) * (size_t)b->R * std::max(1u, b->maxM1)));
 	b->keepChan = keep != 0;
 	return WR_OK;
 }
@@ -890,7 +1195,7 @@ long wr_bank_read_stage(wr_bank *b, unsigned rx, int stage, float *out, size_t c
 	if (stage == WR_STAGE_CHANNEL) {
 		WR_REQUIRE(b->keepChan && b->d_chan, WR_ESTATE, "wr_bank_read_stage: channel stream not kept (wr_bank_keep_channel)");
 		size_t n = std::min<size_t>((size_t)b->lastM1 * 2, cap);
-		WR_CUDA(cudaMemcpy(out, b->d_chan + (size_t)rx * b->maxM1, sizeof(float) * n, cudaMemcpyDeviceToHost));
+		WR_CUDA(cudaMemcpy(out, b->d_chan + ((size_t)b->chanSide * b->R + rx) * std::max(1u, b->maxM1), sizeof(float) * n, cudaMemcpyDeviceToHost));
 		return (long)n;
 	}
 	wr::set_error("wr_bank_read_stage: unknown stage %d", stage);

@@ -51,7 +51,31 @@ struct ChanArgs {
 	size_t chan_stride;
 	unsigned F, M1, n1, d1;
 	unsigned TK, ntiles;
+	// Pipelined host path (wr_bank_submit): the tuner block is being copied in by another stream.
+	// in_flag counts the blocks that have landed; the kernel's loaders wait until it reaches in_seq.
+	// nullptr = the block is already resident.  err (mapped host memory) receives WR_SYNC_TIMEOUT
+	// if that never happens.
+	const unsigned *in_flag;
+	unsigned in_seq;
+	unsigned *err;
+	unsigned long long *ts;  // optional trace record of this block (WR_TRACE): kTs* device timestamps
+	unsigned long long *cta_ts;  // optional per-CTA {start, end} of this block (WR_TRACE_CTA)
+	unsigned poll_ns;        // pause between two looks at in_flag
+	int wait_late;           // 1: the kernel waits for its predecessor (programmatic dependent launch) only before it exits
 };
+
+// trace record of one block: %globaltimer nanoseconds written by the kernels
+enum { kTsChanStart = 0, kTsChanInput = 1, kTsChanEnd = 2, kTsDemodStart = 3, kTsDemodEnd = 4, kTsWords = 8 };
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
+constexpr unsigned kSyncTimeout = 1u;   // bit in ChanArgs::err: the input flag was not raised within kSpinNs
+constexpr unsigned long long kSpinNs = 2000000000ull;
 
 struct AudioArgs {
 	const float *x;          // demod side `cur`: [R][dstride] = history | new

@@ -388,6 +388,15 @@ struct DemodAudioArgs {
 	unsigned M1, M2, n2, d2;
 	unsigned TK, ntiles;
 	float out_scale;         // 1, or 32768 for the encoder's sample format (reference mp3encoder.cxx:66-73)
+	// Pipelined host path: the last CTA to finish publishes done_seq in done_flag (device memory), which
+	// the copy-out stream waits on -- no event between the kernels of consecutive blocks, so the
+	// programmatic overlap of this grid with the next block's channel kernel survives.
+	unsigned *done_count;    // nullptr = nobody waits
+	unsigned *done_flag;     // in HBM (a copy-out stream waits) ...
+	unsigned *host_done;     // ... or in mapped host memory, when `audio` itself is the caller's pinned buffer
+	unsigned done_seq;
+	unsigned long long *ts;  // optional trace record (wr_bank.cuh)
+	unsigned long long *cta_ts;  // optional per-CTA {start, end} of this block (WR_TRACE_CTA)
 };
 
 // sample i of [history | demod(chan)] for receiver r
@@ -400,8 +409,46 @@ __device__ __forceinline__ float demod_at(const DemodAudioArgs &a, const float *
 	return demod(mode, ch[k], k ? ch[k - 1] : prev0);
 }
 
+// End of a CTA: count it; the last one of the grid raises the flag (release: every CTA fenced its
+// stores before it counted itself).
+__device__ __forceinline__ void demod_audio_done(const DemodAudioArgs &a, unsigned r, unsigned tile, unsigned tid)
+{
+	if (a.cta_ts && tid == 0)
+		a.cta_ts[2 * (r * gridDim.x + tile) + 1] = global_ns();
+	if (!a.done_count)
+		return;
+	__syncthreads();
+	if (tid == 0) {
+		if (a.host_done)
+			__threadfence_system();   // this CTA's audio went over PCIe
+		else
+			__threadfence();
+		const unsigned total = gridDim.x * gridDim.y;
+		if (atomicAdd(a.done_count, 1u) == total - 1u) {
+			*a.done_count = 0;      // the next launch of this kernel starts after this grid completed
+			if (a.ts)
+				a.ts[kTsDemodEnd] = global_ns();
+			if (a.host_done) {
+				__threadfence_system();
+				*reinterpret_cast<volatile unsigned*>(a.host_done) = a.done_seq;
+			} else if (a.done_flag) {
+				__threadfence();
+				atomicExch(a.done_flag, a.done_seq);
+			}
+		}
+	}
+}
+
+// This kernel runs under the NEXT block's channel kernel (programmatic dependent launch), whose
+// CTA needs almost a whole SM: it starts on an SM only when that SM's demodulator CTAs have
+// drained, so the life time of a CTA here is on the critical path of the block.  It is all
+// latency -- hence every global load of a tile is issued before anything waits for one, and the
+// CTA is wide enough to stage a tile of the common geometry in a single round.
+constexpr int kDemodThreads = 192;
+constexpr int kDemodRounds = 2;
+
 template <int kThreads>
-__global__ void __launch_bounds__(kThreads) demod_audio_kernel_v2(const DemodAudioArgs a)
+__global__ void __launch_bounds__(kThreads, 8) demod_audio_kernel_v2(const DemodAudioArgs a)
 {
 	extern __shared__ float4 wr_smem_da[];
 	const unsigned r = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
@@ -411,6 +458,12 @@ __global__ void __launch_bounds__(kThreads) demod_audio_kernel_v2(const DemodAud
 	// start its prologue now.  Both are no-ops for a plain launch.
 	asm volatile("griddepcontrol.wait;" ::: "memory");
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+	if (a.ts && tid == 0) {
+		if (r == 0 && tile == 0)
+			a.ts[kTsDemodStart] = global_ns();
+		if (a.cta_ts)
+			a.cta_ts[2 * (r * gridDim.x + tile)] = global_ns();
+	}
 	const RxConf cf = a.conf[r];
 	const RxState st = a.st_in[r];
 	const float2 prev0 = make_float2(st.prev_i, st.prev_q);
@@ -429,6 +482,7 @@ __global__ void __launch_bounds__(kThreads) demod_audio_kernel_v2(const DemodAud
 			a.st_out[r].prev_i = lastc.x;
 			a.st_out[r].prev_q = lastc.y;
 		}
+		demod_audio_done(a, r, tile, tid);
 		return;
 	}
 
@@ -443,14 +497,46 @@ __global__ void __launch_bounds__(kThreads) demod_audio_kernel_v2(const DemodAud
 	// (and written to the demod stream in HBM) by exactly one tile
 	const unsigned L = nout * d2 + n2 - 1;
 	const unsigned i0 = m0 * d2;
-	for (unsigned i = tid; i < L; i += kThreads) {
-		const float v = demod_at(a, xr, ch, cf.mode, prev0, i0 + i);
-		s[i] = v;
-		if (i >= n2 - 1)
-			xr[i0 + i] = v;
+	const float tap0 = tid < n2 ? a.taps2[(size_t)r * n2 + tid] : 0.0f;
+	for (unsigned ib = tid; ib < L; ib += kDemodRounds * kThreads) {
+		// operands of up to kDemodRounds samples first: their loads are in flight together
+		float2 cur[kDemodRounds], prv[kDemodRounds];
+		float hist[kDemodRounds];
+		#pragma unroll
+		for (int u = 0; u < kDemodRounds; u++) {
+			const unsigned il = ib + u * kThreads, i = i0 + il;
+			cur[u] = prv[u] = make_float2(0.0f, 0.0f);
+			hist[u] = 0.0f;
+			if (il < L) {
+				if (i < n2 - 1) {
+					hist[u] = xr[i];
+				} else {
+					const unsigned k = i - (n2 - 1);
+					cur[u] = ch[k];
+					if (k)
+						prv[u] = ch[k - 1];
+				}
+			}
+		}
+		if (ib == tid) {
+			if (tid < n2)
+				rt[tid] = tap0;
+			for (unsigned i = tid + kThreads; i < n2; i += kThreads)
+				rt[i] = a.taps2[(size_t)r * n2 + i];
+		}
+		#pragma unroll
+		for (int u = 0; u < kDemodRounds; u++) {
+			const unsigned il = ib + u * kThreads, i = i0 + il;
+			if (il < L) {
+				float v = hist[u];
+				if (i >= n2 - 1) {
+					v = demod(cf.mode, cur[u], i == n2 - 1 ? prev0 : prv[u]);
+					xr[i] = v;
+				}
+				s[il] = v;
+			}
+		}
 	}
-	for (unsigned i = tid; i < n2; i += kThreads)
-		rt[i] = a.taps2[(size_t)r * n2 + i];
 	__syncthreads();
 	for (unsigned o = tid; o < nout; o += kThreads) {
 		float acc = 0.0f;
@@ -459,6 +545,7 @@ __global__ void __launch_bounds__(kThreads) demod_audio_kernel_v2(const DemodAud
 			tap1(acc, rt[j], p[j]);
 		a.audio[(size_t)r * a.audio_stride + m0 + o] = __fmul_rn(acc, a.out_scale);
 	}
+	demod_audio_done(a, r, tile, tid);
 }
 
 // ------------------------------------------------------------------ host side ----

@@ -27,8 +27,9 @@
 //   * Slots are handed over with mbarriers (full/empty per slot); a small descriptor per slot
 //     tells the FIR warps which receiver and which pass it holds.
 //   * Tuner blocks arrive as float IQ or as raw RTL-SDR bytes (converted in the load path).
-//   * Launched with programmatic stream serialization: only the FIR warps wait for the previous
-//     kernel in the stream (the demodulator of the block before).
+//   * Launched with programmatic stream serialization: the whole kernel may run under the previous
+//     kernel in the stream (the demodulator of the block before, which reads the other side of the
+//     double-buffered channel-rate stream); it only waits for it before it exits.
 // NCO: the sine and cosine table entries of a frame are reconstructed TOGETHER in the two halves
 // of packed f32x2 registers (wr_lo3.h): one byte permute per entry builds the float index, ten
 // packed instructions produce both bases and both padded table positions; written stage by stage
@@ -507,6 +508,36 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 		unsigned kuse = 0;           // how many times the ring has wrapped
 		unsigned unit = u0;
 		bool tableReady = false;
+		const bool tracer = a.ts && blockIdx.x == 0 && mt == 0;
+		if (tracer)
+			a.ts[kTsChanStart] = global_ns();
+		if (a.cta_ts && mt == 0)
+			a.cta_ts[2 * blockIdx.x] = global_ns();
+		if (a.in_flag) {
+			// Pipelined host path: the copy-in stream raises the flag behind the tuner block.  One
+			// warp per CTA polls, with warp-uniform control flow (a lane spinning on its own leaves
+			// the warp diverged for the rest of the kernel: measured, the mixing ran at half
+			// speed), and sparsely (148 CTAs polling one L2 line back to back slowed the very copy
+			// they were waiting for); the other mixer warps sleep in the named barrier.
+			if (mt < 32) {
+				const unsigned long long t0 = global_ns();
+				for (;;) {
+					unsigned seen;
+					asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.in_flag) : "memory");
+					if (__any_sync(0xFFFFFFFFu, (int)(seen - a.in_seq) >= 0))
+						break;
+					if (__any_sync(0xFFFFFFFFu, global_ns() - t0 > kSpinNs)) {
+						if (mt == 0)
+							atomicOr(a.err, kSyncTimeout);   // never hang the GPU on a copy that did not come
+						break;
+					}
+					__nanosleep(a.poll_ns);
+				}
+			}
+			bar_sync(kV3BarMix, NMT);
+		}
+		if (tracer)
+			a.ts[kTsChanInput] = global_ns();
 		while (unit < u1) {
 			// ---- a run of consecutive passes [p0, pend) of one receiver group ----
 			const unsigned rg = unit / P, p0 = unit - rg * P;
@@ -678,6 +709,10 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 				kuse++;
 			}
 		}
+		if (tracer)
+			a.ts[kTsChanEnd] = global_ns();
+		if (a.cta_ts && mt == 0)
+			a.cta_ts[2 * blockIdx.x + 1] = global_ns();
 	} else {
 		// ================================== FIR warps ==================================
 		const unsigned fw = (tid - NMT) >> 5, lane = tid & 31;
@@ -685,7 +720,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 		// FIR warp fw serves slot fw % S and, of its NG groups of 32 outputs, every FW-th one
 		const unsigned slot = fw % S, sub = fw / S;
 		// the demodulator of the previous block may still be reading the channel-rate buffer
-		asm volatile("griddepcontrol.wait;" ::: "memory");
+		if (!a.wait_late)
+			asm volatile("griddepcontrol.wait;" ::: "memory");
 		for (unsigned kuse = 0; ; kuse++) {
 			mbar_wait(full32 + 8u * slot, kuse & 1u);
 			unsigned r, p, unused, rl;
@@ -713,6 +749,12 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 				mbar_arrive(empty32 + 8u * slot);
 		}
 	}
+	// Programmatic dependent launch: this grid may have run entirely under the previous kernel in
+	// the stream, the demodulator of the block before.  Nothing here reads what that kernel writes
+	// and nothing it reads is written here (the channel-rate buffer and the carried state alternate
+	// between two sides), but the NEXT demodulator waits only for this grid -- so this grid must not
+	// complete before its predecessor has, or two demodulator kernels could overlap.
+	asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ------------------------------------------------------------------ host side ----
@@ -876,10 +918,9 @@ inline int v3_launch_chan(V3Plan &p, ChanArgs &ca, bool u8, cudaStream_t st, uns
 	v.prmtHi = 0x4B00u;
 	const unsigned long long units = (unsigned long long)v.nGroups * v.P;
 	const unsigned grid = (unsigned)std::min<unsigned long long>(units, (unsigned long long)p.numSMs);
-	// Programmatic dependent launch: this grid may start while the previous kernel in the stream
-	// (the demodulator of the block before) is still draining; everything up to the first store
-	// of channel-rate IQ -- table staging, group set-up, mixing -- is independent of it, and the
-	// FIR warps execute griddepcontrol.wait before that store.
+	// Programmatic dependent launch: this grid may run while the previous kernel in the stream (the
+	// demodulator of the block before) is still at work; it executes griddepcontrol.wait only
+	// before it exits (see the end of the kernel).
 	cudaLaunchConfig_t cfg = {};
 	cudaLaunchAttribute attr[1];
 	cfg.gridDim = dim3(grid);
