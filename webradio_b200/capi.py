@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwebradio_b200.so")
+LIB_PATH = os.environ.get("WEBRADIO_B200_LIB") or os.path.join(HERE, "libwebradio_b200.so")   # the override is for A/B runs of two builds
 
 AM, FM, USB, LSB = 0, 1, 2, 3
 MODES = {"AM": AM, "FM": FM, "USB": USB, "LSB": LSB}

@@ -465,14 +465,18 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 		da.M2 = M2;
 		da.n2 = b->n2;
 		da.d2 = b->d2;
-		// 128 audio outputs per CTA, fewer when that would leave most SMs without a CTA (a single
-		// receiver's block is 16 tiles of 128): the demodulator in front of the FIR is the long
-		// pole of a tile, and smaller tiles spread it over more SMs
-		da.TK = 128;
+		// Audio outputs per CTA.  A tile demodulates the n2-1 samples in front of it again, so large
+		// tiles do less work -- but the NEXT block's channel kernel starts on an SM only when this
+		// grid's CTAs have drained from it, so when the whole grid is resident at once (a few CTAs
+		// per SM) what counts is the life time of a CTA: 128 outputs, staged in one round.  Fewer
+		// still when that would leave most SMs without a CTA (a single receiver's block is 16
+		// tiles of 128).
+		da.TK = (unsigned long long)b->R * ((M2 + 255) / 256) >= 16ull * (unsigned)b->numSMs ? 256 : 128;
 		while (da.TK > 16 && (unsigned long long)b->R * ((M2 + da.TK - 1) / da.TK) < 296ull)
 			da.TK /= 2;
 		da.ntiles = (M2 + da.TK - 1) / da.TK;
 		da.out_scale = b->outScale;
+		da.negzero = -0.0f;
 		da.done_count = (handOut != OUT_EVENT || ts) ? b->d_sync + 2 : nullptr;
 		da.done_flag = handOut == OUT_FLAG ? b->d_sync + 1 : nullptr;
 		da.host_done = handOut == OUT_DIRECT ? b->h_err + 1 : nullptr;

@@ -388,6 +388,7 @@ struct DemodAudioArgs {
 	unsigned M1, M2, n2, d2;
 	unsigned TK, ntiles;
 	float out_scale;         // 1, or 32768 for the encoder's sample format (reference mp3encoder.cxx:66-73)
+	float negzero;           // -0.0f, opaque to the compiler (mul2_rn_exact)
 	// Pipelined host path: the last CTA to finish publishes done_seq in done_flag (device memory), which
 	// the copy-out stream waits on -- no event between the kernels of consecutive blocks, so the
 	// programmatic overlap of this grid with the next block's channel kernel survives.
@@ -448,7 +449,7 @@ constexpr int kDemodThreads = 192;
 constexpr int kDemodRounds = 2;
 
 template <int kThreads>
-__global__ void __launch_bounds__(kThreads, 8) demod_audio_kernel_v2(const DemodAudioArgs a)
+__global__ void __launch_bounds__(kThreads, 7) demod_audio_kernel_v2(const DemodAudioArgs a)
 {
 	extern __shared__ float4 wr_smem_da[];
 	const unsigned r = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
@@ -538,12 +539,29 @@ __global__ void __launch_bounds__(kThreads, 8) demod_audio_kernel_v2(const Demod
 		}
 	}
 	__syncthreads();
-	for (unsigned o = tid; o < nout; o += kThreads) {
-		float acc = 0.0f;
-		const float *p = s + (size_t)o * d2;
-		for (unsigned j = 0; j < n2; j++)
-			tap1(acc, rt[j], p[j]);
-		a.audio[(size_t)r * a.audio_stride + m0 + o] = __fmul_rn(acc, a.out_scale);
+	// Audio FIR, two outputs per thread (o and o + H) in the two halves of packed f32x2 registers:
+	// each output's taps in the reference's order (lowpass.cxx:151-159), products and sums rounded
+	// separately (mul2_rn_exact), taps four per 128-bit load.
+	const float2 nz = make_float2(a.negzero, a.negzero);
+	const unsigned H = (nout + 1) / 2;
+	for (unsigned o = tid; o < H; o += kThreads) {
+		const bool two = o + H < nout;
+		const float *p0 = s + (size_t)o * d2;
+		const float *p1 = s + (size_t)(two ? o + H : o) * d2;
+		float2 acc = make_float2(0.0f, 0.0f);
+		unsigned j = 0;
+		for (; j + 3 < n2; j += 4) {
+			const float4 c = *reinterpret_cast<const float4*>(rt + j);
+			acc = __fadd2_rn(acc, mul2_rn_exact(make_float2(c.x, c.x), make_float2(p0[j], p1[j]), nz));
+			acc = __fadd2_rn(acc, mul2_rn_exact(make_float2(c.y, c.y), make_float2(p0[j + 1], p1[j + 1]), nz));
+			acc = __fadd2_rn(acc, mul2_rn_exact(make_float2(c.z, c.z), make_float2(p0[j + 2], p1[j + 2]), nz));
+			acc = __fadd2_rn(acc, mul2_rn_exact(make_float2(c.w, c.w), make_float2(p0[j + 3], p1[j + 3]), nz));
+		}
+		for (; j < n2; j++)
+			acc = __fadd2_rn(acc, mul2_rn_exact(make_float2(rt[j], rt[j]), make_float2(p0[j], p1[j]), nz));
+		a.audio[(size_t)r * a.audio_stride + m0 + o] = __fmul_rn(acc.x, a.out_scale);
+		if (two)
+			a.audio[(size_t)r * a.audio_stride + m0 + o + H] = __fmul_rn(acc.y, a.out_scale);
 	}
 	demod_audio_done(a, r, tile, tid);
 }
