@@ -192,6 +192,7 @@ struct wr_bank {
 	unsigned seq = 0;           // blocks submitted through wr_bank_submit
 	int handIn = IN_EVENT, handOut = OUT_EVENT;
 	unsigned pollNs = 1000;     // WR_POLL_NS: pause between two looks of the channel kernel at the copy-in counter
+	int demodPerSM = -1;        // WR_DEMOD_PER_SM: > 0 = persistent demodulator grid of that many CTAs per SM, 0 = one CTA per tile, < 0 = by bank size
 	int waitLate = 1;           // WR_WAIT_LATE: the channel kernel runs under the previous block's demodulator kernel
 	// the device address of a pinned output buffer (OUT_DIRECT): small cache of the runtime's answer
 	struct HostMap { const void *host; void *dev; size_t bytes; } hostMap[8] = {};
@@ -485,8 +486,20 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 		da.cta_ts = cta_ts ? cta_ts + 2 * kCtaTraceChan : nullptr;
 		size_t lmax = (size_t)da.TK * b->d2 + b->n2 - 1;
 		size_t smem = sizeof(float) * (((lmax + 3) & ~(size_t)3) + b->n2);
-		dim3 grid(da.ntiles + 1, b->R);
-		if (cta_ts && (size_t)grid.x * grid.y > kCtaTraceDemod)
+		const unsigned long long items = (unsigned long long)(da.ntiles + 1) * b->R;
+		WR_REQUIRE(items <= 0x7FFFFFFFull, WR_EINVAL, "receiver bank too large for one launch");
+		da.items = (unsigned)items;
+		// Grid: one CTA per item -- or, for a small bank under the v3 channel kernel, a PERSISTENT
+		// grid of two CTAs per SM that walk the items.  Two of these CTAs fit beside the channel
+		// kernel's CTA (registers), so the next block's channel kernel starts on every SM at once
+		// instead of waiting for seven short-lived CTAs per SM to drain (cfg2: 21.8 -> 20.7 us per
+		// block); the grid then runs for most of that kernel's life time, which a large bank
+		// cannot afford (cfg5, 17408 items: 0.91 -> 1.14 ms).
+		int perSM = b->demodPerSM;
+		if (perSM < 0)
+			perSM = (useV3 && b->v3.pdl && items <= 10ull * (unsigned)b->numSMs) ? 2 : 0;
+		dim3 grid(perSM > 0 ? (unsigned)std::min<unsigned long long>(items, (unsigned long long)perSM * (unsigned)b->numSMs) : (unsigned)items);
+		if (cta_ts && grid.x > kCtaTraceDemod)
 			da.cta_ts = nullptr;
 		cudaLaunchConfig_t cfg = {};
 		cudaLaunchAttribute attr[1];
@@ -685,6 +698,8 @@ wr_bank *wr_bank_create(int device, unsigned n_streams, unsigned n_receivers, un
 	default_handover(b);
 	if (const char *e = getenv("WR_POLL_NS"))
 		b->pollNs = (unsigned)atoi(e);
+	if (const char *e = getenv("WR_DEMOD_PER_SM"))
+		b->demodPerSM = atoi(e);
 	if (const char *e = getenv("WR_WAIT_LATE"))
 		b->waitLate = atoi(e) != 0;
 	if ((b->tracePath = getenv("WR_TRACE")) != nullptr) {

@@ -387,6 +387,7 @@ struct DemodAudioArgs {
 	size_t audio_stride;
 	unsigned M1, M2, n2, d2;
 	unsigned TK, ntiles;
+	unsigned items;          // (ntiles + 1) * receivers
 	float out_scale;         // 1, or 32768 for the encoder's sample format (reference mp3encoder.cxx:66-73)
 	float negzero;           // -0.0f, opaque to the compiler (mul2_rn_exact)
 	// Pipelined host path: the last CTA to finish publishes done_seq in done_flag (device memory), which
@@ -412,10 +413,10 @@ __device__ __forceinline__ float demod_at(const DemodAudioArgs &a, const float *
 
 // End of a CTA: count it; the last one of the grid raises the flag (release: every CTA fenced its
 // stores before it counted itself).
-__device__ __forceinline__ void demod_audio_done(const DemodAudioArgs &a, unsigned r, unsigned tile, unsigned tid)
+__device__ __forceinline__ void demod_audio_done(const DemodAudioArgs &a, unsigned tid)
 {
 	if (a.cta_ts && tid == 0)
-		a.cta_ts[2 * (r * gridDim.x + tile) + 1] = global_ns();
+		a.cta_ts[2 * blockIdx.x + 1] = global_ns();
 	if (!a.done_count)
 		return;
 	__syncthreads();
@@ -452,7 +453,7 @@ template <int kThreads>
 __global__ void __launch_bounds__(kThreads, 7) demod_audio_kernel_v2(const DemodAudioArgs a)
 {
 	extern __shared__ float4 wr_smem_da[];
-	const unsigned r = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+	const unsigned tid = threadIdx.x;
 	const unsigned n2 = a.n2, d2 = a.d2;
 	// Programmatic dependent launch, both ways: this grid may have been launched while the channel
 	// kernel that feeds it was still running (wait for it), and the next block's channel kernel may
@@ -460,11 +461,15 @@ __global__ void __launch_bounds__(kThreads, 7) demod_audio_kernel_v2(const Demod
 	asm volatile("griddepcontrol.wait;" ::: "memory");
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 	if (a.ts && tid == 0) {
-		if (r == 0 && tile == 0)
+		if (blockIdx.x == 0)
 			a.ts[kTsDemodStart] = global_ns();
 		if (a.cta_ts)
-			a.cta_ts[2 * (r * gridDim.x + tile)] = global_ns();
+			a.cta_ts[2 * blockIdx.x] = global_ns();
 	}
+	// work items (receiver, tile): one per CTA, or -- persistent grid -- every gridDim.x-th one
+	const unsigned perRx = a.ntiles + 1;
+	for (unsigned w = blockIdx.x; w < a.items; w += gridDim.x) {
+	const unsigned r = w / perRx, tile = w - r * perRx;
 	const RxConf cf = a.conf[r];
 	const RxState st = a.st_in[r];
 	const float2 prev0 = make_float2(st.prev_i, st.prev_q);
@@ -483,8 +488,7 @@ __global__ void __launch_bounds__(kThreads, 7) demod_audio_kernel_v2(const Demod
 			a.st_out[r].prev_i = lastc.x;
 			a.st_out[r].prev_q = lastc.y;
 		}
-		demod_audio_done(a, r, tile, tid);
-		return;
+		continue;
 	}
 
 	const unsigned Lmax = a.TK * d2 + n2 - 1;
@@ -563,7 +567,9 @@ __global__ void __launch_bounds__(kThreads, 7) demod_audio_kernel_v2(const Demod
 		if (two)
 			a.audio[(size_t)r * a.audio_stride + m0 + o + H] = __fmul_rn(acc.y, a.out_scale);
 	}
-	demod_audio_done(a, r, tile, tid);
+	__syncthreads();    // the staged window is rewritten by the next item
+	}
+	demod_audio_done(a, tid);
 }
 
 // ------------------------------------------------------------------ host side ----
