@@ -28,14 +28,16 @@ echo "== bench cfg3, v2 kernels (for the record)"
 timeout 900 python bench.py --workload cfg3 --variant 2 --no-cpu-baseline 2>/dev/null | tee $OUT/bench_cfg3_v2.json | cut -c1-200
 echo "== bench cfg2, v1 kernels (for the record)"
 timeout 900 python bench.py --variant 1 --no-cpu-baseline 2>/dev/null | tee $OUT/bench_cfg2_v1.json | cut -c1-200
+# under ncu the host path hands blocks over by events (WR_HAND_IN=0): a kernel that waits for a copy
+# would be timed with its wait
 echo "== ncu launch list (cfg2, short)"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/launches_cfg2.csv \
+WR_HAND_IN=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/launches_cfg2.csv \
   python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $OUT/ncu_launches_cfg2.log 2>&1
 echo "== ncu full: fused channel kernel (cfg2, cfg3), spectrum kernel (cfg4)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:chan_kernel -s 6 -c 1 -o $OUT/prof_chan_cfg2 -f \
+WR_HAND_IN=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:chan_kernel -s 6 -c 1 -o $OUT/prof_chan_cfg2 -f \
   python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_cfg2.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:chan_kernel -s 4 -c 1 -o $OUT/prof_chan_cfg3 -f \
+WR_HAND_IN=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:chan_kernel -s 4 -c 1 -o $OUT/prof_chan_cfg3 -f \
   python bench.py --workload cfg3 --steps 4 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_cfg3.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:spectrum_kernel -s 3 -c 1 -o $OUT/prof_spectrum_cfg4 -f \
+WR_HAND_IN=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:spectrum_kernel -s 3 -c 1 -o $OUT/prof_spectrum_cfg4 -f \
   python bench.py --workload cfg4 --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_cfg4.log 2>&1
 ls -la $OUT

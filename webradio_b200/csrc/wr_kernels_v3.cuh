@@ -772,6 +772,7 @@ struct V3Plan {
 	int numSMs = 0;
 	unsigned n1 = 0, d1 = 0;
 	unsigned SF = 0, RB = 1;
+	unsigned unitsPerSM = 6;       // receiver groups are halved until there are this many (group, pass) units per SM (WR_V3_UNITS_PER_SM)
 	size_t smemBytes = 0;
 	int16_t *d_delta = nullptr;
 	wr::Lo3Coef coef = {};
@@ -819,6 +820,8 @@ inline int v3_init(V3Plan &p, int device, unsigned n1, unsigned d1, unsigned max
 	p.kernel = nullptr;
 	if (const char *e = getenv("WR_V3_PDL"))
 		p.pdl = atoi(e) != 0;
+	if (const char *e = getenv("WR_V3_UNITS_PER_SM"))
+		p.unitsPerSM = (unsigned)std::max(1, atoi(e));
 	if (n1 == 64 && d1 == 10) v3_fill<64, 10, 4>(p);
 	else if (n1 == 64 && d1 == 8) v3_fill<64, 8, 4>(p);     // 2.048 MSPS -> 256 k
 	else if (n1 == 127 && d1 == 50) v3_fill<127, 50, 4>(p);
@@ -885,7 +888,7 @@ inline int v3_set_groups(V3Plan &p, const RxConf *h_conf, unsigned R, cudaStream
 			groups.push_back(make_int4((int)i, (int)n, (int)h_conf[order[i]].stream, 0));
 			i += n;
 		}
-		if (cap == 1 || (unsigned long long)groups.size() * passes >= 6ull * (unsigned)p.numSMs)
+		if (cap == 1 || (unsigned long long)groups.size() * passes >= (unsigned long long)p.unitsPerSM * (unsigned)p.numSMs)
 			break;
 	}
 	p.groupCap = cap;
