@@ -192,6 +192,7 @@ struct wr_bank {
 	unsigned seq = 0;           // blocks submitted through wr_bank_submit
 	int handIn = IN_EVENT, handOut = OUT_EVENT;
 	unsigned pollNs = 1000;     // WR_POLL_NS: pause between two looks of the channel kernel at the copy-in counter
+	int demodRegs = 0;
 	int demodPerSM = -1;        // WR_DEMOD_PER_SM: > 0 = persistent demodulator grid of that many CTAs per SM, 0 = one CTA per tile, < 0 = by bank size
 	int waitLate = 1;           // WR_WAIT_LATE: the channel kernel runs under the previous block's demodulator kernel
 	// the device address of a pinned output buffer (OUT_DIRECT): small cache of the runtime's answer
@@ -496,8 +497,18 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 		// block); the grid then runs for most of that kernel's life time, which a large bank
 		// cannot afford (cfg5, 17408 items: 0.91 -> 1.14 ms).
 		int perSM = b->demodPerSM;
-		if (perSM < 0)
-			perSM = (useV3 && b->v3.pdl && items <= 10ull * (unsigned)b->numSMs) ? 2 : 0;
+		if (perSM < 0) {
+			// ... and only if two of them really fit beside the channel kernel's CTA: a second
+			// one that does not would hold that CTA back for its whole life time (cfg2 fed raw
+			// bytes, whose channel kernel needs 8 more registers per thread: 21 -> 33 us)
+			if (b->demodRegs == 0) {
+				cudaFuncAttributes fa;
+				WR_CUDA(cudaFuncGetAttributes(&fa, wrd::demod_audio_kernel_v2<wrd::kDemodThreads>));
+				b->demodRegs = fa.numRegs;
+			}
+			const int fit = useV3 ? wrd::v3_spare_regs(b->v3, u8) / (((b->demodRegs + 7) & ~7) * wrd::kDemodThreads) : 0;
+			perSM = (useV3 && b->v3.pdl && fit >= 2 && items <= 10ull * (unsigned)b->numSMs) ? 2 : 0;
+		}
 		dim3 grid(perSM > 0 ? (unsigned)std::min<unsigned long long>(items, (unsigned long long)perSM * (unsigned)b->numSMs) : (unsigned)items);
 		if (cta_ts && grid.x > kCtaTraceDemod)
 			da.cta_ts = nullptr;

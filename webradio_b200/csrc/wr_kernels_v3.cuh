@@ -767,6 +767,7 @@ struct V3Plan {
 	V3Kernel kernel8 = nullptr;    // raw RTL-SDR bytes
 	V3Kernel kernelH = nullptr;    // the same two, instantiated for groups of at most RB/2 receivers:
 	V3Kernel kernel8H = nullptr;   // half the unrolled mixer code when the groups are small anyway
+	int regs[4] = { 0, 0, 0, 0 };  // registers per thread of kernel, kernel8, kernelH, kernel8H
 	unsigned groupCap = 0;         // largest group v3_set_groups built
 	int device = 0;
 	int numSMs = 0;
@@ -837,6 +838,14 @@ inline int v3_init(V3Plan &p, int device, unsigned n1, unsigned d1, unsigned max
 	WR_CUDA(cudaFuncSetAttribute(p.kernel8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
 	WR_CUDA(cudaFuncSetAttribute(p.kernelH, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
 	WR_CUDA(cudaFuncSetAttribute(p.kernel8H, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
+	{
+		const V3Kernel ks[4] = { p.kernel, p.kernel8, p.kernelH, p.kernel8H };
+		for (int i = 0; i < 4; i++) {
+			cudaFuncAttributes fa;
+			WR_CUDA(cudaFuncGetAttributes(&fa, ks[i]));
+			p.regs[i] = fa.numRegs;
+		}
+	}
 	WR_CUDA(cudaMalloc(&p.d_delta, kV3TableBytes));
 	p.ok = true;
 	return WR_OK;
@@ -906,6 +915,15 @@ inline int v3_set_groups(V3Plan &p, const RxConf *h_conf, unsigned R, cudaStream
 	WR_CUDA(cudaStreamSynchronize(st)); // locals
 	p.nGroups = (unsigned)groups.size();
 	return WR_OK;
+}
+
+// Registers of an SM that the channel kernel's CTA leaves to other kernels' CTAs (what decides how
+// many demodulator CTAs run beside it).
+inline int v3_spare_regs(const V3Plan &p, bool u8)
+{
+	const bool half = p.RB > 1 && p.groupCap <= p.RB / 2;
+	const int r = p.regs[(half ? 2 : 0) + (u8 ? 1 : 0)];
+	return 65536 - ((r + 7) & ~7) * kV3Threads;
 }
 
 inline int v3_launch_chan(V3Plan &p, ChanArgs &ca, bool u8, cudaStream_t st, unsigned long long *launches)
