@@ -17,7 +17,7 @@ HARNESS  := tests/harness/libwr_blocks_harness.so
 BLOCKSRC := webradio_b200/dsp/dspblock.cxx webradio_b200/dsp/downconverter.cxx webradio_b200/dsp/lowpass.cxx \
             webradio_b200/dsp/demodulator.cxx webradio_b200/io/spectrumsink.cxx webradio_b200/dsp/gpubank.cxx
 
-.PHONY: all lib harness dropin oracle clean
+.PHONY: all lib harness dropin oracle tools clean
 all: lib
 lib: $(LIB)
 
@@ -56,6 +56,12 @@ dropin: $(LIB)
 
 oracle:
 	$(MAKE) -C oracle port ref
+
+# stand-alone micro-benchmarks (run on the GPU box; build/ travels with gpurun)
+tools: build/ubench_copy
+build/ubench_copy: tools/ubench_copy.cu
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O2 -o $@ $<
 
 clean:
 	rm -rf build $(LIB) $(HARNESS)

@@ -26,6 +26,10 @@ for a, b in BENCH.items():
     if os.path.exists(p) and os.path.getsize(p):
         shutil.copy(p, os.path.join(dst, f"{prefix}_{b}.json"))
 
+for a, b in (("timeline_cfg2.txt", "timeline_cfg2.txt"), ("ubench_copy.txt", "ubench_copy.txt")):
+    if os.path.exists(os.path.join(src, a)) and os.path.getsize(os.path.join(src, a)):
+        shutil.copy(os.path.join(src, a), os.path.join(dst, f"{prefix}_{b}"))
+
 if os.path.exists(os.path.join(src, "nproc.txt")):
     shutil.copy(os.path.join(src, "nproc.txt"), os.path.join(dst, f"{prefix}_host_cpu.txt"))
 

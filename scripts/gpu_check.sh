@@ -40,4 +40,9 @@ WR_HAND_IN=0 timeout 900 ncu --set full --clock-control none --import-source on 
   python bench.py --workload cfg3 --steps 4 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_cfg3.log 2>&1
 WR_HAND_IN=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:spectrum_kernel -s 3 -c 1 -o $OUT/prof_spectrum_cfg4 -f \
   python bench.py --workload cfg4 --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_cfg4.log 2>&1
+echo "== block timeline of the default line (WR_TRACE / WR_TRACE_CTA), block-sized PCIe copies"
+WR_TRACE=$OUT/trace_cfg2.csv WR_TRACE_CTA=$OUT/cta_cfg2.csv timeout 300 python bench.py --no-cpu-baseline --steps 500 > /dev/null 2>&1
+{ echo "python bench.py --steps 500 under WR_TRACE / WR_TRACE_CTA (cfg2): per-block and per-CTA device timestamps"; echo;
+  python scripts/trace_summary.py $OUT/trace_cfg2.csv 20 480; echo; python scripts/cta_summary.py $OUT/cta_cfg2.csv; } > $OUT/timeline_cfg2.txt 2>&1
+[ -x build/ubench_copy ] && ./build/ubench_copy > $OUT/ubench_copy.txt 2>&1
 ls -la $OUT
