@@ -193,6 +193,7 @@ struct wr_bank {
 	int handIn = IN_EVENT, handOut = OUT_EVENT;
 	unsigned pollNs = 1000;     // WR_POLL_NS: pause between two looks of the channel kernel at the copy-in counter
 	int demodRegs = 0;
+	bool anyFM = true;          // any receiver in FM mode (as of the last configuration upload)
 	int demodPerSM = -1;        // WR_DEMOD_PER_SM: > 0 = persistent demodulator grid of that many CTAs per SM, 0 = one CTA per tile, < 0 = by bank size
 	int waitLate = 1;           // WR_WAIT_LATE: the channel kernel runs under the previous block's demodulator kernel
 	// the device address of a pinned output buffer (OUT_DIRECT): small cache of the runtime's answer
@@ -257,6 +258,9 @@ int apply_pending(wr_bank *b, cudaStream_t st)
 			return rc;
 	}
 	if (b->confDirty) {
+		b->anyFM = false;
+		for (unsigned r = 0; r < b->R; r++)
+			b->anyFM = b->anyFM || b->h_conf[r].mode == WR_MODE_FM;
 		memcpy(b->p_conf, b->h_conf.data(), sizeof(RxConf) * b->R);
 		WR_CUDA(cudaMemcpyAsync(b->d_conf, b->p_conf, sizeof(RxConf) * b->R, cudaMemcpyHostToDevice, st));
 		b->confDirty = false;
@@ -507,7 +511,11 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 				b->demodRegs = fa.numRegs;
 			}
 			const int fit = useV3 ? wrd::v3_spare_regs(b->v3, u8) / (((b->demodRegs + 7) & ~7) * wrd::kDemodThreads) : 0;
-			perSM = (useV3 && b->v3.pdl && fit >= 2 && items <= 10ull * (unsigned)b->numSMs) ? 2 : 0;
+			// banks without an FM receiver demodulate for next to nothing (a square root or a sum
+			// per sample), so they can afford the persistent grid at several times the size
+			// (cfg3, 9216 items: 291.7 -> 287.1 us)
+			const unsigned long long cap = (b->anyFM ? 10ull : 64ull) * (unsigned)b->numSMs;
+			perSM = (useV3 && b->v3.pdl && fit >= 2 && items <= cap) ? 2 : 0;
 		}
 		dim3 grid(perSM > 0 ? (unsigned)std::min<unsigned long long>(items, (unsigned long long)perSM * (unsigned)b->numSMs) : (unsigned)items);
 		if (cta_ts && grid.x > kCtaTraceDemod)
