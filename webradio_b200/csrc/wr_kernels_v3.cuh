@@ -426,7 +426,7 @@ template <> struct RawIO<true> {
 };
 
 template <int N1, int D1, int RB, bool U8>
-__global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a, const V3Args v)
+__device__ __forceinline__ void chan_body_v3(const ChanArgs &a, const V3Args &v)
 {
 	using G = V3Geo<N1, D1>;
 	using IO = RawIO<U8>;
@@ -757,6 +757,20 @@ __global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a
 	asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+template <int N1, int D1, int RB, bool U8>
+__global__ void __launch_bounds__(kV3Threads, 1) chan_kernel_v3(const ChanArgs a, const V3Args v)
+{
+	chan_body_v3<N1, D1, RB, U8>(a, v);
+}
+
+// The same kernel held to 96 registers per thread: 16 K of an SM's registers stay free, enough for
+// two of the demodulator kernel's CTAs beside this one (wr_bank.cu: persistent demodulator grid).
+template <int N1, int D1, int RB, bool U8>
+__global__ void __maxnreg__(96) chan_kernel_v3_r96(const ChanArgs a, const V3Args v)
+{
+	chan_body_v3<N1, D1, RB, U8>(a, v);
+}
+
 // ------------------------------------------------------------------ host side ----
 
 typedef void (*V3Kernel)(const ChanArgs, const V3Args);
@@ -792,7 +806,10 @@ inline void v3_fill(V3Plan &p)
 	p.kernel = chan_kernel_v3<N1, D1, RB, false>;
 	p.kernel8 = chan_kernel_v3<N1, D1, RB, true>;
 	p.kernelH = chan_kernel_v3<N1, D1, (RB > 1 ? RB / 2 : 1), false>;
-	p.kernel8H = chan_kernel_v3<N1, D1, (RB > 1 ? RB / 2 : 1), true>;
+	// raw bytes, small groups: the 96-register build (no spills; 105 otherwise), so that small
+	// banks fed raw bytes get the persistent demodulator grid too (cfg2 fed bytes: 22.5 -> 21.6 us).
+	// The full-size kernels lose more to the cap than the grid brings (cfg5: 842 -> 864 us).
+	p.kernel8H = chan_kernel_v3_r96<N1, D1, (RB > 1 ? RB / 2 : 1), true>;
 	p.SF = G::SF;
 	p.RB = RB;
 	p.smemBytes = kV3TableBytes + (size_t)kV3Slots * G::SLOT * 8 + (size_t)RB * G::kTapsStride + (size_t)kV3Slots * 16;
