@@ -145,16 +145,17 @@ def _cpu_threads(n_rx):
     return min(cores, n_rx * replicas), replicas
 
 
-def cpu_reference_run(w, steps, warmup, max_seconds=None):
+def cpu_reference_run(w, steps, warmup, max_seconds=None, threads=None):
     """The reference's CPU chain on the host cores.  Each worker thread owns an independent graph
     (tuner source + its share of the receivers), exactly how the reference would be scaled out --
-    its own Radio::run visits receivers sequentially on one thread (radio.cxx:56-59).
+    its own Radio::run visits receivers sequentially on one thread (radio.cxx:56-59), which is
+    what `threads=1` times (single thread next to all cores).
     Returns dict(value MS/s, seconds, steps, cores, kind, sample)."""
     import graphlib as G
     t1, t2 = workload_taps(w)
     ifs, modes = synth.workload_ifs(w), synth.workload_modes(w)
     F, R, T = w["frames"], w["n_rx"], w["n_streams"]
-    nthreads, replicas = _cpu_threads(R)
+    nthreads, replicas = _cpu_threads(R) if threads is None else (threads, 1)
     total_rx = R * replicas
     iq = [synth.lattice_noise(F, stream=t) for t in range(min(T, 8))]
     use_ref = G.have("ref")
@@ -232,6 +233,7 @@ def reference_arm(args, w, wname):
     steps = args.steps if args.steps is not None else 20
     warmup = args.warmup if args.warmup is not None else 3
     r = cpu_reference_run(w, steps, warmup, max_seconds=120.0)
+    r1 = cpu_reference_run(w, 3, 1, max_seconds=10.0, threads=1)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "MSamples/s",
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": warmup,
@@ -239,7 +241,8 @@ def reference_arm(args, w, wname):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": bench_config(w, wname, None),
         "cpu_baseline": {"value": r["value"], "unit": "MSamples/s", "cores": r["cores"], "kind": r["kind"],
-                         "sample": r["sample"], "host_cores": r["host_cores"]},
+                         "sample": r["sample"], "host_cores": r["host_cores"],
+                         "single_thread_value": r1["value"], "single_thread_sample": r1["sample"]},
         "e2e": {"value": r["value"], "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -449,6 +452,10 @@ def gpu_arm(args, w, wname):
         r = cpu_reference_run(w, 1000, 1, max_seconds=args.cpu_seconds)
         cpu = {"value": r["value"], "unit": "MSamples/s", "cores": r["cores"], "kind": r["kind"],
                "sample": r["sample"], "host_cores": r["host_cores"]}
+        # the reference as shipped: ONE DSP thread visits every receiver (radio.cxx:56-59)
+        r1 = cpu_reference_run(w, 1000, 1, max_seconds=min(4.0, args.cpu_seconds), threads=1)
+        cpu["single_thread_value"] = r1["value"]
+        cpu["single_thread_sample"] = r1["sample"]
 
     if rank == 0:
         line = {
