@@ -49,7 +49,7 @@ DROPIN := tests/harness/libwr_radio_dropin.so
 dropin: $(LIB)
 	@if [ -f "$(REF)/src/radio.cxx" ]; then \
 	  $(CXX) -std=c++11 -O2 -fPIC -Wall -shared -DWR_QUIET_DEBUG -Iinclude -Itests/harness/stubs -Iwebradio_b200 \
-	    -Iwebradio_b200/dsp -Iwebradio_b200/io -I$(REF)/src \
+	    -Iwebradio_b200/dsp -Iwebradio_b200/io -I$(REF)/src -I$(REF)/src/io \
 	    -o $(DROPIN) $(REF)/src/radio.cxx tests/harness/radio_dropin.cxx $(BLOCKSRC) \
 	    -Lwebradio_b200 -lwebradio_b200 -Wl,-Bsymbolic -Wl,-rpath,'$$ORIGIN/../../webradio_b200' -lpthread && echo "built $(DROPIN)"; \
 	else echo "reference tree not mounted: keeping prebuilt $(DROPIN) (if any)"; fi
