@@ -381,12 +381,15 @@ def gpu_arm(args, w, wname):
     clk = clocks.stop()
     # Host-timed, so a hiccup of the host shows: `reps` timed regions of `esteps` steps each, the
     # MEDIAN is reported and all of them are listed.
-    reps = 5 if T == 1 else 1
+    reps = 5 if T == 1 else 3
     # warm-up: the host path needs ~0.2 s of traffic before it is steady (measured: 144 k, 149 k,
     # 180 k, 222 k, 224 k MS/s over the first five regions of 2000 steps after a 3-step warm-up;
     # PCIe link and host clocks ramp)
+    # ... and every slot of the pipeline must have been used once: a slot's HBM buffers are
+    # allocated on first use (cudaMalloc synchronises), so fewer warm-up blocks than the depth put
+    # allocations into the timed region (r01k: cfg3 fed bytes 6.1 k instead of ~25 k MS/s)
     for _ in range(4 if T == 1 else 1):
-        e2e_pipelined(esteps if T == 1 else min(3, esteps))
+        e2e_pipelined(esteps if T == 1 else depth + 2)
     e2e_runs, sync_runs = [], []
     ssteps = min(esteps, 200)
     for _ in range(reps):
