@@ -485,8 +485,60 @@ def gpu_arm(args, w, wname):
         dist.destroy_process_group()
 
 
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner
+    under torchrun does), so file descriptor 1 is pointed at stderr for the life of the process and
+    the JSON line goes to the saved, real stdout -- after which fd 1 is restored."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def emit(real_fd, text):
+    sys.stdout.flush()
+    os.dup2(real_fd, 1)
+    os.close(real_fd)
+    sys.stdout.write(text)
+    sys.stdout.flush()
+
+
+class _Capture:
+    """stdout of the arms while fd 1 is diverted: keeps what they print (the JSON line)."""
+
+    def __init__(self):
+        self.parts = []
+
+    def write(self, x):
+        self.parts.append(x)
+
+    def flush(self):
+        pass
+
+    def isatty(self):
+        return False
+
+    def writable(self):
+        return True
+
+    def fileno(self):
+        return 1   # diverted to stderr while the arms run
+
+    encoding = "utf-8"
+
+
 def main():
     args = parse_args()
+    real, cap, py_stdout = claim_stdout(), _Capture(), sys.stdout
+    sys.stdout = cap
+    try:
+        run(args)
+    finally:
+        sys.stdout = py_stdout
+        emit(real, "".join(cap.parts))
+
+
+def run(args):
     if args.workload == "cfg4":
         from webradio_b200 import bench_spectrum
         return bench_spectrum.main(args)
