@@ -17,7 +17,7 @@ HARNESS  := tests/harness/libwr_blocks_harness.so
 BLOCKSRC := webradio_b200/dsp/dspblock.cxx webradio_b200/dsp/downconverter.cxx webradio_b200/dsp/lowpass.cxx \
             webradio_b200/dsp/demodulator.cxx webradio_b200/io/spectrumsink.cxx webradio_b200/dsp/gpubank.cxx
 
-.PHONY: all lib harness dropin oracle tools clean
+.PHONY: all lib harness harness-mock dropin dropin-mock oracle tools clean
 all: lib
 lib: $(LIB)
 
@@ -42,6 +42,18 @@ $(HARNESS): tests/harness/graph_harness.cxx $(BLOCKSRC) $(wildcard webradio_b200
 	$(CXX) -std=c++11 -O2 -fPIC -Wall -shared -Iinclude -Iwebradio_b200 -Iwebradio_b200/dsp -Iwebradio_b200/io \
 	  -o $@ tests/harness/graph_harness.cxx $(BLOCKSRC) -Lwebradio_b200 -lwebradio_b200 -Wl,-Bsymbolic -Wl,-rpath,'$$ORIGIN/../../webradio_b200' -lpthread
 
+# TEST INFRASTRUCTURE: the same drop-in blocks and graph driver over a CPU stand-in for the device
+# entry points (tests/harness/mock_capi.cxx, arithmetic by the oracle) -- exercises the blocks'
+# HOST logic in the CPU test suite.  The product's own host cold path (wr_host.o) is linked in.
+HARNESS_MOCK := tests/harness/libwr_blocks_harness_mock.so
+CUDA_LIB ?= /usr/local/cuda/lib64
+harness-mock: $(HARNESS_MOCK)
+$(HARNESS_MOCK): tests/harness/graph_harness.cxx tests/harness/mock_capi.cxx $(BLOCKSRC) $(wildcard webradio_b200/dsp/*.h webradio_b200/io/*.h) build/wr_host.o oracle/wr_oracle.c oracle/wr_oracle.h
+	$(MAKE) -s -C oracle port
+	$(CXX) -std=c++11 -O2 -fPIC -Wall -shared -Iinclude -Iwebradio_b200 -Iwebradio_b200/dsp -Iwebradio_b200/io \
+	  -o $@ tests/harness/graph_harness.cxx tests/harness/mock_capi.cxx $(BLOCKSRC) build/wr_host.o \
+	  -Loracle -lwr_oracle -L$(CUDA_LIB) -lcudart_static -Wl,-Bsymbolic -Wl,-rpath,'$$ORIGIN/../../oracle' -lpthread -ldl -lrt
+
 # The reference's own graph glue (src/radio.cxx, UNMODIFIED, compiled where it lies) linked against
 # the drop-in blocks.  Only buildable where the reference tree is mounted; the .so travels.
 REF ?= /root/reference
@@ -54,6 +66,17 @@ dropin: $(LIB)
 	    -Lwebradio_b200 -lwebradio_b200 -Wl,-Bsymbolic -Wl,-rpath,'$$ORIGIN/../../webradio_b200' -lpthread && echo "built $(DROPIN)"; \
 	else echo "reference tree not mounted: keeping prebuilt $(DROPIN) (if any)"; fi
 
+# ... and the same glue over the CPU stand-in of tests/harness/mock_capi.cxx (CPU test suite)
+DROPIN_MOCK := tests/harness/libwr_radio_dropin_mock.so
+dropin-mock: build/wr_host.o
+	@if [ -f "$(REF)/src/radio.cxx" ]; then \
+	  $(MAKE) -s -C oracle port && \
+	  $(CXX) -std=c++11 -O2 -fPIC -Wall -shared -DWR_QUIET_DEBUG -Iinclude -Itests/harness/stubs -Iwebradio_b200 \
+	    -Iwebradio_b200/dsp -Iwebradio_b200/io -I$(REF)/src -I$(REF)/src/io \
+	    -o $(DROPIN_MOCK) $(REF)/src/radio.cxx tests/harness/radio_dropin.cxx tests/harness/mock_capi.cxx $(BLOCKSRC) build/wr_host.o \
+	    -Loracle -lwr_oracle -L$(CUDA_LIB) -lcudart_static -Wl,-Bsymbolic -Wl,-rpath,'$$ORIGIN/../../oracle' -lpthread -ldl -lrt && echo "built $(DROPIN_MOCK)"; \
+	else echo "reference tree not mounted: keeping prebuilt $(DROPIN_MOCK) (if any)"; fi
+
 oracle:
 	$(MAKE) -C oracle port ref
 
@@ -64,4 +87,4 @@ build/ubench_copy: tools/ubench_copy.cu
 	$(NVCC) $(ARCH) -O2 -o $@ $<
 
 clean:
-	rm -rf build $(LIB) $(HARNESS)
+	rm -rf build $(LIB) $(HARNESS) $(HARNESS_MOCK)

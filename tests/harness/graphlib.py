@@ -3,6 +3,8 @@
 The same C ABI is exported by two builds of that one source:
   * oracle/_ref/libwr_ref.so               -- the unmodified reference blocks (CPU)
   * tests/harness/libwr_blocks_harness.so  -- webradio_b200's GPU-backed drop-in blocks
+  * tests/harness/libwr_blocks_harness_mock.so -- the same drop-in blocks over a CPU stand-in for
+    the device entry points (tests/harness/mock_capi.cxx): host logic only, for the CPU suite
 so a test can build the reference's receiver graph (reference src/radio.cxx:62-90)
 on either and compare stage by stage.
 """
@@ -14,6 +16,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libwr_ref.so")
 BLOCKS_SO = os.path.join(ROOT, "tests", "harness", "libwr_blocks_harness.so")
+MOCK_SO = os.path.join(ROOT, "tests", "harness", "libwr_blocks_harness_mock.so")
+_PATHS = {"ref": REF_SO, "blocks": BLOCKS_SO, "mock": MOCK_SO}
 
 MODES = {"AM": 0, "FM": 1, "USB": 2, "LSB": 3}
 STAGES = {"mixed": 0, "channel": 1, "demod": 2, "audio": 3}
@@ -55,8 +59,8 @@ _libs = {}
 
 
 def load(which):
-    """which: 'ref' or 'blocks'."""
-    path = REF_SO if which == "ref" else BLOCKS_SO
+    """which: 'ref', 'blocks' or 'mock'."""
+    path = _PATHS[which]
     if path not in _libs:
         if not os.path.exists(path):
             raise FileNotFoundError(path)
@@ -65,7 +69,7 @@ def load(which):
 
 
 def have(which):
-    return os.path.exists(REF_SO if which == "ref" else BLOCKS_SO)
+    return os.path.exists(_PATHS[which])
 
 
 def _f32(a):

@@ -1,0 +1,285 @@
+"""HOST logic of the DspBlock drop-in classes (webradio_b200/dsp, webradio_b200/io) on the CPU:
+the same C++ blocks and graph driver as tests/test_blocks_gpu.py, linked against a CPU stand-in for
+the device entry points (tests/harness/mock_capi.cxx -- test infrastructure, arithmetic by the
+oracle) instead of libwebradio_b200.so, compared with the unmodified reference blocks
+(oracle/_ref) through the plugin surface only.
+
+What this pins without a GPU: receiver chains are batched into ONE bank per tuner block, triggered
+by the first receiver visited; each chain gets its own slice; setIF / setModeString / setPassband
+reach the bank at the next block boundary; a consumer attached between stages turns the chain
+into strict per-block stage calls; NCO phase, FIR histories and the FM look-back sample carry
+across blocks; SpectrumSink.  What it does NOT check is the CUDA arithmetic (tests -m gpu do).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import graphlib as G
+from helpers import assert_biteq
+from webradio_b200 import synth
+
+pytestmark = pytest.mark.skipif(not (G.have("mock") and G.have("ref")),
+                                reason="libwr_blocks_harness_mock.so / oracle/_ref not built")
+
+FS, F = 2400000, 20000
+
+
+def counters():
+    lib = G.load("mock")
+    for f in ("wr_mock_bank_process_calls", "wr_mock_stage_calls", "wr_mock_banks_created"):
+        getattr(lib, f).restype = C.c_ulonglong
+    return lib
+
+
+def pair(capture, modes, ifs, **kw):
+    gs = []
+    for which in ("mock", "ref"):
+        g = G.Graph(which, FS, F)
+        for m, f in zip(modes, ifs):
+            g.add_receiver(if_hz=f, mode=m, capture=capture, **kw)
+        assert g.start()
+        gs.append(g)
+    return gs
+
+
+def test_fused_chains_one_bank_call_per_block():
+    modes = ["AM", "FM", "USB", "LSB", "AM", "USB"]
+    ifs = [100000, -345678, 0, 612345, -900000, 7]
+    lib = counters()
+    lib.wr_mock_reset_counters()
+    g, r = pair(0x8, modes, ifs)
+    try:
+        for b in range(4):
+            iq = synth.structured(F, FS, ifs[:4], [0, 1, 0, 0], start=b * F, fm_dev=50000.0)
+            assert g.run(iq) and r.run(iq)
+            for i, m in enumerate(modes):
+                assert_biteq(g.get(i, "audio"), r.get(i, "audio"), f"fused rx{i} {m} block {b}")
+        # six receivers, four blocks: ONE bank, ONE batched call per tuner block, no stage calls
+        assert lib.wr_mock_banks_created() == 1
+        assert lib.wr_mock_bank_process_calls() == 4
+        assert lib.wr_mock_stage_calls() == 0
+    finally:
+        g.close(); r.close()
+
+
+def test_strict_stage_blocks_when_every_stage_is_tapped():
+    modes = ["AM", "FM", "USB", "LSB"]
+    ifs = [100000, -345678, 5, 612345]
+    lib = counters()
+    lib.wr_mock_reset_counters()
+    g, r = pair(0xF, modes, ifs)
+    try:
+        for b in range(3):
+            iq = synth.lattice_noise(F, stream=4, start=b * F)
+            assert g.run(iq) and r.run(iq)
+            for i in range(4):
+                for stage in ("mixed", "channel", "demod", "audio"):
+                    assert_biteq(g.get(i, stage), r.get(i, stage), f"strict rx{i} {stage} b{b}")
+        # a consumer sits between the stages: no bank, four stage calls per receiver per block
+        assert lib.wr_mock_bank_process_calls() == 0
+        assert lib.wr_mock_stage_calls() == 4 * 4 * 3
+    finally:
+        g.close(); r.close()
+
+
+def test_mixed_graph_fused_and_strict_side_by_side():
+    """Receivers 0 and 2 are plain chains (fused), receiver 1 has a tap after the mixer (strict)."""
+    lib = counters()
+    lib.wr_mock_reset_counters()
+    gs = []
+    for which in ("mock", "ref"):
+        g = G.Graph(which, FS, F)
+        g.add_receiver(if_hz=50000, mode="AM", capture=0x8)
+        g.add_receiver(if_hz=-70000, mode="USB", capture=0x9)
+        g.add_receiver(if_hz=123456, mode="FM", capture=0x8)
+        assert g.start()
+        gs.append(g)
+    g, r = gs
+    try:
+        for b in range(3):
+            iq = synth.lattice_noise(F, stream=9, start=b * F)
+            assert g.run(iq) and r.run(iq)
+            for i in range(3):
+                assert_biteq(g.get(i, "audio"), r.get(i, "audio"), f"rx{i} block {b}")
+            assert_biteq(g.get(1, "mixed"), r.get(1, "mixed"), f"rx1 mixed block {b}")
+        assert lib.wr_mock_bank_process_calls() == 3
+        assert lib.wr_mock_stage_calls() == 4 * 3
+    finally:
+        g.close(); r.close()
+
+
+def test_setters_take_effect_at_block_boundaries():
+    """setIF / setModeString / setPassband on running blocks (what the REST handlers do, reference
+    src/web/receiverhandler.cxx:125-140), on fused chains -- FM included."""
+    modes = ["AM", "USB", "FM"]
+    ifs = [50000, -250000, 400000]
+    g, r = pair(0x8, modes, ifs)
+    try:
+        for b in range(7):
+            if b == 2:
+                for x in (g, r):
+                    x.set_if(0, -123456)
+                    assert x.set_mode(1, "LSB")
+            if b == 3:
+                for x in (g, r):
+                    assert x.set_passband(2, 0, 200000) == 200000
+                    assert x.set_passband(2, 1, 20000) == 20000
+            if b == 4:
+                for x in (g, r):
+                    assert x.set_mode(0, "FM")
+                    x.set_if(2, 0)
+            if b == 5:
+                for x in (g, r):
+                    assert x.set_mode(2, "AM")
+                    assert not x.set_mode(1, "CW")       # rejected, mode unchanged (demodulator.cxx:47-56)
+            iq = synth.lattice_noise(F, stream=5, start=b * F)
+            assert g.run(iq) and r.run(iq)
+            for i in range(3):
+                assert_biteq(g.get(i, "audio"), r.get(i, "audio"), f"rx{i} block {b}")
+    finally:
+        g.close(); r.close()
+
+
+@pytest.mark.parametrize("n1,d1,d2", [(127, 50, 1), (255, 50, 1), (64, 8, 4)])
+def test_injected_taps_and_other_geometries(n1, d1, d2):
+    """cfg2 / cfg3 / 2.048 MSPS-style geometries through the blocks: injected channel taps."""
+    fs = 2048000 if d1 == 8 else FS
+    frames = 20480 if d1 == 8 else F
+    t1 = synth.windowed_sinc(n1, 12500 / fs)
+    gs = []
+    for which in ("mock", "ref"):
+        g = G.Graph(which, fs, frames)
+        for i in range(3):
+            g.add_receiver(if_hz=100000 * i - 50000, mode=["USB", "FM", "AM"][i], ch_rate=0, ch_decim=d1,
+                           au_rate=0, au_decim=d2, au_passband=3000, capture=0x8)
+        assert g.start()
+        gs.append(g)
+    g, r = gs
+    try:
+        for i in range(3):
+            g.set_taps(i, 0, t1)
+            r.set_taps(i, 0, t1)
+        for b in range(3):
+            iq = synth.lattice_noise(frames, stream=6, start=b * frames)
+            assert g.run(iq) and r.run(iq)
+            for i in range(3):
+                assert_biteq(g.get(i, "audio"), r.get(i, "audio"), f"{n1}-tap rx{i} block {b}")
+    finally:
+        g.close(); r.close()
+
+
+def test_two_geometries_make_two_banks():
+    """Receivers with different filter geometry cannot share a bank: one bank per geometry, each
+    run once per block."""
+    lib = counters()
+    lib.wr_mock_reset_counters()
+    gs = []
+    for which in ("mock", "ref"):
+        g = G.Graph(which, FS, F)
+        g.add_receiver(if_hz=1000, mode="AM", capture=0x8)                                     # 240 k / 48 k
+        g.add_receiver(if_hz=-2000, mode="USB", capture=0x8)
+        g.add_receiver(if_hz=3000, mode="LSB", ch_rate=0, ch_decim=50, au_rate=0, au_decim=1, capture=0x8)
+        assert g.start()
+        gs.append(g)
+    g, r = gs
+    try:
+        for b in range(2):
+            iq = synth.lattice_noise(F, stream=2, start=b * F)
+            assert g.run(iq) and r.run(iq)
+            for i in range(3):
+                assert_biteq(g.get(i, "audio"), r.get(i, "audio"), f"rx{i} block {b}")
+        assert lib.wr_mock_banks_created() == 2
+        assert lib.wr_mock_bank_process_calls() == 4
+    finally:
+        g.close(); r.close()
+
+
+def test_spectrum_sink_block():
+    n = 512
+    g = G.Graph("mock", FS, F)
+    r = G.Graph("ref", FS, F)
+    try:
+        for x in (g, r):
+            x.add_spectrum(n)
+            x.add_receiver(if_hz=0, mode="AM", capture=0x8)
+            assert x.start()
+        for b in range(3):
+            iq = synth.structured(F, FS, [300000, -700000], [0, 1], start=b * F, noise_db=-40.0)
+            assert g.run(iq) and r.run(iq)
+            assert_biteq(g.spectrum(n), r.spectrum(n), f"spectrum block {b}")
+            assert_biteq(g.get(0, "audio"), r.get(0, "audio"), f"audio next to the spectrum sink, block {b}")
+    finally:
+        g.close(); r.close()
+
+
+def test_profile_counters_count_frames():
+    """DSPBLOCK_PROFILE bookkeeping (dspblock.cxx:186-204): every block of a fused chain still counts
+    the frames it was handed, exactly as the reference's blocks do."""
+    with G.Graph("mock", FS, F) as g, G.Graph("ref", FS, F) as r:
+        for x in (g, r):
+            x.add_receiver(capture=0x8)
+            assert x.start()
+            for b in range(3):
+                assert x.run(synth.lattice_noise(F, stream=1, start=b * F))
+        _, frames = g.profile(0)
+        _, want = r.profile(0)
+        assert frames == want == [3 * F, 3 * F, 3 * F // 10, 3 * F // 10]
+
+
+DROPIN_MOCK = os.path.join(G.ROOT, "tests", "harness", "libwr_radio_dropin_mock.so")
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN_MOCK), reason="libwr_radio_dropin_mock.so not built (needs the reference tree)")
+def test_reference_radio_glue_drives_the_dropin_blocks():
+    """The reference's UNMODIFIED src/radio.cxx (FrontEnd / Receiver / Radio::run) compiled against
+    the drop-in headers and driven as src/main.cxx drives it -- the host half of the drop-in claim,
+    on the CPU stand-in; tests/test_blocks_gpu.py runs the same rig on the CUDA library."""
+    L = C.CDLL(DROPIN_MOCK)
+    fp = C.POINTER(C.c_float)
+    L.wrr_create.restype = C.c_void_p
+    L.wrr_create.argtypes = [C.c_uint, C.c_uint, C.c_uint]
+    L.wrr_add_receiver.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    L.wrr_start.argtypes = [C.c_void_p]
+    L.wrr_run.argtypes = [C.c_void_p, fp]
+    L.wrr_retune.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_uint]
+    L.wrr_audio.restype = C.c_long
+    L.wrr_audio.argtypes = [C.c_void_p, C.c_int, fp, C.c_long]
+    L.wrr_spectrum.argtypes = [C.c_void_p, fp]
+    L.wrr_destroy.argtypes = [C.c_void_p]
+    L.wr_mock_bank_process_calls.restype = C.c_ulonglong
+    L.wr_mock_stage_calls.restype = C.c_ulonglong
+
+    frames = 102400  # the shipped block: 204800 floats (reference src/main.cxx:75)
+    rig = L.wrr_create(FS, frames, 512)
+    modes = ["AM", "USB", "FM", "AM"]
+    ifs = [0, 100000, -200000, 555555]
+    ref = G.Graph("ref", FS, frames)
+    ref.add_spectrum(512)
+    for m, f in zip(modes, ifs):
+        assert L.wrr_add_receiver(rig, f, m.encode()) >= 0
+        ref.add_receiver(if_hz=f, mode=m, capture=0x8)  # same defaults as Receiver() (radio.cxx:78-82)
+    assert L.wrr_start(rig) == 0 and ref.start()
+    try:
+        for b in range(3):
+            if b == 2:
+                assert L.wrr_retune(rig, 1, -77777, b"LSB", 100000) == 0
+                ref.set_if(1, -77777); ref.set_mode(1, "LSB"); ref.set_passband(1, 0, 100000)
+            iq = synth.lattice_noise(frames, stream=11, start=b * frames)
+            assert L.wrr_run(rig, iq.ctypes.data_as(fp)) == 0
+            assert ref.run(iq)
+            for i in range(4):
+                n = L.wrr_audio(rig, i, None, 0)
+                assert n == frames // 50
+                got = np.empty(n, np.float32)
+                L.wrr_audio(rig, i, got.ctypes.data_as(fp), n)
+                assert_biteq(got, ref.get(i, "audio"), f"radio.cxx drop-in rx{i} block {b}")
+            db = np.empty(512, np.float32)
+            assert L.wrr_spectrum(rig, db.ctypes.data_as(fp)) == 512
+            assert_biteq(db, ref.spectrum(512), f"spectrum block {b}")
+        # Radio::run visits four receivers per block; the first visit runs the one bank
+        assert L.wr_mock_bank_process_calls() == 3 and L.wr_mock_stage_calls() == 0
+    finally:
+        L.wrr_destroy(rig)
+        ref.close()
