@@ -123,6 +123,13 @@ int wr_rx_reset(wr_bank *b, unsigned rx, unsigned flags);
 int wr_rx_set_phase(wr_bank *b, unsigned rx, uint32_t phase);
 /* Read back NCO phase (reference downconverter.h:58) as of the last completed block. */
 int wr_rx_get_phase(wr_bank *b, unsigned rx, uint32_t *phase);
+/* The FM discriminator's look-back sample {prev_i, prev_q} (reference demodulator.h:60-61; set in
+ * the constructor only, so the reference's Demodulator carries it across stop()/start(), e.g.
+ * Receiver::setFrontEnd on a live radio, radio.cxx:109-117): read it as of the last completed
+ * block, or overwrite it (takes effect at the next block boundary) -- lets a receiver take it
+ * along from one bank to another.  prev_iq has two floats. */
+int wr_rx_get_lookback(wr_bank *b, unsigned rx, float *prev_iq);
+int wr_rx_set_lookback(wr_bank *b, unsigned rx, const float *prev_iq);
 
 /* One block through every receiver, HOST buffers (the DspBlock::process data convention,
  * reference src/dsp/dspblock.cxx:177-195: synchronous, results host-visible on return).

@@ -233,6 +233,30 @@ long wrh_graph_get(void *h, int rx, int stage, float *out, long cap)
 	return n;
 }
 
+/* Receiver::setFrontEnd(NULL) / setFrontEnd(frontEnd) on a live pipeline (reference
+ * radio.cxx:109-117,151-163): the tuner disconnects the chain's first block, which stops the
+ * chain (dspblock.cxx:78-91), or connects it again, which starts it on the spot with the rates it
+ * was last given (dspblock.cxx:57-76). */
+int wrh_graph_detach(void *h, int rx)
+{
+	Graph *g = (Graph*)h;
+	if (rx < 0 || rx >= (int)g->rx.size())
+		return -1;
+	QuietStderr q(g_quiet);
+	g->src->disconnect(g->rx[rx].dc);
+	return 0;
+}
+
+int wrh_graph_attach(void *h, int rx)
+{
+	Graph *g = (Graph*)h;
+	if (rx < 0 || rx >= (int)g->rx.size())
+		return -1;
+	QuietStderr q(g_quiet);
+	g->src->connect(g->rx[rx].dc);
+	return g->rx[rx].dc->isRunning() ? 0 : -1;
+}
+
 int wrh_graph_set_if(void *h, int rx, int hz)
 {
 	Graph *g = (Graph*)h;

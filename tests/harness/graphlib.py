@@ -39,6 +39,9 @@ def _bind(path):
     lib.wrh_graph_get.restype = C.c_long
     lib.wrh_graph_get.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp, C.c_long]
     lib.wrh_graph_set_if.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    if hasattr(lib, "wrh_graph_detach"):
+        lib.wrh_graph_detach.argtypes = [C.c_void_p, C.c_int]
+        lib.wrh_graph_attach.argtypes = [C.c_void_p, C.c_int]
     lib.wrh_graph_set_mode.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
     lib.wrh_graph_get_mode.argtypes = [C.c_void_p, C.c_int]
     lib.wrh_graph_set_passband.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint]
@@ -116,6 +119,14 @@ class Graph:
         out = np.empty(n, dtype=np.float32)
         self.lib.wrh_graph_get(self.h, rx, s, out.ctypes.data_as(_fp), n)
         return out
+
+    def detach(self, rx):
+        """Receiver::setFrontEnd(NULL) on a live pipeline."""
+        return self.lib.wrh_graph_detach(self.h, rx) == 0
+
+    def attach(self, rx):
+        """Receiver::setFrontEnd(frontEnd) on a live pipeline; False if the chain did not start."""
+        return self.lib.wrh_graph_attach(self.h, rx) == 0
 
     def set_if(self, rx, hz):
         return self.lib.wrh_graph_set_if(self.h, rx, hz)

@@ -156,6 +156,38 @@ int wr_rx_get_phase(wr_bank *b, unsigned rx, uint32_t *phase)
 	return WR_OK;
 }
 
+int wr_rx_reset(wr_bank *b, unsigned rx, unsigned flags)
+{
+	if (!b || rx >= b->R)
+		return WR_EINVAL;
+	Rx &x = b->rx[rx];
+	if (flags & WR_RESET_PHASE)
+		x.phase = 0;
+	if (flags & WR_RESET_DEMOD)
+		x.prev[0] = x.prev[1] = 0.0f;
+	if (flags & (WR_RESET_CHANNEL | WR_RESET_AUDIO))
+		return WR_EINVAL;   /* not needed by the blocks; the oracle's FIR has no history reset */
+	return WR_OK;
+}
+
+int wr_rx_set_lookback(wr_bank *b, unsigned rx, const float *prev_iq)
+{
+	if (!b || rx >= b->R || !prev_iq)
+		return WR_EINVAL;
+	b->rx[rx].prev[0] = prev_iq[0];
+	b->rx[rx].prev[1] = prev_iq[1];
+	return WR_OK;
+}
+
+int wr_rx_get_lookback(wr_bank *b, unsigned rx, float *prev_iq)
+{
+	if (!b || rx >= b->R || !prev_iq)
+		return WR_EINVAL;
+	prev_iq[0] = b->rx[rx].prev[0];
+	prev_iq[1] = b->rx[rx].prev[1];
+	return WR_OK;
+}
+
 int wr_bank_process(wr_bank *b, const float *iq_host, unsigned nframes, float *audio_host, size_t audio_stride)
 {
 	if (!b || !iq_host || !audio_host || nframes > b->maxF)

@@ -228,6 +228,39 @@ def test_profile_counters_count_frames():
         assert frames == want == [3 * F, 3 * F, 3 * F // 10, 3 * F // 10]
 
 
+@pytest.mark.parametrize("capture", [0x8, 0xF], ids=["fused", "strict"])
+def test_hot_detach_and_reattach(capture):
+    """tests/lookback_cases.py::hot_reattach on the stand-in (assert_fm is bit-exact on a glibc box)."""
+    import lookback_cases as LC
+    lib = counters()
+    lib.wr_mock_reset_counters()
+    LC.hot_reattach("mock", capture)
+    if capture == 0x8:
+        # fused throughout; each re-attached chain got a bank of its own
+        assert lib.wr_mock_stage_calls() == 0
+        assert lib.wr_mock_banks_created() == 3
+
+
+def test_lookback_travels_between_strict_and_fused():
+    """A chain that starts strict-free (fused), is stopped and comes back keeps its discriminator
+    history; checked directly on the stand-in's bank API as the blocks use it."""
+    lib = G.load("mock")
+    fp = C.POINTER(C.c_float)
+    lib.wr_bank_create.restype = C.c_void_p
+    lib.wr_bank_create.argtypes = [C.c_int] + [C.c_uint] * 7
+    lib.wr_rx_set_lookback.argtypes = [C.c_void_p, C.c_uint, fp]
+    lib.wr_rx_get_lookback.argtypes = [C.c_void_p, C.c_uint, fp]
+    lib.wr_bank_destroy.argtypes = [C.c_void_p]
+    b = lib.wr_bank_create(0, 1, 2, 1000, 64, 10, 64, 5)
+    v = (C.c_float * 2)(0.25, -0.5)
+    assert lib.wr_rx_set_lookback(b, 1, v) == 0
+    w = (C.c_float * 2)()
+    assert lib.wr_rx_get_lookback(b, 1, w) == 0 and (w[0], w[1]) == (0.25, -0.5)
+    assert lib.wr_rx_get_lookback(b, 0, w) == 0 and (w[0], w[1]) == (0.0, 0.0)
+    assert lib.wr_rx_get_lookback(b, 2, w) != 0
+    lib.wr_bank_destroy(b)
+
+
 DROPIN_MOCK = os.path.join(G.ROOT, "tests", "harness", "libwr_radio_dropin_mock.so")
 
 
@@ -283,3 +316,79 @@ def test_reference_radio_glue_drives_the_dropin_blocks():
     finally:
         L.wrr_destroy(rig)
         ref.close()
+
+
+class MockBank:
+    """capi.Bank's methods (the subset tests/lookback_cases.py uses) over the CPU stand-in."""
+
+    def __init__(self, n_rx, max_frames, n1, d1, n2, d2):
+        L = self.L = G.load("mock")
+        fp, vp, u = C.POINTER(C.c_float), C.c_void_p, C.c_uint
+        L.wr_bank_create.restype = vp
+        L.wr_bank_create.argtypes = [C.c_int] + [u] * 7
+        L.wr_bank_destroy.argtypes = [vp]
+        L.wr_rx_set_taps.argtypes = [vp, u, C.c_int, fp, u]
+        L.wr_rx_set_phase_step.argtypes = [vp, u, C.c_int32]
+        L.wr_rx_set_mode.argtypes = [vp, u, C.c_int]
+        L.wr_rx_set_phase.argtypes = [vp, u, C.c_uint32]
+        L.wr_rx_get_phase.argtypes = [vp, u, C.POINTER(C.c_uint32)]
+        L.wr_rx_set_lookback.argtypes = [vp, u, fp]
+        L.wr_rx_get_lookback.argtypes = [vp, u, fp]
+        L.wr_rx_reset.argtypes = [vp, u, u]
+        L.wr_bank_process.argtypes = [vp, fp, u, fp, C.c_size_t]
+        self.R, self.d1, self.d2 = n_rx, d1, d2
+        self.h = L.wr_bank_create(0, 1, n_rx, max_frames, n1, d1, n2, d2)
+        assert self.h
+
+    def close(self):
+        if self.h:
+            self.L.wr_bank_destroy(self.h)
+            self.h = None
+
+    def set_taps(self, rx, stage, coeff):
+        c = np.ascontiguousarray(coeff, np.float32)
+        assert self.L.wr_rx_set_taps(self.h, rx, stage, c.ctypes.data_as(C.POINTER(C.c_float)), c.size) == 0
+
+    def set_phase_step(self, rx, step):
+        assert self.L.wr_rx_set_phase_step(self.h, rx, step) == 0
+
+    def set_mode(self, rx, mode):
+        assert self.L.wr_rx_set_mode(self.h, rx, mode) == 0
+
+    def set_phase(self, rx, phase):
+        assert self.L.wr_rx_set_phase(self.h, rx, phase) == 0
+
+    def get_phase(self, rx):
+        v = C.c_uint32(0)
+        assert self.L.wr_rx_get_phase(self.h, rx, C.byref(v)) == 0
+        return v.value
+
+    def set_lookback(self, rx, iq):
+        v = (C.c_float * 2)(float(iq[0]), float(iq[1]))
+        assert self.L.wr_rx_set_lookback(self.h, rx, v) == 0
+
+    def get_lookback(self, rx):
+        v = (C.c_float * 2)()
+        assert self.L.wr_rx_get_lookback(self.h, rx, v) == 0
+        return np.array([v[0], v[1]], np.float32)
+
+    def reset(self, rx, flags):
+        assert self.L.wr_rx_reset(self.h, rx, flags) == 0
+
+    def process(self, iq):
+        a = np.ascontiguousarray(iq, np.float32)
+        n = a.size // 2
+        m2 = n // self.d1 // self.d2
+        out = np.zeros((self.R, m2), np.float32)
+        fp = C.POINTER(C.c_float)
+        assert self.L.wr_bank_process(self.h, a.ctypes.data_as(fp), n, out.ctypes.data_as(fp), m2) == 0
+        return out
+
+
+def test_lookback_carry_over_case_on_the_stand_in(wro):
+    """The body tests/test_zz_lookback_gpu.py runs on the CUDA library, dry-run here."""
+    import lookback_cases as LC
+    t1 = wro.lowpass_design(LC.N1, 80000, LC.FS)
+    t2 = wro.lowpass_design(LC.N2, 8000, LC.FS // LC.D1)
+    LC.carry_over(lambda: MockBank(1, LC.F, LC.N1, LC.D1, LC.N2, LC.D2), wro, t1, t2,
+                  wro.phase_step(LC.IF_HZ, LC.FS))

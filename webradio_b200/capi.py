@@ -25,7 +25,7 @@ SYMBOLS = [
     "wr_version", "wr_last_error", "wr_device_count", "wr_phase_step", "wr_build_sintable",
     "wr_lowpass_design", "wr_lo_compress_check", "wr_lo3_compress_check", "wr_atan2f_host",
     "wr_bank_create", "wr_bank_destroy", "wr_bank_set_sintable", "wr_rx_set_stream",
-    "wr_rx_set_phase_step", "wr_rx_set_taps", "wr_bank_design_taps", "wr_rx_get_taps", "wr_rx_set_mode", "wr_rx_reset", "wr_rx_set_phase", "wr_rx_get_phase",
+    "wr_rx_set_phase_step", "wr_rx_set_taps", "wr_bank_design_taps", "wr_rx_get_taps", "wr_rx_set_mode", "wr_rx_reset", "wr_rx_set_phase", "wr_rx_get_phase", "wr_rx_set_lookback", "wr_rx_get_lookback",
     "wr_bank_process", "wr_bank_process_device", "wr_bank_submit", "wr_bank_wait",
     "wr_bank_process_u8", "wr_bank_process_device_u8", "wr_bank_submit_u8",
     "wr_bank_run_device_steps_u8", "wr_bank_run_host_steps_u8",
@@ -75,6 +75,8 @@ def lib():
     L.wr_rx_reset.argtypes = [vp, u, u]
     L.wr_rx_set_phase.argtypes = [vp, u, C.c_uint32]
     L.wr_rx_get_phase.argtypes = [vp, u, C.POINTER(C.c_uint32)]
+    L.wr_rx_set_lookback.argtypes = [vp, u, C.POINTER(C.c_float)]
+    L.wr_rx_get_lookback.argtypes = [vp, u, C.POINTER(C.c_float)]
     L.wr_bank_process.argtypes = [vp, vp, u, vp, sz]
     L.wr_bank_process_device.argtypes = [vp, vp, sz, u, vp, sz, vp]
     L.wr_bank_submit.argtypes = [vp, vp, u, vp, sz]
@@ -228,6 +230,16 @@ class Bank:
         v = C.c_uint32(0)
         _check(self.L.wr_rx_get_phase(self.h, rx, C.byref(v)), "wr_rx_get_phase")
         return v.value
+
+    def set_lookback(self, rx, prev_iq):
+        """The FM discriminator's look-back sample (prev_i, prev_q); applies at the next block."""
+        v = (C.c_float * 2)(float(prev_iq[0]), float(prev_iq[1]))
+        _check(self.L.wr_rx_set_lookback(self.h, rx, v), "wr_rx_set_lookback")
+
+    def get_lookback(self, rx):
+        v = (C.c_float * 2)()
+        _check(self.L.wr_rx_get_lookback(self.h, rx, v), "wr_rx_get_lookback")
+        return np.array([v[0], v[1]], np.float32)
 
     def out_frames(self, nframes):
         return nframes // self.d1 // self.d2

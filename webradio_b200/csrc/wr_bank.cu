@@ -29,9 +29,10 @@ constexpr int kSlots = 6;        // most blocks the submit/wait path keeps in fl
 constexpr int kThreadsV1 = 128;
 
 constexpr unsigned kSetPhase = 0x100u; // internal flag: overwrite the phase with a given value
+constexpr unsigned kSetPrev = 0x200u;  // internal flag: overwrite the FM look-back sample with a given value
 
 __global__ void reset_kernel(RxState *st, float2 *hist1, float *demod_hist, unsigned rx,
-		unsigned n1m1, unsigned n2m1, size_t dstride, unsigned flags, uint32_t phaseValue)
+		unsigned n1m1, unsigned n2m1, size_t dstride, unsigned flags, uint32_t phaseValue, float2 prevValue)
 {
 	const unsigned tid = threadIdx.x;
 	if (tid == 0) {
@@ -42,6 +43,10 @@ __global__ void reset_kernel(RxState *st, float2 *hist1, float *demod_hist, unsi
 		if (flags & WR_RESET_DEMOD) {
 			st[rx].prev_i = 0.0f;
 			st[rx].prev_q = 0.0f;
+		}
+		if (flags & kSetPrev) {
+			st[rx].prev_i = prevValue.x;
+			st[rx].prev_q = prevValue.y;
 		}
 	}
 	if (flags & WR_RESET_CHANNEL)
@@ -173,6 +178,7 @@ struct wr_bank {
 	std::vector<float> h_taps1, h_taps2;   // reversed, as the kernels read them
 	std::vector<unsigned> h_reset;         // pending WR_RESET_* per receiver
 	std::vector<uint32_t> h_phase;         // pending wr_rx_set_phase values
+	std::vector<float2> h_prev;            // pending wr_rx_set_lookback values
 	bool confDirty = true, taps1Dirty = true, taps2Dirty = true, resetDirty = false;
 	bool tableDirty = false;
 	bool streamsDirty = true;              // receiver -> stream map changed (v2 regroups)
@@ -292,7 +298,7 @@ int apply_pending(wr_bank *b, cudaStream_t st)
 			if (!b->h_reset[r])
 				continue;
 			reset_kernel<<<1, 128, 0, st>>>(b->d_state[b->cur], b->d_hist1[b->cur], b->d_demod[b->cur],
-					r, b->n1 - 1, b->n2 - 1, b->dstride, b->h_reset[r], b->h_phase[r]);
+					r, b->n1 - 1, b->n2 - 1, b->dstride, b->h_reset[r], b->h_phase[r], b->h_prev[r]);
 			b->launches++;
 			b->h_reset[r] = 0;
 		}
@@ -757,6 +763,7 @@ wr_bank *wr_bank_create(int device, unsigned n_streams, unsigned n_receivers, un
 	b->h_taps2.assign((size_t)R * n2, 0.0f);
 	b->h_reset.assign(R, 0);
 	b->h_phase.assign(R, 0);
+	b->h_prev.assign(R, make_float2(0.0f, 0.0f));
 	b->h_table.resize(WR_SINTABLE_SIZE);
 	wr_build_sintable(b->h_table.data());
 	b->tableDirty = true;
@@ -894,6 +901,8 @@ int wr_rx_reset(wr_bank *b, unsigned rx, unsigned flags)
 	WR_REQUIRE(b && rx < b->R, WR_EINVAL, "wr_rx_reset: rx %u out of range", rx);
 	std::lock_guard<std::mutex> lk(b->mu);
 	b->h_reset[rx] |= flags;
+	if (flags & WR_RESET_DEMOD)
+		b->h_reset[rx] &= ~kSetPrev;   // a reset after wr_rx_set_lookback wins
 	b->resetDirty = true;
 	return WR_OK;
 }
@@ -917,6 +926,29 @@ int wr_rx_get_phase(wr_bank *b, unsigned rx, uint32_t *phase)
 	RxState st;
 	WR_CUDA(cudaMemcpy(&st, b->d_state[b->cur] + rx, sizeof(st), cudaMemcpyDeviceToHost));
 	*phase = st.phase;
+	return WR_OK;
+}
+
+int wr_rx_set_lookback(wr_bank *b, unsigned rx, const float *prev_iq)
+{
+	WR_REQUIRE(b && prev_iq && rx < b->R, WR_EINVAL, "wr_rx_set_lookback: bad argument");
+	std::lock_guard<std::mutex> lk(b->mu);
+	b->h_reset[rx] = (b->h_reset[rx] & ~WR_RESET_DEMOD) | kSetPrev;
+	b->h_prev[rx] = make_float2(prev_iq[0], prev_iq[1]);
+	b->resetDirty = true;
+	return WR_OK;
+}
+
+int wr_rx_get_lookback(wr_bank *b, unsigned rx, float *prev_iq)
+{
+	WR_REQUIRE(b && prev_iq && rx < b->R, WR_EINVAL, "wr_rx_get_lookback: bad argument");
+	if (!wr::use_device(b->device))
+		return WR_ENODEV;
+	WR_CUDA(cudaStreamSynchronize(b->compute));
+	RxState st;
+	WR_CUDA(cudaMemcpy(&st, b->d_state[b->cur] + rx, sizeof(st), cudaMemcpyDeviceToHost));
+	prev_iq[0] = st.prev_i;
+	prev_iq[1] = st.prev_q;
 	return WR_OK;
 }
 

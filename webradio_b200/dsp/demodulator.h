@@ -33,6 +33,10 @@ public:
 
 	// ---- fused-bank hand-off ----
 	void setFused(bool fused) { _fused = fused; }
+	// the FM look-back sample travels with the block: into a bank when the chain joins one, back
+	// out when it leaves (the reference's prev_i/prev_q live in the object, demodulator.h:60-61)
+	const float *lookback() const { return prev; }
+	void setLookback(const float *iq) { prev[0] = iq[0]; prev[1] = iq[1]; }
 
 private:
 	bool init();

@@ -51,6 +51,7 @@ bool fusable(DownConverter *dc, Chain *out)
 	out->audio = audio;
 	out->step = 0;
 	out->phase0 = 0;
+	out->prev0[0] = out->prev0[1] = 0.0f;
 	out->mode = -1;
 	out->chanTapsVersion = out->audioTapsVersion = 0;
 	out->active = true;
@@ -104,8 +105,10 @@ bool FusedBank::seal(unsigned nframes)
 		LOG_ERROR("receiver bank: %s\n", wr_last_error());
 		return false;
 	}
-	for (size_t i = 0; i < _chains.size(); i++)
+	for (size_t i = 0; i < _chains.size(); i++) {
 		wr_rx_set_phase(_bank, (unsigned)i, _chains[i].phase0);
+		wr_rx_set_lookback(_bank, (unsigned)i, _chains[i].prev0);
+	}
 	_audioStride = std::max(1u, nframes / _d1 / _d2);
 	_audio.assign((size_t)_audioStride * _chains.size(), 0.0f);
 	LOG_DEBUG("receiver bank: %u chains fused on device %d (taps %u/%u, decimation %u/%u)\n",
@@ -229,6 +232,8 @@ FusedBank *planFor(DownConverter *dc, int *slot)
 				sc.audio->firLength() != n2 || sc.audio->DspBlock::decimation() != d2)
 			continue;
 		sc.phase0 = d->phaseNow();
+		sc.prev0[0] = sc.demod->lookback()[0];
+		sc.prev0[1] = sc.demod->lookback()[1];
 		int s = target->add(sc);
 		sc.chan->attachBank(target, s, false);
 		sc.demod->setFused(true);
@@ -273,6 +278,10 @@ void FusedBank::detach(int slot)
 		return;
 	Chain &c = _chains[slot];
 	c.chan->detachBank();
+	// the discriminator's look-back sample goes back into the block it belongs to
+	float prev[2];
+	if (_bank && wr_rx_get_lookback(_bank, (unsigned)slot, prev) == WR_OK)
+		c.demod->setLookback(prev);
 	c.demod->setFused(false);
 	c.audio->detachBank();
 	c.active = false;

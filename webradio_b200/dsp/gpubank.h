@@ -35,6 +35,7 @@ struct Chain {
 	// what was last pushed to the bank
 	int32_t step;
 	uint32_t phase0; // NCO phase the chain brings along when it joins
+	float prev0[2];  // ... and the FM look-back sample (prev_i, prev_q)
 	int mode;
 	uint64_t chanTapsVersion, audioTapsVersion;
 	bool active;
