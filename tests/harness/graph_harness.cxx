@@ -257,6 +257,17 @@ int wrh_graph_attach(void *h, int rx)
 	return g->rx[rx].dc->isRunning() ? 0 : -1;
 }
 
+/* DspSource::stop() then start() (what a tuner restart does, reference dspblock.cxx:106-167): every
+ * block is deinitialised and initialised again. */
+int wrh_graph_restart(void *h)
+{
+	Graph *g = (Graph*)h;
+	QuietStderr q(g_quiet);
+	g->src->stop();
+	g->started = g->src->start();
+	return g->started ? 0 : -1;
+}
+
 int wrh_graph_set_if(void *h, int rx, int hz)
 {
 	Graph *g = (Graph*)h;

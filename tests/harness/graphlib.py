@@ -42,6 +42,8 @@ def _bind(path):
     if hasattr(lib, "wrh_graph_detach"):
         lib.wrh_graph_detach.argtypes = [C.c_void_p, C.c_int]
         lib.wrh_graph_attach.argtypes = [C.c_void_p, C.c_int]
+    if hasattr(lib, "wrh_graph_restart"):
+        lib.wrh_graph_restart.argtypes = [C.c_void_p]
     lib.wrh_graph_set_mode.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
     lib.wrh_graph_get_mode.argtypes = [C.c_void_p, C.c_int]
     lib.wrh_graph_set_passband.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint]
@@ -127,6 +129,10 @@ class Graph:
     def attach(self, rx):
         """Receiver::setFrontEnd(frontEnd) on a live pipeline; False if the chain did not start."""
         return self.lib.wrh_graph_attach(self.h, rx) == 0
+
+    def restart(self):
+        """DspSource::stop() followed by start()."""
+        return self.lib.wrh_graph_restart(self.h) == 0
 
     def set_if(self, rx, hz):
         return self.lib.wrh_graph_set_if(self.h, rx, hz)

@@ -102,7 +102,13 @@ def hot_reattach(which, capture):
         gs.append(g)
     g, r = gs
     try:
-        for b in range(9):
+        for b in range(11):
+            if b == 9:
+                # the whole pipeline stopped and started again (a tuner restart): every chain is
+                # re-initialised at once, with all receivers attached
+                for x in (g, r):
+                    assert x.attach(0)
+                    assert x.restart()
             if b == 2:
                 for x in (g, r):
                     assert x.detach(1)
