@@ -315,6 +315,37 @@ def test_spectrum_sink_sizes(n, first):
         g.close(); r.close()
 
 
+def test_extreme_setter_values():
+    """IFs at and beyond Nyquist, the int range's ends, pass-bands of 0, above the sample rate and one
+    that collapses the design to all-zero taps: step arithmetic (downconverter.cxx:65,80) and design
+    (lowpass.cxx:164-189) wrap and truncate exactly as the reference's."""
+    modes = ["AM", "FM", "USB", "LSB"]
+    ifs = [1199999, -1200000, 2400000, -7777777]
+    g, r = pair(0x8, modes, ifs)
+    try:
+        for b in range(8):
+            if b == 2:
+                for x in (g, r):
+                    assert x.set_passband(0, 0, 12500) == 12500 and x.set_passband(1, 1, 100) == 100
+                    assert x.set_passband(2, 0, 1200000) == 1200000 and x.set_passband(3, 1, 120000) == 120000
+            if b == 4:
+                for x in (g, r):
+                    assert x.set_if(0, 2**31 - 1) == 2**31 - 1 and x.set_if(1, -2**31) == -2**31
+                    x.set_if(2, 123456789)
+            if b == 6:
+                for x in (g, r):
+                    assert x.set_passband(0, 0, 0) == 0
+                    x.set_passband(1, 0, 4000000000)
+            iq = synth.lattice_noise(F, stream=5, start=b * F)
+            assert g.run(iq) and r.run(iq)
+            for i in range(4):
+                assert_biteq(g.get_taps(i, 0), r.get_taps(i, 0), f"rx{i} channel taps block {b}")
+                assert_biteq(g.get_taps(i, 1), r.get_taps(i, 1), f"rx{i} audio taps block {b}")
+                assert_biteq(g.get(i, "audio"), r.get(i, "audio"), f"rx{i} block {b}")
+    finally:
+        g.close(); r.close()
+
+
 DROPIN_MOCK = os.path.join(G.ROOT, "tests", "harness", "libwr_radio_dropin_mock.so")
 
 
