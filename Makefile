@@ -6,6 +6,7 @@
 #   make oracle     -> oracle/libwr_oracle.so and, where /root/reference is mounted, oracle/_ref/
 NVCC     ?= nvcc
 CXX      ?= g++
+CC       ?= gcc
 ARCH     := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS  := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude -Iwebradio_b200/csrc
 # sample path: every product/sum is an explicit _rn intrinsic; -fmad=false is belt and braces
@@ -17,7 +18,7 @@ HARNESS  := tests/harness/libwr_blocks_harness.so
 BLOCKSRC := webradio_b200/dsp/dspblock.cxx webradio_b200/dsp/downconverter.cxx webradio_b200/dsp/lowpass.cxx \
             webradio_b200/dsp/demodulator.cxx webradio_b200/io/spectrumsink.cxx webradio_b200/dsp/gpubank.cxx
 
-.PHONY: all lib harness harness-mock dropin dropin-mock oracle tools clean
+.PHONY: all lib harness harness-mock dropin dropin-mock asan-check oracle tools clean
 all: lib
 lib: $(LIB)
 
@@ -53,6 +54,18 @@ $(HARNESS_MOCK): tests/harness/graph_harness.cxx tests/harness/mock_capi.cxx $(B
 	$(CXX) -std=c++11 -O2 -fPIC -Wall -shared -Iinclude -Iwebradio_b200 -Iwebradio_b200/dsp -Iwebradio_b200/io \
 	  -o $@ tests/harness/graph_harness.cxx tests/harness/mock_capi.cxx $(BLOCKSRC) build/wr_host.o \
 	  -Loracle -lwr_oracle -L$(CUDA_LIB) -lcudart_static -Wl,-Bsymbolic -Wl,-rpath,'$$ORIGIN/../../oracle' -lpthread -ldl -lrt
+
+# Host logic of the drop-in blocks under AddressSanitizer + UBSan (stand-in back-end, no GPU)
+ASAN_CC  ?= /usr/bin/gcc
+ASAN_CXX ?= /usr/bin/g++
+asan-check: build/wr_host.o
+	@mkdir -p build
+	$(ASAN_CC) -std=c11 -O1 -g -ffp-contract=off -fsanitize=address,undefined -c oracle/wr_oracle.c -o build/wr_oracle_asan.o
+	$(ASAN_CXX) -std=c++11 -O1 -g -DWR_QUIET_DEBUG -fsanitize=address,undefined -fno-omit-frame-pointer -Iinclude -Iwebradio_b200 \
+	  -Iwebradio_b200/dsp -Iwebradio_b200/io -o build/host_scenario_asan tests/harness/host_scenario.cxx \
+	  tests/harness/graph_harness.cxx tests/harness/mock_capi.cxx $(BLOCKSRC) build/wr_oracle_asan.o build/wr_host.o \
+	  -L$(CUDA_LIB) -lcudart_static -lpthread -ldl -lrt -lm
+	ASAN_OPTIONS=detect_leaks=1 UBSAN_OPTIONS=halt_on_error=1 ./build/host_scenario_asan
 
 # The reference's own graph glue (src/radio.cxx, UNMODIFIED, compiled where it lies) linked against
 # the drop-in blocks.  Only buildable where the reference tree is mounted; the .so travels.

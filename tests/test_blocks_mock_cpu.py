@@ -477,3 +477,19 @@ def test_lookback_carry_over_case_on_the_stand_in(wro):
     t2 = wro.lowpass_design(LC.N2, 8000, LC.FS // LC.D1)
     LC.carry_over(lambda: MockBank(1, LC.F, LC.N1, LC.D1, LC.N2, LC.D2), wro, t1, t2,
                   wro.phase_step(LC.IF_HZ, LC.FS))
+
+
+def test_host_logic_under_address_sanitizer():
+    """make asan-check: tests/harness/host_scenario.cxx (detach / attach / restart / teardown in both
+    orders on two live pipelines) built with -fsanitize=address,undefined over the stand-in."""
+    import shutil
+    import subprocess
+    if not shutil.which("make") or not shutil.which("g++"):
+        pytest.skip("no toolchain")
+    p = subprocess.run(["make", "-s", "asan-check"], cwd=G.ROOT, capture_output=True, text=True, timeout=600)
+    out = p.stdout + p.stderr
+    if "cannot find -lasan" in out or "cannot find -lubsan" in out or "libasan" in out and "No such file" in out:
+        pytest.skip("sanitizer runtime not installed")
+    assert p.returncode == 0, out[-3000:]
+    assert "scenario done" in out
+    assert "AddressSanitizer" not in out and "runtime error" not in out, out[-3000:]

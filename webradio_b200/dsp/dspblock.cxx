@@ -31,6 +31,15 @@ DspBlock::~DspBlock()
 	// reference dspblock.cxx:51-55
 	if (_isRunning)
 		stop();
+	// Blocks may be deleted in either order (the reference's destructor never looks at its
+	// consumers unless it is running).  The upstream() link added here must not change that: a
+	// consumer that goes away takes itself off its producer's list, so the loop below only ever
+	// walks over live blocks.
+	if (_producer) {
+		vector<DspBlock*> &siblings = _producer->_consumers;
+		siblings.erase(std::remove(siblings.begin(), siblings.end(), this), siblings.end());
+		g_topologySerial++;
+	}
 	for (size_t i = 0; i < _consumers.size(); i++)
 		if (_consumers[i]->_producer == this)
 			_consumers[i]->_producer = NULL;

@@ -78,14 +78,16 @@ bool LowPass::init()
 		return false;
 	}
 	recalculate();
-	// a (re)started filter begins with an all-zero history (the reference frees `block` in deinit)
-	if (stage)
-		wr_stage_fir_reset(stage);
 	return true;
 }
 
+// reference lowpass.cxx:118-129.  The history goes HERE, with `block` -- not in init(): a block
+// that is started twice without a stop in between (DspBlock::connect of an already connected
+// consumer on a live pipeline, dspblock.cxx:59-62) keeps filtering where it was.
 void LowPass::deinit()
 {
+	if (stage)
+		wr_stage_fir_reset(stage);
 	std::lock_guard<std::mutex> lk(tapsLock);
 	vector<float>().swap(coeff);
 }
