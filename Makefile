@@ -18,7 +18,7 @@ HARNESS  := tests/harness/libwr_blocks_harness.so
 BLOCKSRC := webradio_b200/dsp/dspblock.cxx webradio_b200/dsp/downconverter.cxx webradio_b200/dsp/lowpass.cxx \
             webradio_b200/dsp/demodulator.cxx webradio_b200/io/spectrumsink.cxx webradio_b200/dsp/gpubank.cxx
 
-.PHONY: all lib harness harness-mock dropin dropin-mock asan-check oracle tools clean
+.PHONY: all lib harness harness-mock dropin dropin-mock asan-check tsan-check oracle tools clean
 all: lib
 lib: $(LIB)
 
@@ -66,6 +66,16 @@ asan-check: build/wr_host.o
 	  tests/harness/graph_harness.cxx tests/harness/mock_capi.cxx $(BLOCKSRC) build/wr_oracle_asan.o build/wr_host.o \
 	  -L$(CUDA_LIB) -lcudart_static -lpthread -ldl -lrt -lm
 	ASAN_OPTIONS=detect_leaks=1 UBSAN_OPTIONS=halt_on_error=1 ./build/host_scenario_asan
+
+# ... and under ThreadSanitizer: the DSP thread against two threads doing what the REST handlers do
+tsan-check: build/wr_host.o
+	@mkdir -p build
+	$(ASAN_CC) -std=c11 -O1 -g -ffp-contract=off -fsanitize=thread -c oracle/wr_oracle.c -o build/wr_oracle_tsan.o
+	$(ASAN_CXX) -std=c++11 -O1 -g -DWR_QUIET_DEBUG -fsanitize=thread -fno-omit-frame-pointer -Iinclude -Iwebradio_b200 \
+	  -Iwebradio_b200/dsp -Iwebradio_b200/io -o build/host_threads_tsan tests/harness/host_threads.cxx \
+	  tests/harness/graph_harness.cxx tests/harness/mock_capi.cxx $(BLOCKSRC) build/wr_oracle_tsan.o build/wr_host.o \
+	  -L$(CUDA_LIB) -lcudart_static -lpthread -ldl -lrt -lm
+	TSAN_OPTIONS=halt_on_error=1 ./build/host_threads_tsan
 
 # The reference's own graph glue (src/radio.cxx, UNMODIFIED, compiled where it lies) linked against
 # the drop-in blocks.  Only buildable where the reference tree is mounted; the .so travels.

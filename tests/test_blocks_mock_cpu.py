@@ -493,3 +493,22 @@ def test_host_logic_under_address_sanitizer():
     assert p.returncode == 0, out[-3000:]
     assert "scenario done" in out
     assert "AddressSanitizer" not in out and "runtime error" not in out, out[-3000:]
+
+
+def test_setters_from_other_threads_under_thread_sanitizer():
+    """make tsan-check: tests/harness/host_threads.cxx -- the DSP thread runs blocks while two threads
+    call setIF / setModeString / setPassband / getSpectrum and the getters with no locking of their own,
+    as libmicrohttpd's connection threads do in the reference (src/web/receiverhandler.cxx:113-140)."""
+    import shutil
+    import subprocess
+    if not shutil.which("make") or not shutil.which("g++"):
+        pytest.skip("no toolchain")
+    p = subprocess.run(["make", "-s", "tsan-check"], cwd=G.ROOT, capture_output=True, text=True, timeout=900)
+    out = p.stdout + p.stderr
+    if "cannot find -ltsan" in out or ("libtsan" in out and "No such file" in out):
+        pytest.skip("sanitizer runtime not installed")
+    if "unexpected memory mapping" in out or "ThreadSanitizer: unsupported" in out:
+        pytest.skip("ThreadSanitizer cannot run in this sandbox")
+    assert p.returncode == 0, out[-3000:]
+    assert "threads done" in out
+    assert "ThreadSanitizer: data race" not in out, out[-3000:]

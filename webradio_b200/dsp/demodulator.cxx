@@ -29,7 +29,7 @@ bool Demodulator::setModeString(const string &mode)
 {
 	for (size_t i = 0; i < _modeStrings.size(); i++)
 		if (_modeStrings[i] == mode) {
-			_mode = (Mode)i;
+			setMode((Mode)i);
 			return true;
 		}
 	return false;
@@ -56,7 +56,7 @@ bool Demodulator::process(const vector<sample_t> &inBuffer, vector<sample_t> &ou
 {
 	if (_fused)
 		return true; // demodulated inside the bank kernel's epilogue
-	const Mode m = _mode;
+	const Mode m = mode();
 	if (m < AM || m >= MAX_MODE) {
 		LOG_ERROR("Bad mode\n");
 		return false;

@@ -3,6 +3,7 @@
 #ifndef DEMODULATOR_H_
 #define DEMODULATOR_H_
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -26,9 +27,9 @@ public:
 		MAX_MODE
 	};
 
-	const Mode mode() const { return _mode; }
-	void setMode(const Mode mode) { _mode = mode; }
-	const string &modeString() const { return _modeStrings[_mode]; }
+	const Mode mode() const { return (Mode)_mode.load(std::memory_order_relaxed); }
+	void setMode(const Mode mode) { _mode.store((int)mode, std::memory_order_relaxed); }
+	const string &modeString() const { return _modeStrings[mode()]; }
 	bool setModeString(const string &mode);
 
 	// ---- fused-bank hand-off ----
@@ -43,7 +44,8 @@ private:
 	void deinit();
 	bool process(const vector<sample_t> &inBuffer, vector<sample_t> &outBuffer);
 
-	volatile Mode _mode;
+	// written by HTTP threads (setMode/setModeString), read by the DSP thread once per block
+	std::atomic<int> _mode;
 	vector<string> _modeStrings;
 	float prev[2]; // prev_i, prev_q (reference demodulator.h:60-61)
 	wr_stage *stage;

@@ -3,6 +3,7 @@
 #ifndef DOWNCONVERTER_H_
 #define DOWNCONVERTER_H_
 
+#include <atomic>
 #include <stdint.h>
 
 #include <string>
@@ -44,11 +45,12 @@ private:
 	bool process(const vector<sample_t> &inBuffer, vector<sample_t> &outBuffer);
 
 	LowPass *filter;
-	volatile int _if;
+	// _if and phaseStep are written by HTTP threads (setIF) and read by the DSP thread once per block
+	std::atomic<int> _if;
 
 	// NCO state (reference downconverter.h:57-59); the sine table itself lives in HBM
 	uint32_t phase;
-	volatile int32_t phaseStep;
+	std::atomic<int32_t> phaseStep;
 
 	// execution back-ends
 	wrhost::FusedBank *bank;

@@ -4,6 +4,7 @@
 #ifndef FILTER_H_
 #define FILTER_H_
 
+#include <atomic>
 #include <stdint.h>
 
 #include <mutex>
@@ -51,9 +52,9 @@ private:
 	unsigned int _firLength;
 	vector<float> coeff;
 	mutable std::mutex tapsLock;
-	volatile uint64_t _tapsVersion;
+	std::atomic<uint64_t> _tapsVersion;   // bumped under tapsLock, polled by the DSP thread without it
 	uint64_t stageTapsVersion;
-	unsigned int _passband;
+	std::atomic<unsigned int> _passband;
 
 	unsigned int _reqDecimation;
 	unsigned int _reqOutputRate;
