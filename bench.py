@@ -438,6 +438,8 @@ def gpu_arm(args, w, wname):
         "kernel": f"chan_kernel_v{variant_used}: fused NCO mix + channel FIR" if variant_used >= 2 else "chan_kernel_v1: fused NCO mix + channel FIR + demod",
         "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        # SURVEY.md 8d also asks for the fraction of the chip's nominal ~8 TB/s
+        "frac_of_nominal_8000_gbs": achieved / 8000.0,
         "algorithmic_bytes_per_launch": kb, "kernel_ms": chan_ms_avg, "audio_kernel_ms": audio_ms_avg,
         # serialised kernel times (CUDA events around each kernel); in the timed region above the
         # next block's channel kernel starts under this block's demodulator kernel (programmatic
