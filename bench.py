@@ -145,7 +145,7 @@ def _cpu_threads(n_rx):
     return min(cores, n_rx * replicas), replicas
 
 
-def cpu_reference_run(w, steps, warmup, max_seconds=None, threads=None):
+def cpu_reference_run(w, steps, warmup, max_seconds=None, threads=None, flavour="ref"):
     """The reference's CPU chain on the host cores.  Each worker thread owns an independent graph
     (tuner source + its share of the receivers), exactly how the reference would be scaled out --
     its own Radio::run visits receivers sequentially on one thread (radio.cxx:56-59), which is
@@ -158,7 +158,7 @@ def cpu_reference_run(w, steps, warmup, max_seconds=None, threads=None):
     nthreads, replicas = _cpu_threads(R) if threads is None else (threads, 1)
     total_rx = R * replicas
     iq = [synth.lattice_noise(F, stream=t) for t in range(min(T, 8))]
-    use_ref = G.have("ref")
+    use_ref = G.have(flavour)
     assign = [[] for _ in range(nthreads)]
     for i in range(total_rx):
         assign[i % nthreads].append(i % R)
@@ -172,7 +172,7 @@ def cpu_reference_run(w, steps, warmup, max_seconds=None, threads=None):
                 per_stream.setdefault(r % T % len(iq), []).append(r)
             gl = []
             for s, rxs in per_stream.items():
-                g = G.Graph("ref", w["fs"], F)
+                g = G.Graph(flavour, w["fs"], F)
                 for r in rxs:
                     g.add_receiver(if_hz=int(ifs[r]), ch_passband=w["pb1"], ch_rate=0, ch_decim=w["d1"],
                                    mode=int(modes[r]), au_passband=w["pb2"], au_rate=0, au_decim=w["d2"], capture=0)
@@ -221,9 +221,21 @@ def cpu_reference_run(w, steps, warmup, max_seconds=None, threads=None):
         "kind": "reference" if use_ref else "port",
         "sample": f"{steps} blocks of {F} frames x {total_rx} receivers "
                   f"({replicas} replica(s) of the workload) on {nthreads} threads, "
-                  f"{'oracle/_ref (unmodified reference, g++ -O2 -ffp-contract=off)' if use_ref else 'oracle port'}",
+                  + (("oracle/_ref (unmodified reference, g++ -O0, the reference's stock flags)" if flavour == "ref_O0" else
+                      "oracle/_ref (unmodified reference, g++ -O2 -ffp-contract=off)") if use_ref else "oracle port"),
         "host_cores": os.cpu_count(),
     }
+
+
+def stock_flags_run(w, seconds):
+    """The same chain built the way the reference's stock ./configure builds it (-O0, see
+    oracle/Makefile), all host threads, a short sample: SURVEY.md 8d asks for it once.  The
+    headline CPU figure stays the -O2 build, which is the faster one."""
+    import graphlib as G
+    if not G.have("ref_O0"):
+        return {}
+    r = cpu_reference_run(w, 1000, 1, max_seconds=seconds, flavour="ref_O0")
+    return {"stock_O0_value": r["value"], "stock_O0_sample": r["sample"]}
 
 
 def reference_arm(args, w, wname):
@@ -234,6 +246,7 @@ def reference_arm(args, w, wname):
     warmup = args.warmup if args.warmup is not None else 3
     r = cpu_reference_run(w, steps, warmup, max_seconds=120.0)
     r1 = cpu_reference_run(w, 3, 1, max_seconds=10.0, threads=1)
+    stock = stock_flags_run(w, 5.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "MSamples/s",
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": warmup,
@@ -242,7 +255,7 @@ def reference_arm(args, w, wname):
         "config": bench_config(w, wname, None),
         "cpu_baseline": {"value": r["value"], "unit": "MSamples/s", "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"], "host_cores": r["host_cores"],
-                         "single_thread_value": r1["value"], "single_thread_sample": r1["sample"]},
+                         "single_thread_value": r1["value"], "single_thread_sample": r1["sample"], **stock},
         "e2e": {"value": r["value"], "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -461,6 +474,7 @@ def gpu_arm(args, w, wname):
         r1 = cpu_reference_run(w, 1000, 1, max_seconds=min(4.0, args.cpu_seconds), threads=1)
         cpu["single_thread_value"] = r1["value"]
         cpu["single_thread_sample"] = r1["sample"]
+        cpu.update(stock_flags_run(w, min(3.0, args.cpu_seconds)))
 
     if rank == 0:
         line = {

@@ -17,7 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libwr_ref.so")
 BLOCKS_SO = os.path.join(ROOT, "tests", "harness", "libwr_blocks_harness.so")
 MOCK_SO = os.path.join(ROOT, "tests", "harness", "libwr_blocks_harness_mock.so")
-_PATHS = {"ref": REF_SO, "blocks": BLOCKS_SO, "mock": MOCK_SO}
+REF_O0_SO = os.path.join(ROOT, "oracle", "_ref", "libwr_ref_O0.so")
+_PATHS = {"ref": REF_SO, "ref_O0": REF_O0_SO, "blocks": BLOCKS_SO, "mock": MOCK_SO}
 
 MODES = {"AM": 0, "FM": 1, "USB": 2, "LSB": 3}
 STAGES = {"mixed": 0, "channel": 1, "demod": 2, "audio": 3}

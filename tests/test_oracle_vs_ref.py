@@ -143,3 +143,34 @@ def test_spectrum(wro, n):
             assert_biteq(ref, sp.get(), f"spectrum block {b}")
             assert rows.shape[0] in (3, 4)
             assert_biteq(rows[-1], ref, "last row")
+
+
+@pytest.mark.skipif(not G.have("ref_O0"), reason="oracle/_ref/libwr_ref_O0.so not built")
+def test_pinned_flags_equal_the_stock_build():
+    """the oracle's pinned flags (-O2 -ffp-contract=off, no -march) must give what the
+    reference's stock build (-O0: configure.ac:6 pre-sets CXXFLAGS, so autoconf adds no -O2) gives,
+    bit for bit -- every stage of every mode, the filter design, the spectrum."""
+    fs, frames = 2400000, 20000
+    gs = []
+    for which in ("ref", "ref_O0"):
+        g = G.Graph(which, fs, frames)
+        for i, m in enumerate(["AM", "FM", "USB", "LSB"]):
+            g.add_receiver(if_hz=[100000, -345678, 5, 612345][i], mode=m, capture=0xF)
+        g.add_spectrum(512)
+        assert g.start()
+        gs.append(g)
+    a, b = gs
+    try:
+        for i in range(4):
+            assert_biteq(a.get_taps(i, 0), b.get_taps(i, 0), "channel design")
+            assert_biteq(a.get_taps(i, 1), b.get_taps(i, 1), "audio design")
+        for blk in range(3):
+            iq = synth.structured(frames, fs, [100000, -345678], [0, 1], start=blk * frames, fm_dev=50000.0)
+            assert a.run(iq) and b.run(iq)
+            for i in range(4):
+                for stage in ("mixed", "channel", "demod", "audio"):
+                    assert_biteq(a.get(i, stage), b.get(i, stage), f"rx{i} {stage} block {blk}")
+            assert_biteq(a.spectrum(512), b.spectrum(512), f"spectrum block {blk}")
+    finally:
+        a.close()
+        b.close()
