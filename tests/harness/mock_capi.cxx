@@ -75,6 +75,9 @@ unsigned long long wr_mock_bank_process_calls(void) { return g_bank_process_call
 unsigned long long wr_mock_stage_calls(void) { return g_stage_calls; }
 unsigned long long wr_mock_banks_created(void) { return g_banks_created; }
 void wr_mock_reset_counters(void) { g_bank_process_calls = g_stage_calls = g_banks_created = 0; }
+/* failure injection: the next `n` bank / stage compute calls report a CUDA error (WR_ECUDA) */
+static int g_fail_bank, g_fail_stage;
+void wr_mock_fail_next(int bank_calls, int stage_calls) { g_fail_bank = bank_calls; g_fail_stage = stage_calls; }
 
 wr_bank *wr_bank_create(int, unsigned n_streams, unsigned n_receivers, unsigned max_frames,
 		unsigned n1, unsigned d1, unsigned n2, unsigned d2)
@@ -194,6 +197,10 @@ int wr_bank_process(wr_bank *b, const float *iq_host, unsigned nframes, float *a
 		return WR_EINVAL;
 	g_bank_process_calls++;
 	b->calls++;
+	if (g_fail_bank > 0) {
+		g_fail_bank--;
+		return WR_ECUDA;
+	}
 	const unsigned m1 = nframes / b->d1;
 	b->mixed.resize(2 * (size_t)nframes + 2);
 	b->chan.resize(2 * (size_t)m1 + 2);
@@ -232,6 +239,10 @@ int wr_stage_mix(wr_stage *s, const float *table_or_null, uint32_t *phase, int32
 	if (!s || !phase || (nframes && (!iq_host || !out_host)))
 		return WR_EINVAL;
 	g_stage_calls++;
+	if (g_fail_stage > 0) {
+		g_fail_stage--;
+		return WR_ECUDA;
+	}
 	wro_mix(table_or_null ? table_or_null : sintable().data(), phase, step, iq_host, nframes, out_host);
 	return WR_OK;
 }

@@ -346,6 +346,25 @@ def test_extreme_setter_values():
         g.close(); r.close()
 
 
+def test_a_device_error_fails_the_block_and_nothing_else():
+    """SURVEY.md 8b, errors: a failing library call must surface as process() == false -> run() ==
+    false (dspblock.cxx:192-195), never as an exception or a crash, and the pipeline must be usable
+    for the next block."""
+    lib = counters()
+    lib.wr_mock_fail_next.argtypes = [C.c_int, C.c_int]
+    for capture in (0x8, 0xF):
+        with G.Graph("mock", FS, F) as g:
+            for i in range(3):
+                g.add_receiver(if_hz=1000 * i, mode="FM", capture=capture)
+            assert g.start()
+            assert g.run(synth.lattice_noise(F, stream=1))
+            lib.wr_mock_fail_next(1, 1)
+            assert not g.run(synth.lattice_noise(F, stream=1, start=F))
+            lib.wr_mock_fail_next(0, 0)
+            assert g.run(synth.lattice_noise(F, stream=1, start=2 * F))
+            assert g.get(2, "audio").size == F // 50
+
+
 DROPIN_MOCK = os.path.join(G.ROOT, "tests", "harness", "libwr_radio_dropin_mock.so")
 
 
