@@ -16,13 +16,10 @@ uint64_t DspBlock::topologySerial() { return g_topologySerial.load(); }
 
 DspBlock::DspBlock(const string &name, const string &type) :
 	_outputSampleRate(DEFAULT_SAMPLE_RATE), _outputChannels(DEFAULT_CHANNELS),
+	_producer(NULL), _isRunning(false), _runSerial(0),
 	_name(name), _type(type),
 	_inputSampleRate(DEFAULT_SAMPLE_RATE), _inputChannels(DEFAULT_CHANNELS),
-	_decimation(1), _interpolation(1),
-#ifdef DSPBLOCK_PROFILE
-	_totalNanoseconds(0), _totalIn(0), _totalOut(0),
-#endif
-	_isRunning(false), _runSerial(0), _producer(NULL)
+	_decimation(1), _interpolation(1)
 {
 }
 
@@ -47,20 +44,20 @@ DspBlock::~DspBlock()
 
 // reference dspblock.cxx:57-76: a block joining a running pipeline is started on the spot
 // (without a rate cascade -- the newcomer keeps whatever rates it was last given); duplicates
-// are refused.
+// are refused -- after that start, as in the reference.
 void DspBlock::connect(DspBlock *block)
 {
 	if (_isRunning)
 		block->start();
-	if (std::find(_consumers.begin(), _consumers.end(), block) != _consumers.end()) {
-		LOG_ERROR("%s:%s is already a consumer of %s:%s\n", block->type().c_str(), block->name().c_str(),
-				type().c_str(), name().c_str());
+	const bool known = std::find(_consumers.begin(), _consumers.end(), block) != _consumers.end();
+	if (known) {
+		LOG_ERROR("%s is already a consumer of %s\n", block->label().c_str(), label().c_str());
 		return;
 	}
-	_consumers.push_back(block);
 	block->_producer = this;
+	_consumers.push_back(block);
 	g_topologySerial++;
-	LOG_DEBUG("%s:%s now feeds %s:%s\n", type().c_str(), name().c_str(), block->type().c_str(), block->name().c_str());
+	LOG_DEBUG("%s now feeds %s\n", label().c_str(), block->label().c_str());
 }
 
 // reference dspblock.cxx:78-91
@@ -72,7 +69,7 @@ void DspBlock::disconnect(DspBlock *block)
 	if (block->_producer == this)
 		block->_producer = NULL;
 	g_topologySerial++;
-	LOG_DEBUG("%s:%s no longer feeds %s:%s\n", type().c_str(), name().c_str(), block->type().c_str(), block->name().c_str());
+	LOG_DEBUG("%s no longer feeds %s\n", label().c_str(), block->label().c_str());
 }
 
 #ifdef DSPBLOCK_PROFILE
@@ -80,12 +77,32 @@ void DspBlock::disconnect(DspBlock *block)
 uint64_t DspBlock::nsPerFrameAll() const
 {
 	uint64_t sum = nsPerFrameOne();
-	LOG_DEBUG("%s:%s %" PRIu64 " ns/frame\n", type().c_str(), name().c_str(), sum);
+	LOG_DEBUG("%s %" PRIu64 " ns/frame\n", label().c_str(), sum);
 	for (size_t i = 0; i < _consumers.size(); i++)
 		sum += _consumers[i]->nsPerFrameAll();
 	return sum;
 }
+
+static inline uint64_t cpuTimeNs()
+{
+	timespec t;
+	clock_gettime(CLOCK_PROCESS_CPUTIME_ID, &t);
+	return (uint64_t)t.tv_sec * 1000000000ull + (uint64_t)t.tv_nsec;
+}
 #endif
+
+bool DspBlock::negotiateRates()
+{
+	const unsigned int in = _inputSampleRate, out = _outputSampleRate;
+	_decimation = _interpolation = 1;
+	if (in == 0 || out == 0)
+		return false;
+	if (out <= in)
+		_decimation = in / out;
+	else
+		_interpolation = out / in;
+	return in * _interpolation / _decimation == out;
+}
 
 // reference dspblock.cxx:106-151
 bool DspBlock::start()
@@ -94,42 +111,32 @@ bool DspBlock::start()
 	_outputSampleRate = _inputSampleRate;
 	_outputChannels = _inputChannels;
 
-	LOG_DEBUG("starting %s:%s\n", type().c_str(), name().c_str());
+	LOG_DEBUG("starting %s\n", label().c_str());
 	if (!init()) {
-		LOG_ERROR("%s:%s failed to initialise\n", type().c_str(), name().c_str());
+		LOG_ERROR("%s failed to initialise\n", label().c_str());
 		return false;
 	}
-
-	// whole-number rate change only, in one direction
-	if (_outputSampleRate <= _inputSampleRate) {
-		_interpolation = 1;
-		_decimation = _outputSampleRate ? _inputSampleRate / _outputSampleRate : 0;
-	} else {
-		_decimation = 1;
-		_interpolation = _inputSampleRate ? _outputSampleRate / _inputSampleRate : 0;
-	}
-	if (_decimation == 0 || _interpolation == 0 ||
-			_inputSampleRate * _interpolation / _decimation != _outputSampleRate) {
+	if (!negotiateRates()) {
 		LOG_ERROR("Sample rates must be integer related\n");
 		deinit();
 		return false;
 	}
 
 #ifdef DSPBLOCK_PROFILE
-	_totalNanoseconds = 0;
-	_totalIn = _totalOut = 0;
+	_spent = Spent();
 #endif
 	_isRunning = true;
 
+	// hand the format downstream; one consumer that cannot start takes the pipeline down
 	for (size_t i = 0; i < _consumers.size(); i++) {
 		DspBlock *c = _consumers[i];
 		c->setSampleRate(_outputSampleRate);
 		c->setChannels(_outputChannels);
-		if (!c->start()) {
-			LOG_ERROR("downstream of %s:%s failed to start, stopping the pipeline\n", type().c_str(), name().c_str());
-			stop();
-			return false;
-		}
+		if (c->start())
+			continue;
+		LOG_ERROR("downstream of %s failed to start, stopping the pipeline\n", label().c_str());
+		stop();
+		return false;
 	}
 	return true;
 }
@@ -140,7 +147,7 @@ void DspBlock::stop()
 	for (size_t i = 0; i < _consumers.size(); i++)
 		_consumers[i]->stop();
 	if (_isRunning) {
-		LOG_DEBUG("stopping %s:%s\n", type().c_str(), name().c_str());
+		LOG_DEBUG("stopping %s\n", label().c_str());
 		_isRunning = false;
 		deinit();
 	}
@@ -161,24 +168,21 @@ bool DspBlock::run(const vector<sample_t> &inBuffer)
 	const unsigned int outframes = inframes * _interpolation / _decimation;
 	const size_t want = (size_t)outframes * _outputChannels;
 	if (_buffer.size() != want) {
-		LOG_DEBUG("%s:%s output buffer -> %u frames x %u channels\n", type().c_str(), name().c_str(),
-				outframes, _outputChannels);
+		LOG_DEBUG("%s output buffer -> %u frames x %u channels\n", label().c_str(), outframes, _outputChannels);
 		_buffer.resize(want);
 	}
 
 #ifdef DSPBLOCK_PROFILE
-	timespec t0, t1;
-	clock_gettime(CLOCK_PROCESS_CPUTIME_ID, &t0);
+	const uint64_t t0 = cpuTimeNs();
 #endif
 	if (!process(inBuffer, _buffer)) {
-		LOG_ERROR("Pipeline failed at block %s:%s\n", type().c_str(), name().c_str());
+		LOG_ERROR("Pipeline failed at block %s\n", label().c_str());
 		return false;
 	}
 #ifdef DSPBLOCK_PROFILE
-	clock_gettime(CLOCK_PROCESS_CPUTIME_ID, &t1);
-	_totalNanoseconds += (uint64_t)((int64_t)(t1.tv_sec - t0.tv_sec) * 1000000000LL + (int64_t)(t1.tv_nsec - t0.tv_nsec));
-	_totalIn += inframes;
-	_totalOut += outframes;
+	_spent.ns += cpuTimeNs() - t0;
+	_spent.framesIn += inframes;
+	_spent.framesOut += outframes;
 #endif
 
 	for (size_t i = 0; i < _consumers.size(); i++)
@@ -190,16 +194,14 @@ bool DspBlock::run(const vector<sample_t> &inBuffer)
 // reference dspblock.cxx:214-231: ignored while running
 void DspBlock::setSampleRate(unsigned int rate)
 {
-	if (_isRunning)
-		return;
-	_inputSampleRate = rate;
+	if (!_isRunning)
+		_inputSampleRate = rate;
 }
 
 void DspBlock::setChannels(unsigned int channels)
 {
-	if (_isRunning)
-		return;
-	_inputChannels = channels;
+	if (!_isRunning)
+		_inputChannels = channels;
 }
 
 DspSource::DspSource(const string &name, const string &type) :

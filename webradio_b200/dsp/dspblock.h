@@ -53,10 +53,10 @@ public:
 #ifdef DSPBLOCK_PROFILE
 	uint64_t nsPerFrameAll() const;
 	// the reference divides by zero before the first block; this returns 0 instead
-	uint64_t nsPerFrameOne() const { return _totalIn ? _totalNanoseconds / _totalIn : 0; }
-	uint64_t totalNanoseconds() const { return _totalNanoseconds; }
-	unsigned int totalIn() const { return (unsigned int)_totalIn; }
-	unsigned int totalOut() const { return (unsigned int)_totalOut; }
+	uint64_t nsPerFrameOne() const { return _spent.framesIn ? _spent.ns / _spent.framesIn : 0; }
+	uint64_t totalNanoseconds() const { return _spent.ns; }
+	unsigned int totalIn() const { return (unsigned int)_spent.framesIn; }
+	unsigned int totalOut() const { return (unsigned int)_spent.framesOut; }
 #endif
 
 	bool isRunning() const { return _isRunning; }
@@ -87,29 +87,38 @@ protected:
 	unsigned int _outputChannels;
 
 private:
+	// reachable only through DspSource (friend), exactly as in the reference
 	bool start();
 	void stop();
 	bool run(const vector<sample_t> &inBuffer);
 	void setSampleRate(unsigned int rate);
 	void setChannels(unsigned int channels);
 
+	// whole-number rate change in one direction, or failure (reference dspblock.cxx:119-130)
+	bool negotiateRates();
+	string label() const { return _type + ":" + _name; }
+
+	// graph
+	DspBlock *_producer;
+	vector<DspBlock*> _consumers;
+	vector<sample_t> _buffer;   // this block's output, handed to every consumer
+	bool _isRunning;
+	uint64_t _runSerial;
+
+	// identity and negotiated format
 	const string _name;
 	const string _type;
 	unsigned int _inputSampleRate;
 	unsigned int _inputChannels;
 	unsigned int _decimation;
 	unsigned int _interpolation;
-#ifdef DSPBLOCK_PROFILE
-	uint64_t _totalNanoseconds;
-	uint64_t _totalIn;
-	uint64_t _totalOut;
-#endif
-	bool _isRunning;
-	uint64_t _runSerial;
-	DspBlock *_producer;
 
-	vector<sample_t> _buffer;
-	vector<DspBlock*> _consumers;
+#ifdef DSPBLOCK_PROFILE
+	struct Spent {
+		uint64_t ns, framesIn, framesOut;
+		Spent() : ns(0), framesIn(0), framesOut(0) {}
+	} _spent;
+#endif
 };
 
 class DspSource : public DspBlock
