@@ -48,6 +48,12 @@ int main()
 			if (b == 2) { wrh_graph_detach(g, 1); wrh_graph_detach(g, 3); }
 			if (b == 3) { wrh_graph_set_if(g, 0, -99999); wrh_graph_set_mode(g, 2, "FM"); wrh_graph_set_passband(g, 5, 0, 200000); }
 			if (b == 4) { wrh_graph_attach(g, 1); }
+			if (b == 7 && round == 0) {
+				// a receiver created on a live radio (POST /receivers in the reference's web UI): it starts
+				// with the default 48 kHz input rate -- meaningless output, but it must not corrupt anything
+				wrh_graph_add_receiver(g, 4242, 80000, 240000, 0, 1, 8000, 48000, 0, 0x8);
+				wrh_graph_add_receiver(g, -4242, 80000, 240000, 0, 0, 8000, 48000, 0, 0xF);
+			}
 			if (b == 5) { wrh_graph_detach(g, 0); wrh_graph_detach(g, 2); wrh_graph_detach(g, 4); wrh_graph_detach(g, 5); wrh_graph_detach(g, 1); }
 			if (b == 6) { wrh_graph_attach(g, 3); wrh_graph_attach(g, 5); }
 			if (b == 8) { wrh_graph_restart(g); wrh_graph_restart(g2); }
