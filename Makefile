@@ -56,8 +56,9 @@ $(HARNESS_MOCK): tests/harness/graph_harness.cxx tests/harness/mock_capi.cxx $(B
 	  -Loracle -lwr_oracle -L$(CUDA_LIB) -lcudart_static -Wl,-Bsymbolic -Wl,-rpath,'$$ORIGIN/../../oracle' -lpthread -ldl -lrt
 
 # Host logic of the drop-in blocks under AddressSanitizer + UBSan (stand-in back-end, no GPU)
-ASAN_CC  ?= /usr/bin/gcc
-ASAN_CXX ?= /usr/bin/g++
+# the distribution's compiler: it ships the sanitizer runtimes (a toolchain under /opt may not)
+ASAN_CC  ?= $(shell command -v /usr/bin/gcc || command -v gcc)
+ASAN_CXX ?= $(shell command -v /usr/bin/g++ || command -v g++)
 asan-check: build/wr_host.o
 	@mkdir -p build
 	$(ASAN_CC) -std=c11 -O1 -g -ffp-contract=off -fsanitize=address,undefined -c oracle/wr_oracle.c -o build/wr_oracle_asan.o
