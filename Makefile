@@ -67,6 +67,14 @@ asan-check: build/wr_host.o
 	  tests/harness/graph_harness.cxx tests/harness/mock_capi.cxx $(BLOCKSRC) build/wr_oracle_asan.o build/wr_host.o \
 	  -L$(CUDA_LIB) -lcudart_static -lpthread -ldl -lrt -lm
 	ASAN_OPTIONS=detect_leaks=1 UBSAN_OPTIONS=halt_on_error=1 ./build/host_scenario_asan
+	@if [ -f "$(REF)/src/radio.cxx" ]; then \
+	  $(ASAN_CXX) -std=c++11 -O1 -g -DWR_QUIET_DEBUG -fsanitize=address,undefined -fno-omit-frame-pointer -Iinclude \
+	    -Itests/harness/stubs -Iwebradio_b200 -Iwebradio_b200/dsp -Iwebradio_b200/io -I$(REF)/src -I$(REF)/src/io \
+	    -o build/radio_scenario_asan tests/harness/radio_scenario.cxx $(REF)/src/radio.cxx tests/harness/radio_dropin.cxx \
+	    tests/harness/mock_capi.cxx $(BLOCKSRC) build/wr_oracle_asan.o build/wr_host.o \
+	    -L$(CUDA_LIB) -lcudart_static -lpthread -ldl -lrt -lm && \
+	  ASAN_OPTIONS=detect_leaks=1 UBSAN_OPTIONS=halt_on_error=1 ./build/radio_scenario_asan; \
+	else echo "reference tree not mounted: radio glue scenario skipped"; fi
 
 # ... and under ThreadSanitizer: the DSP thread against two threads doing what the REST handlers do
 tsan-check: build/wr_host.o
