@@ -183,3 +183,70 @@ def test_spectrum_hop_counts_frames(wro):
     assert r1.shape[0] + r2.shape[0] == total
     whole = wro.Spectrum(512, 256).process(iq)
     assert_biteq(np.concatenate([r1, r2]), whole, "split spectrum stream")
+
+
+# ---- randomised geometries against an independent numpy float32 restatement ----
+
+from hypothesis import given, settings, strategies as st   # noqa: E402
+
+
+def numpy_fir(taps, x, ch, d, hist):
+    """lowpass.cxx:133-159 with numpy float32 vectors: for each tap j (in the reference's order) one
+    rounded product and one rounded sum, over all outputs at once."""
+    n = len(taps)
+    block = np.concatenate([hist, x]).reshape(-1, ch)
+    nout = (len(x) // ch) // d
+    acc = np.zeros((nout, ch), np.float32)
+    base = np.arange(nout) * d
+    for j in range(n):
+        acc = (acc + (np.float32(taps[n - 1 - j]) * block[base + j]).astype(np.float32)).astype(np.float32)
+    return acc.ravel(), block[len(block) - (n - 1):].ravel() if n > 1 else np.zeros(0, np.float32)
+
+
+@settings(max_examples=40, deadline=None)
+@given(n=st.integers(1, 300), d=st.integers(1, 64), ch=st.sampled_from([1, 2]), blocks=st.integers(1, 3),
+       mult=st.integers(1, 12), seed=st.integers(0, 2**31 - 1))
+def test_fir_random_geometry(wro, n, d, ch, blocks, mult, seed):
+    rng = np.random.default_rng(seed)
+    taps = rng.standard_normal(n).astype(np.float32)
+    frames = d * mult
+    f = wro.Fir(ch, taps, d)
+    hist = np.zeros((n - 1) * ch, np.float32)
+    for _ in range(blocks):
+        x = ((rng.integers(0, 256, frames * ch).astype(np.float32) - 128.0) / 128.0).astype(np.float32)
+        got = f.process(x)
+        want, hist = numpy_fir(taps, x, ch, d, hist)
+        assert_biteq(got, want, f"n={n} d={d} ch={ch} frames={frames}")
+
+
+@settings(max_examples=40, deadline=None)
+@given(phase=st.integers(0, 2**31 - 1), step=st.integers(-2**31, 2**31 - 1), frames=st.integers(1, 3000),
+       seed=st.integers(0, 2**31 - 1))
+def test_mixer_random_phase_and_step(wro, phase, step, frames, seed):
+    """downconverter.cxx:97-111 with numpy: index from the pre-increment phase, 31-bit wrap, four
+    rounded products, two rounded sums."""
+    t = wro.sintable()
+    rng = np.random.default_rng(seed)
+    iq = ((rng.integers(0, 256, 2 * frames).astype(np.float32) - 128.0) / 128.0).astype(np.float32)
+    ph = (phase + np.arange(frames, dtype=np.int64) * step) & 0x7FFFFFFF
+    si = (ph >> 15).astype(np.int64)
+    ci = (si + 16384) & 0xFFFF
+    s, c = t[si], t[ci]
+    i, q = iq[0::2], iq[1::2]
+    want = np.empty_like(iq)
+    want[0::2] = ((i * c).astype(np.float32) + (q * s).astype(np.float32)).astype(np.float32)
+    want[1::2] = ((q * c).astype(np.float32) - (i * s).astype(np.float32)).astype(np.float32)
+    got, end = wro.mix(t, phase, step, iq)
+    assert end == int((phase + frames * step) & 0x7FFFFFFF)
+    assert_biteq(got, want, f"phase={phase} step={step}")
+
+
+@settings(max_examples=30, deadline=None)
+@given(if_hz=st.integers(-2**31, 2**31 - 1), fs=st.integers(1, 2**32 - 1))
+def test_phase_step_formula(wro, if_hz, fs):
+    """downconverter.cxx:65,80: (int)((int64)hz * 2^31 / (int64)Fs), truncating toward zero, then
+    narrowed to 32 bits."""
+    q = abs(if_hz) * 2**31 // fs
+    q = -q if if_hz < 0 else q
+    q = (q + 2**31) % 2**32 - 2**31          # the (int) narrowing of an out-of-range int64
+    assert wro.phase_step(if_hz, fs) == q
