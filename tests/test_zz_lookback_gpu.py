@@ -26,3 +26,17 @@ def test_hot_detach_and_reattach_on_the_gpu_blocks(capture):
     if not hasattr(G.load("blocks"), "wrh_graph_detach") or not hasattr(G.load("ref"), "wrh_graph_detach"):
         pytest.skip("harness libraries predate wrh_graph_detach")
     LC.hot_reattach("blocks", capture)
+
+
+@pytest.mark.skipif(not (G.have("blocks") and G.have("ref")), reason="harness libraries not built")
+@pytest.mark.parametrize("seed", range(12))
+def test_random_scenario_on_the_gpu_blocks(seed):
+    """tests/fuzz_cases.py on the CUDA library: seeded sequences of setters, detach / attach and
+    restarts over fused, strict and mixed chains, every tapped stage bit for bit against the
+    reference blocks (the same seeds run on the CPU stand-in in tests/test_blocks_fuzz_cpu.py)."""
+    if not hasattr(G.load("blocks"), "wrh_graph_detach") or not hasattr(G.load("ref"), "wrh_graph_restart"):
+        pytest.skip("harness libraries predate wrh_graph_detach / wrh_graph_restart")
+    if not fm_exact():
+        pytest.skip("FM is bit-exact only against glibc's atan2f; the tolerance path is covered by test_blocks_gpu.py")
+    from fuzz_cases import scenario
+    scenario(seed, which="blocks")
