@@ -18,7 +18,7 @@ HARNESS  := tests/harness/libwr_blocks_harness.so
 BLOCKSRC := webradio_b200/dsp/dspblock.cxx webradio_b200/dsp/downconverter.cxx webradio_b200/dsp/lowpass.cxx \
             webradio_b200/dsp/demodulator.cxx webradio_b200/io/spectrumsink.cxx webradio_b200/dsp/gpubank.cxx
 
-.PHONY: all lib harness harness-mock dropin dropin-mock asan-check tsan-check oracle tools clean
+.PHONY: all lib lib-exp harness harness-mock dropin dropin-mock asan-check tsan-check oracle tools clean
 all: lib
 lib: $(LIB)
 
@@ -37,6 +37,15 @@ build/wr_host.o: $(CSRC)/wr_host.cpp $(CSRC)/wr_common.h include/webradio_b200.h
 
 $(LIB): $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart_static -lpthread -ldl -lrt
+
+# Experimental twin of the library for A/B runs on a GPU box (never loaded unless WEBRADIO_B200_LIB points at it):
+# same sources, experiment macros on.  EXPFLAGS picks the experiment(s).
+EXPFLAGS ?= -DWR_EXP_FIR_SLEEP=200
+LIB_EXP  := webradio_b200/libwebradio_b200_exp.so
+lib-exp:
+	@mkdir -p build/exp
+	$(NVCC) $(NVFLAGS) $(PARITY) $(EXPFLAGS) -c $(CSRC)/wr_bank.cu -o build/exp/wr_bank.o
+	$(NVCC) $(ARCH) -shared -o $(LIB_EXP) build/exp/wr_bank.o build/wr_stage.o build/wr_spectrum.o build/wr_host.o -lcudart_static -lpthread -ldl -lrt
 
 harness: $(HARNESS)
 $(HARNESS): tests/harness/graph_harness.cxx $(BLOCKSRC) $(wildcard webradio_b200/dsp/*.h webradio_b200/io/*.h) $(LIB)

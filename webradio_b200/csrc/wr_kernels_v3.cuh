@@ -173,6 +173,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity)
 			"@!p bra WR_MBAR_WAIT%=;\n\t}" :: "r"(bar), "r"(parity) : "memory");
 }
 
+// The FIR warps' wait for a full slot.  They are the role with slack, and they spin on schedulers
+// the mixers share: on cfg3 the loop runs 4.8 M times per launch, 7 % of the kernel's executed
+// warp-instructions (profiles/r01_ncu_hotspots_chan_cfg3.txt).  Experiment for the next GPU visit
+// (make lib-exp, then WEBRADIO_B200_LIB=webradio_b200/libwebradio_b200_exp.so): back off with nanosleep between attempts.  Without the
+// macro this is mbar_wait itself -- the default build's code is unchanged.
+#ifdef WR_EXP_FIR_SLEEP
+__device__ __forceinline__ void mbar_wait_fir(uint32_t bar, unsigned parity)
+{
+	asm volatile("{\n\t.reg .pred p;\n"
+			"WR_MBAR_WAITS%=:\n\t"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+			"@p bra WR_MBAR_DONE%=;\n\t"
+			"nanosleep.u32 %2;\n\t"
+			"bra WR_MBAR_WAITS%=;\n"
+			"WR_MBAR_DONE%=:\n\t}" :: "r"(bar), "r"(parity), "n"(WR_EXP_FIR_SLEEP) : "memory");
+}
+#else
+__device__ __forceinline__ void mbar_wait_fir(uint32_t bar, unsigned parity) { mbar_wait(bar, parity); }
+#endif
+
 // Packed constants of the table reconstruction, built once per thread.
 struct Lo3Regs {
 	f2_t tscale, tbias, slotk, slotm, neg1, one, eps, c0, c1, c2, c3;
@@ -723,7 +743,7 @@ __device__ __forceinline__ void chan_body_v3(const ChanArgs &a, const V3Args &v)
 		if (!a.wait_late)
 			asm volatile("griddepcontrol.wait;" ::: "memory");
 		for (unsigned kuse = 0; ; kuse++) {
-			mbar_wait(full32 + 8u * slot, kuse & 1u);
+			mbar_wait_fir(full32 + 8u * slot, kuse & 1u);
 			unsigned r, p, unused, rl;
 			asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r), "=r"(p), "=r"(unused), "=r"(rl) : "r"(desc32 + slot * 16u));
 			if (rl == 0xFFFFFFFFu)
