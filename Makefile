@@ -18,7 +18,7 @@ HARNESS  := tests/harness/libwr_blocks_harness.so
 BLOCKSRC := webradio_b200/dsp/dspblock.cxx webradio_b200/dsp/downconverter.cxx webradio_b200/dsp/lowpass.cxx \
             webradio_b200/dsp/demodulator.cxx webradio_b200/io/spectrumsink.cxx webradio_b200/dsp/gpubank.cxx
 
-.PHONY: all lib lib-exp harness harness-mock dropin dropin-mock asan-check tsan-check oracle tools clean
+.PHONY: all lib lib-exp harness harness-mock dropin dropin-mock asan-check tsan-check oracle check tools clean
 all: lib
 lib: $(LIB)
 
@@ -120,6 +120,10 @@ dropin-mock: build/wr_host.o
 
 oracle:
 	$(MAKE) -C oracle port ref
+
+# everything that can be checked without a GPU
+check: lib harness harness-mock oracle
+	python -m pytest tests -q -m "not gpu"
 
 # stand-alone micro-benchmarks (run on the GPU box; build/ travels with gpurun)
 tools: build/ubench_copy

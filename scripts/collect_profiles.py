@@ -20,7 +20,8 @@ dst = os.path.join(ROOT, "profiles")
 BENCH = {"bench_cfg1": "bench_cfg1", "bench_cfg2": "bench_cfg2", "bench_cfg3": "bench_cfg3", "bench_cfg4": "bench_cfg4",
          "bench_cfg5": "bench_cfg5", "bench_cfg2_u8": "bench_cfg2_u8", "bench_cfg3_u8": "bench_cfg3_u8",
          "bench_cfg2_v1": "bench_cfg2_v1kernels", "bench_cfg2_v2": "bench_cfg2_v2kernels",
-         "bench_cfg3_v2": "bench_cfg3_v2kernels", "bench_ref": "bench_reference_cfg2"}
+         "bench_cfg3_v2": "bench_cfg3_v2kernels", "bench_ref": "bench_reference_cfg2",
+         "bench_cfg5_u8": "bench_cfg5_u8"}
 for a, b in BENCH.items():
     p = os.path.join(src, a + ".json")
     if os.path.exists(p) and os.path.getsize(p):
@@ -87,6 +88,12 @@ for rep, (w, kind) in REPS.items():
         "fma_pipe_cycles_active_pct": get("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
         "source": f"ncu --set full --clock-control none, one launch (profiles/{prefix}_{name}.txt)",
     }
+    # where the warps wait: source-level stall samples of the same capture
+    try:
+        hot = subprocess.check_output([sys.executable, os.path.join(ROOT, "scripts", "ncu_hotspots.py"), p, "14"], text=True)
+        open(os.path.join(dst, f"{prefix}_{name.replace('ncu_full', 'ncu_hotspots')}.txt"), "w").write(hot)
+    except subprocess.CalledProcessError:
+        pass
 if traffic:
     json.dump(traffic, open(os.path.join(dst, "traffic.json"), "w"), indent=1)
 print("profiles/ refreshed from", src)
