@@ -378,7 +378,11 @@ def gpu_arm(args, w, wname):
     nh = min(nbuf, 4 if T > 1 else 16)
     pin_in = [inputs[i].cpu().pin_memory() for i in range(nh)]
     pin_out = [torch.zeros(R, max(M2, 1)).pin_memory() for _ in range(depth + 1)]
-    esteps = steps if T == 1 else min(steps, 10)
+    # e2e is host-timed: a region of a few blocks (a driver may ask for --steps 10) would measure the
+    # host's timer and the link's wake-up, not the path.  Its regions are therefore at least 1000
+    # blocks long for single-tuner workloads (20-30 ms) and at least 5 for the multi-stream ones
+    # (a block there is milliseconds); `e2e.steps` says what was used.
+    esteps = max(steps, 1000) if T == 1 else max(min(steps, 10), 5)
 
     pin_in_ptrs = [x.data_ptr() for x in pin_in]
     pin_out_ptrs = [y.data_ptr() for y in pin_out]
@@ -402,7 +406,7 @@ def gpu_arm(args, w, wname):
     # allocated on first use (cudaMalloc synchronises), so fewer warm-up blocks than the depth put
     # allocations into the timed region (r01k: cfg3 fed bytes 6.1 k instead of ~25 k MS/s)
     for _ in range(4 if T == 1 else 1):
-        e2e_pipelined(esteps if T == 1 else depth + 2)
+        e2e_pipelined(max(esteps, 2000) if T == 1 else depth + 2)
     e2e_runs, sync_runs = [], []
     ssteps = min(esteps, 200)
     for _ in range(reps):
