@@ -2,13 +2,19 @@
 """bench.py -- throughput of the per-receiver DSP hot path (NCO mix -> decimating FIR -> demod ->
 audio FIR) on B200, next to the reference's own CPU path.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3] [--subs cfg2,cfg4,cfg5]
+                  [--impl reference]
 
-One "step" = one tuner block of the workload through every receiver of this rank's bank.
+The line's workload is cfg3 (1024 independent streams, 255 taps: the largest single-GPU config of
+BASELINE.json and the HBM-roofline one) at every N -- weak scaling, each rank owns its
+own tuners.  One "step" = one tuner block of the workload through every receiver of this rank's bank.
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline     dominant kernel's algorithmic bytes / its CUDA-event time vs the measured HBM peak
-  cpu_baseline the reference's CPU chain (oracle/_ref, else the C port) timed on the host cores
-  e2e          same metric through the C ABI with HOST buffers (H2D + kernels + D2H every step)
+  roofline     dominant kernel: ALGORITHMIC bytes of SURVEY.md 8d / its CUDA-event time vs the measured HBM peak
+  cpu_baseline the reference's CPU chain (oracle/_ref, else the C port) on the host cores, same inputs
+  e2e          the same metric through the synchronous C-ABI call the DspBlock drop-in makes, HOST buffers
+               (H2D + kernels + D2H inside every call); pipelined / raw-byte / plug-in figures beside it
+  parity       one output block of this run compared with the oracle inside the run
+  configs      the same record for cfg2, cfg4 (spectrum) and this GPU's share of cfg5
 Receivers are independent: ranks never exchange data (weak scaling, no collective on the path).
 """
 import argparse
@@ -32,36 +38,47 @@ from webradio_b200 import synth  # noqa: E402
 METRIC = "input IQ MSamples/s through downconvert→FIR→demod; achieved HBM GB/s vs peak"
 L2_BYTES = 126 * 1024 * 1024
 HBM_FALLBACK_GBS = 6650.0
+MIN_CPU_SECONDS = 2.0          # no CPU sample shorter than this is reported
+CPU_SAMPLE_RX = 64             # receivers of a large workload the CPU arms run (stated in `sample`)
+TRAFFIC_FILE = os.path.join("profiles", "traffic.json")
 
 
-def parse_args():
+def parse_args(argv=None):
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=None)
     p.add_argument("--warmup", type=int, default=None)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--workload", default="cfg2", choices=sorted(synth.WORKLOADS) + ["cfg4"])
-    p.add_argument("--variant", type=int, default=0, help="kernel family: 0 auto, 1 v1, 2 v2, 3 v3")
+    p.add_argument("--workload", default="cfg3", choices=sorted(synth.WORKLOADS) + ["cfg4"])
+    p.add_argument("--subs", default=None,
+                   help="comma-separated workloads reported under `configs` (default: cfg2,cfg4,cfg5 next to cfg3; "
+                        "'none' for a single record)")
+    p.add_argument("--variant", type=int, default=0, help="kernel family: 0 auto, 1 v1, 2 v2, 3 v3, 4 v4")
     p.add_argument("--input", default="f32", choices=["f32", "u8"],
-                   help="tuner block format: interleaved float IQ (the DspBlock convention) or raw RTL-SDR bytes "
-                        "converted inside the channel kernel's load (SURVEY.md 8f-1)")
+                   help="tuner block format of the DEVICE-timed legs: interleaved float IQ (the DspBlock convention) "
+                        "or raw RTL-SDR bytes converted inside the channel kernel's load (SURVEY.md 8f-1); "
+                        "e2e reports both")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU baseline sample")
-    return p.parse_args()
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=5.0, help="target wall time of each CPU baseline sample")
+    return p.parse_args(argv)
 
 
 # ------------------------------------------------------------------ workload ----
 
-def workload_taps(w):
+def workload_taps(w, design=None):
     """Tap values are an input of the FIR (the reference's own design collapses to all-zero for the
-    narrow pass-bands of cfg2/3/5: maxbin = N*passband/Fs/2 = 0, lowpass.cxx:167).  cfg1 uses the
-    reference design; the others a Hamming windowed-sinc of the same length."""
-    from webradio_b200 import capi
-    if w["n1"] == 64:
-        t1 = capi.lowpass_design(64, w["pb1"], w["fs"])
-    else:
+    narrow pass-bands of cfg2/3/5: maxbin = N*passband/Fs/2 = 0, lowpass.cxx:167).  64-tap stages use
+    the reference design where it is not degenerate; the others a Hamming windowed-sinc of the same
+    length.  `design` is the routine that restates LowPass::recalculate: the product's on the GPU
+    arm, the oracle's on the reference arm (so that arm never maps the product library)."""
+    if design is None:
+        from webradio_b200 import capi
+        design = capi.lowpass_design
+    t1 = design(64, w["pb1"], w["fs"]) if w["n1"] == 64 else np.zeros(0, np.float32)
+    if not np.any(t1):
         t1 = synth.windowed_sinc(w["n1"], w["pb1"] / w["fs"])
-    t2 = capi.lowpass_design(w["n2"], w["pb2"], w["fs"] // w["d1"])
+    t2 = design(w["n2"], w["pb2"], w["fs"] // w["d1"])
     if not np.any(t2):
         t2 = synth.windowed_sinc(w["n2"], w["pb2"] / (w["fs"] // w["d1"]))
     return t1, t2
@@ -75,13 +92,37 @@ def algorithmic_bytes(w, frame_bytes=8):
 
 
 def chan_kernel_bytes(w, variant, frame_bytes=8):
-    """The dominant kernel alone: reads the tuner block(s) once and writes, per channel-rate
-    sample per receiver, the demodulated float (v1: demod fused in) or the IQ pair (v2, v3)."""
+    """What the dominant kernel itself moves: the tuner block(s) once and, per channel-rate sample
+    per receiver, the demodulated float (v1: demod fused in) or the IQ pair (v2, v3, v4)."""
     F, T, R = w["frames"], w["n_streams"], w["n_rx"]
     return frame_bytes * F * T + (8 if variant >= 2 else 4) * R * (F // w["d1"])
 
 
-# ------------------------------------------------------------------ clocks ----
+def bench_config(w, wname):
+    """Identical for both arms (the driver compares them)."""
+    return {"workload": f"{wname}: {w['desc']}", "sample_rate": w["fs"], "frames_per_step": w["frames"],
+            "n_receivers": w["n_rx"], "n_streams": w["n_streams"], "channel_fir": [w["n1"], w["d1"]],
+            "audio_fir": [w["n2"], w["d2"]], "modes": w["modes"],
+            "parallelism": "receivers sharded by tuner, no collective"}
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def stored_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from a COMMITTED ncu --set full capture (never
+    measured in this run; the file says which capture)."""
+    path = os.path.join(ROOT, TRAFFIC_FILE)
+    if not os.path.exists(path):
+        return {}
+    return json.load(open(path)).get(key, {})
+
+
+# ------------------------------------------------------------------ clocks, placement ----
 
 class ClockSampler:
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -95,7 +136,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -109,6 +150,7 @@ class ClockSampler:
             except subprocess.TimeoutExpired:
                 self.proc.kill()
                 out, _ = self.proc.communicate()
+            self.proc = None
         if not out.strip():
             try:
                 out = subprocess.check_output(
@@ -137,31 +179,78 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_near_gpu(local):
+    """Pin this rank (and the pinned buffers it is about to allocate: first touch) to the host cores
+    next to its GPU: eight ranks feeding eight GPUs through one NUMA node was what held the host
+    path's scaling at 0.44 in round 1.  Returns a short description for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        node = int(open(path + "/numa_node").read())
+        cpus = open(path + "/local_cpulist").read().strip()
+        if node < 0 or not cpus:
+            return {"numa_node": node, "bound": False}
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return {"numa_node": node, "cpus": cpus, "bound": bool(ids)}
+    except Exception as e:  # placement is best effort
+        return {"bound": False, "why": str(e)[:80]}
+
+
 # ------------------------------------------------------------------ CPU reference arm ----
 
 def _cpu_threads(n_rx):
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     replicas = max(1, cores // n_rx)
     return min(cores, n_rx * replicas), replicas
 
 
-def cpu_reference_run(w, steps, warmup, max_seconds=None, threads=None, flavour="ref"):
-    """The reference's CPU chain on the host cores.  Each worker thread owns an independent graph
-    (tuner source + its share of the receivers), exactly how the reference would be scaled out --
-    its own Radio::run visits receivers sequentially on one thread (radio.cxx:56-59), which is
+def cpu_sample_receivers(w):
+    """The receivers of a workload the CPU arms run: all of them for a small bank, an evenly spaced
+    subset (whole streams, so every sampled receiver keeps its own tuner stream) for a large one.
+    Throughput is per receiver-frame and receivers are independent, so the figure scales linearly."""
+    R, T = w["n_rx"], w["n_streams"]
+    if R <= CPU_SAMPLE_RX:
+        return list(range(R))
+    per = R // T
+    if per >= CPU_SAMPLE_RX:
+        return list(range(CPU_SAMPLE_RX))            # the first tuner's receivers
+    nstreams = max(1, CPU_SAMPLE_RX // per)
+    step = max(1, T // nstreams)
+    return [s * per + k for s in range(0, step * nstreams, step) for k in range(per)]
+
+
+def cpu_reference_run(w, seconds, threads=None, flavour="ref", steps=None, warmup=1, first_stream=0):
+    """The reference's CPU chain on the host cores, fed the SAME synthetic blocks as the GPU arm
+    (synth.lattice_noise of the receiver's global stream).  Each worker thread owns an independent
+    graph (tuner source + its share of the receivers), exactly how the reference would be scaled out
+    -- its own Radio::run visits receivers sequentially on one thread (radio.cxx:56-59), which is
     what `threads=1` times (single thread next to all cores).
+    Runs `steps` blocks if given, else as many as fill `seconds`; never less than MIN_CPU_SECONDS.
     Returns dict(value MS/s, seconds, steps, cores, kind, sample)."""
     import graphlib as G
-    t1, t2 = workload_taps(w)
+    from oracle import wro
+    t1, t2 = workload_taps(w, wro.lowpass_design)
     ifs, modes = synth.workload_ifs(w), synth.workload_modes(w)
     F, R, T = w["frames"], w["n_rx"], w["n_streams"]
-    nthreads, replicas = _cpu_threads(R) if threads is None else (threads, 1)
-    total_rx = R * replicas
-    iq = [synth.lattice_noise(F, stream=t) for t in range(min(T, 8))]
+    per = R // T
+    rx_ids = cpu_sample_receivers(w)
+    nthreads, replicas = _cpu_threads(len(rx_ids)) if threads is None else (threads, 1)
+    total_rx = len(rx_ids) * replicas
+    streams = sorted({r // per for r in rx_ids})
+    iq = {s: synth.lattice_noise(F, stream=first_stream + s) for s in streams}
     use_ref = G.have(flavour)
     assign = [[] for _ in range(nthreads)]
     for i in range(total_rx):
-        assign[i % nthreads].append(i % R)
+        assign[i % nthreads].append(rx_ids[i % len(rx_ids)])
 
     if use_ref:
         graphs = []
@@ -169,7 +258,7 @@ def cpu_reference_run(w, steps, warmup, max_seconds=None, threads=None, flavour=
             # one graph per (thread, stream) so every receiver is fed its own tuner stream
             per_stream = {}
             for r in assign[th]:
-                per_stream.setdefault(r % T % len(iq), []).append(r)
+                per_stream.setdefault(r // per, []).append(r)
             gl = []
             for s, rxs in per_stream.items():
                 g = G.Graph(flavour, w["fs"], F)
@@ -188,14 +277,13 @@ def cpu_reference_run(w, steps, warmup, max_seconds=None, threads=None, flavour=
                 for g, x in graphs[th]:
                     g.run(x)
     else:
-        from oracle import wro
         rxs = [[wro.Rx(w["fs"], int(ifs[r]), t1, w["d1"], int(modes[r]), t2, w["d2"]) for r in assign[th]]
                for th in range(nthreads)]
 
         def work(th, n):
             for _ in range(n):
                 for j, rx in enumerate(rxs[th]):
-                    rx.process(iq[assign[th][j] % T % len(iq)])
+                    rx.process(iq[assign[th][j] // per])
 
     def run_all(n):
         ths = [threading.Thread(target=work, args=(t, n)) for t in range(nthreads)]
@@ -207,35 +295,46 @@ def cpu_reference_run(w, steps, warmup, max_seconds=None, threads=None, flavour=
         return time.perf_counter() - t0
 
     run_all(max(1, warmup))
-    if max_seconds is not None:
-        probe = run_all(1)
-        steps = max(1, min(steps, int(max_seconds / max(probe, 1e-6))))
-    secs = run_all(steps)
+    probe = max(run_all(1), 1e-6)
+    want = max(seconds, MIN_CPU_SECONDS)
+    n = max(1, int(np.ceil(want / probe))) if steps is None else max(steps, int(np.ceil(1.15 * MIN_CPU_SECONDS / probe)))
+    secs = run_all(n)
+    while secs < MIN_CPU_SECONDS:          # a noisy probe under-sized the sample: time a longer one
+        n = int(np.ceil(n * 1.3 * MIN_CPU_SECONDS / max(secs, 1e-6)))
+        secs = run_all(n)
     if use_ref:
         for gl in graphs:
             for g, _ in gl:
                 g.close()
-    frames = total_rx * F * steps
+    frames = total_rx * F * n
+    what = f"{len(rx_ids)} of the workload's {R} receivers" if len(rx_ids) < R else f"all {R} receivers"
     return {
-        "value": frames / secs / 1e6, "seconds": secs, "steps": steps, "cores": nthreads,
+        "value": frames / secs / 1e6, "seconds": secs, "steps": n, "cores": nthreads,
         "kind": "reference" if use_ref else "port",
-        "sample": f"{steps} blocks of {F} frames x {total_rx} receivers "
-                  f"({replicas} replica(s) of the workload) on {nthreads} threads, "
+        "sample": f"{n} blocks of {F} frames x {total_rx} receivers ({what}, {replicas} replica(s)) on {nthreads} threads, "
+                  f"{secs:.1f} s, synth.lattice_noise blocks (the GPU arm's), "
                   + (("oracle/_ref (unmodified reference, g++ -O0, the reference's stock flags)" if flavour == "ref_O0" else
                       "oracle/_ref (unmodified reference, g++ -O2 -ffp-contract=off)") if use_ref else "oracle port"),
         "host_cores": os.cpu_count(),
     }
 
 
-def stock_flags_run(w, seconds):
-    """The same chain built the way the reference's stock ./configure builds it (-O0, see
-    oracle/Makefile), all host threads, a short sample: SURVEY.md 8d asks for it once.  The
-    headline CPU figure stays the -O2 build, which is the faster one."""
-    import graphlib as G
-    if not G.have("ref_O0"):
-        return {}
-    r = cpu_reference_run(w, 1000, 1, max_seconds=seconds, flavour="ref_O0")
-    return {"stock_O0_value": r["value"], "stock_O0_sample": r["sample"]}
+def cpu_baseline_record(w, seconds, stock=True):
+    r = cpu_reference_run(w, seconds)
+    cpu = {"value": r["value"], "unit": "MSamples/s", "cores": r["cores"], "kind": r["kind"],
+           "sample": r["sample"], "host_cores": r["host_cores"], "seconds": r["seconds"]}
+    # the reference as shipped: ONE DSP thread visits every receiver (radio.cxx:56-59)
+    r1 = cpu_reference_run(w, MIN_CPU_SECONDS, threads=1)
+    cpu["single_thread_value"] = r1["value"]
+    cpu["single_thread_sample"] = r1["sample"]
+    if stock:
+        import graphlib as G
+        if G.have("ref_O0"):
+            # the same chain built the way the reference's stock ./configure builds it (-O0, oracle/Makefile)
+            r0 = cpu_reference_run(w, MIN_CPU_SECONDS, flavour="ref_O0")
+            cpu["stock_O0_value"] = r0["value"]
+            cpu["stock_O0_sample"] = r0["sample"]
+    return cpu
 
 
 def reference_arm(args, w, wname):
@@ -244,60 +343,100 @@ def reference_arm(args, w, wname):
         return
     steps = args.steps if args.steps is not None else 20
     warmup = args.warmup if args.warmup is not None else 3
-    r = cpu_reference_run(w, steps, warmup, max_seconds=120.0)
-    r1 = cpu_reference_run(w, 3, 1, max_seconds=10.0, threads=1)
-    stock = stock_flags_run(w, 5.0)
+    r = cpu_reference_run(w, args.cpu_seconds, steps=steps, warmup=warmup)
+    r1 = cpu_reference_run(w, MIN_CPU_SECONDS, threads=1)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "MSamples/s",
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": warmup,
         "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": bench_config(w, wname, None),
+        "config": bench_config(w, wname),
         "cpu_baseline": {"value": r["value"], "unit": "MSamples/s", "cores": r["cores"], "kind": r["kind"],
-                         "sample": r["sample"], "host_cores": r["host_cores"],
-                         "single_thread_value": r1["value"], "single_thread_sample": r1["sample"], **stock},
+                         "sample": r["sample"], "host_cores": r["host_cores"], "seconds": r["seconds"],
+                         "single_thread_value": r1["value"], "single_thread_sample": r1["sample"]},
         "e2e": {"value": r["value"], "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def bench_config(w, wname, l2_note, input_format="f32"):
-    c = {"workload": f"{wname}: {w['desc']}", "input": "interleaved float IQ" if input_format == "f32" else
-         "raw RTL-SDR bytes (u8 IQ, converted in the channel kernel's load)",
-         "sample_rate": w["fs"], "frames_per_step": w["frames"],
-         "n_receivers": w["n_rx"], "n_streams": w["n_streams"], "channel_fir": [w["n1"], w["d1"]],
-         "audio_fir": [w["n2"], w["d2"]], "modes": w["modes"], "parallelism": "receivers sharded by tuner, no collective"}
-    if l2_note:
-        c["l2"] = l2_note
-    return c
-
-
 # ------------------------------------------------------------------ GPU arm ----
 
-def gpu_arm(args, w, wname):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """What the records of one run share: ranks, the device, the process group."""
 
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local)
+        self.placement = bind_near_gpu(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        if self.world == 1:
+            return [float(v) for v in values]
+        t = self.torch.tensor(list(values), device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def parity_check(w, bank_audio, rx_ids, first_stream, t1, t2):
+    """One output block of THIS run (block 0 of every sampled receiver, fresh state) against the
+    oracle on the same synth block: bit-exact for AM/USB/LSB and -- on a glibc box -- for FM."""
+    from oracle import wro
+    ifs, modes = synth.workload_ifs(w), synth.workload_modes(w)
+    per = w["n_rx"] // w["n_streams"]
+    F = w["frames"]
+    bad, worst, blocks = 0, 0.0, {}
+    for r in rx_ids:
+        s = r // per
+        if s not in blocks:
+            blocks[s] = synth.lattice_noise(F, stream=first_stream + s)
+        want = wro.Rx(w["fs"], int(ifs[r]), t1, w["d1"], int(modes[r]), t2, w["d2"]).process(blocks[s])
+        got = bank_audio[r]
+        if not np.array_equal(got.view(np.uint32), want.view(np.uint32)):
+            bad += 1
+            worst = max(worst, float(np.max(np.abs(got - want))))
+    if bad and (worst > 3e-7 or not np.any(modes[rx_ids] == synth.FM)):
+        raise SystemExit(f"bench.py: parity check FAILED: {bad} of {len(rx_ids)} receivers differ from the oracle "
+                         f"(max abs {worst:g}); no number is reported for a wrong result")
+    return {"receivers_checked": len(rx_ids), "block": 0, "oracle": "oracle/libwr_oracle.so (C port pinned to oracle/_ref)",
+            "bit_exact": bad == 0, "receivers_differing": bad, "max_abs_diff": worst,
+            "inputs": "identical: synth.lattice_noise (numpy) == synth.lattice_u8_torch (device), compared in this run"}
+
+
+def chain_record(ctx, wname, w, steps, warmup, full_cpu=True, plugin=False):
+    """Device-timed throughput, per-kernel roofline, host-path figures, in-run parity and the CPU
+    baseline for one receiver-chain workload on this rank's GPU."""
+    torch = ctx.torch
     from webradio_b200 import capi, shard
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
+    args = ctx.args
     F, R, T = w["frames"], w["n_rx"], w["n_streams"]
     M1 = F // w["d1"]
-    M2 = M1 // w["d2"]
-    steps = args.steps if args.steps is not None else (2000 if T == 1 else 30)
-    warmup = args.warmup if args.warmup is not None else 5
-    warmup = max(warmup, 3)
+    M2 = max(M1 // w["d2"], 1)
+    per = R // T
+    mine = shard.weak_scaling_shard(T, R, ctx.rank, ctx.world)     # this rank's own tuners (global ids)
+    first_stream = mine.tuners[0]
 
-    bank = capi.Bank(T, R, F, w["n1"], w["d1"], w["n2"], w["d2"], device=local)
+    bank = capi.Bank(T, R, F, w["n1"], w["d1"], w["n2"], w["d2"], device=ctx.local)
     bank.set_variant(args.variant)
     t1, t2 = workload_taps(w)
     ifs, modes = synth.workload_ifs(w), synth.workload_modes(w)
@@ -306,163 +445,115 @@ def gpu_arm(args, w, wname):
         bank.set_taps(r, 1, t2)
         bank.set_if(r, int(ifs[r]), w["fs"])
         bank.set_mode(r, int(modes[r]))
-        bank.set_stream(r, r % T)
+        bank.set_stream(r, r // per)
 
-    # synthetic tuner blocks on the RTL-SDR sample lattice (b-128)/128, generated in HBM; a
-    # rotating set larger than L2 so that no step finds its input cached
+    # Synthetic tuner blocks on the RTL-SDR lattice, generated on the device by the same counter hash
+    # as synth.lattice_noise (the CPU arm's generator); consecutive blocks of each stream, a rotating
+    # set larger than L2 whatever --steps says, so that no step finds its input cached.
     u8 = args.input == "u8"
-    frame_bytes = 2 if u8 else 8
-    block_bytes = frame_bytes * F * T
+    fb = 2 if u8 else 8
+    block_bytes = fb * F * T
     nbuf = max(2, -(-int(1.25 * L2_BYTES) // block_bytes))
-    nbuf = min(nbuf, max(2, steps + warmup))
-    # weak scaling: this rank owns its own copy of the workload's tuners and receivers
-    mine = shard.weak_scaling_shard(T, R, rank, world)
-    gen = torch.Generator(device="cuda")
-    gen.manual_seed(0xB200 + mine.tuners[0])
-    inputs = []
-    for _ in range(nbuf):
-        raw = torch.randint(0, 256, (T, F, 2), generator=gen, device="cuda", dtype=torch.int32)
-        inputs.append(raw.to(torch.uint8).contiguous() if u8 else ((raw.float() - 128.0) / 128.0).contiguous())
-        del raw
-    audio = [torch.zeros(R, max(M2, 1), device="cuda") for _ in range(min(nbuf, 8))]
-    l2_note = f"rotating set of {nbuf} distinct input blocks ({nbuf * block_bytes / 2**20:.0f} MiB > L2 126 MiB)" \
-        if nbuf * block_bytes > L2_BYTES else \
-        f"rotating set of {nbuf} input blocks ({nbuf * block_bytes / 2**20:.0f} MiB); run is shorter than the L2-sized set"
-    stream = bank.stream()
-
+    raw = [synth.lattice_u8_torch(F, mine.tuners, start=b * F, device="cuda") for b in range(nbuf)]
+    inputs = raw if u8 else [synth.u8_to_f32_torch(x) for x in raw]
+    # ... and the two generators agree: first block, first and last sampled stream, against numpy
+    rx_ids = cpu_sample_receivers(w)
+    for s in sorted({rx_ids[0] // per, rx_ids[-1] // per}):
+        want = synth.lattice_noise(F, stream=first_stream + s)
+        got = synth.u8_to_f32_torch(raw[0][s]).cpu().numpy().ravel()
+        if not np.array_equal(got, want):
+            raise SystemExit("bench.py: device and host input generators disagree")
+    raw_keep = raw[:min(nbuf, 2)]      # the host path's blocks (both formats are derived from the bytes)
+    audio = [torch.zeros(R, M2, device="cuda") for _ in range(min(nbuf, 4))]
     in_ptrs = [x.data_ptr() for x in inputs]
     out_ptrs = [y.data_ptr() for y in audio]
+    stream = bank.stream()
 
     def run_steps(first, n):
         # n calls of wr_bank_process_device, looped on the C side of the ABI
-        bank.run_device_steps(in_ptrs, F, F, out_ptrs, max(M2, 1), first, n, u8=u8)
+        bank.run_device_steps(in_ptrs, F, F, out_ptrs, M2, first, n, u8=u8)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # ---- block 0 from fresh state: the in-run parity check ----
+    run_steps(0, 1)
+    bank.sync()
+    parity = parity_check(w, audio[0].cpu().numpy(), np.array(rx_ids), first_stream, t1, t2) if ctx.rank == 0 else None
 
-    clocks = ClockSampler(local)
-    run_steps(0, warmup)
+    clocks = ClockSampler(ctx.local)
+    run_steps(1, warmup)
     bank.sync()
 
     # ---- timed region: exactly K steps, CUDA events on the launch stream ----
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     ext = torch.cuda.ExternalStream(stream)
-    barrier()
+    ctx.barrier()
     clocks.start()
     launches0 = bank.launch_count()
     ev0.record(ext)
-    run_steps(warmup, steps)
+    run_steps(1 + warmup, steps)
     ev1.record(ext)
     ev1.synchronize()
     launches = bank.launch_count() - launches0
-    barrier()
+    ctx.barrier()
     # the job finishes when its slowest rank does: MAX over ranks of the device time
-    ms = shard.reduce_max_ms(ev0.elapsed_time(ev1), device="cuda")
-    value = shard.job_throughput(R * F * steps, world, ms) / 1e6
+    ms = ctx.max_over_ranks([ev0.elapsed_time(ev1)])[0]
+    value = shard.job_throughput(R * F * steps, ctx.world, ms) / 1e6
+    # keep the load on long enough for the sampler to see it (a 20-step region of a small bank is 0.5 ms)
+    t_end = time.perf_counter() + 0.4
+    while time.perf_counter() < t_end:
+        run_steps(0, max(steps, 50))
+        bank.sync()
+    clk = clocks.stop()
 
     # ---- per-kernel device time (CUDA events around each kernel, same inputs, K more steps) ----
     bank.set_timing(True)
-    ksteps = min(steps, 2000)
-    run_steps(warmup + steps, ksteps)
+    ksteps = min(max(steps, 20), 2000)
+    run_steps(0, ksteps)
     chan_ms, audio_ms, nb = bank.kernel_times()
     bank.set_timing(False)
     chan_ms_avg = chan_ms / max(nb, 1)
     audio_ms_avg = audio_ms / max(nb, 1)
-
-    # ---- e2e: C ABI with HOST (pinned) buffers, H2D + kernels + D2H every step, pipelined ----
-    depth = bank.pipeline_depth()
-    nh = min(nbuf, 4 if T > 1 else 16)
-    pin_in = [inputs[i].cpu().pin_memory() for i in range(nh)]
-    pin_out = [torch.zeros(R, max(M2, 1)).pin_memory() for _ in range(depth + 1)]
-    # e2e is host-timed: a region of a few blocks (a driver may ask for --steps 10) would measure the
-    # host's timer and the link's wake-up, not the path.  Its regions are therefore at least 1000
-    # blocks long for single-tuner workloads (20-30 ms) and at least 5 for the multi-stream ones
-    # (a block there is milliseconds); `e2e.steps` says what was used.
-    esteps = max(steps, 1000) if T == 1 else max(min(steps, 10), 5)
-
-    pin_in_ptrs = [x.data_ptr() for x in pin_in]
-    pin_out_ptrs = [y.data_ptr() for y in pin_out]
-
-    def e2e_pipelined(n):
-        bank.run_host_steps(pin_in_ptrs, F, pin_out_ptrs, max(M2, 1), 0, n, pipelined=True, u8=u8)
-
-    def e2e_sync(n):
-        bank.run_host_steps(pin_in_ptrs, F, pin_out_ptrs, max(M2, 1), 0, n, pipelined=False, u8=u8)
-
-    # The clock sampler (an nvidia-smi loop) covered the device-timed region above; it is stopped
-    # here because its driver queries stall the submitting thread of a host-driven loop.
-    clk = clocks.stop()
-    # Host-timed, so a hiccup of the host shows: `reps` timed regions of `esteps` steps each, the
-    # MEDIAN is reported and all of them are listed.
-    reps = 5 if T == 1 else 3
-    # warm-up: the host path needs ~0.2 s of traffic before it is steady (measured: 144 k, 149 k,
-    # 180 k, 222 k, 224 k MS/s over the first five regions of 2000 steps after a 3-step warm-up;
-    # PCIe link and host clocks ramp)
-    # ... and every slot of the pipeline must have been used once: a slot's HBM buffers are
-    # allocated on first use (cudaMalloc synchronises), so fewer warm-up blocks than the depth put
-    # allocations into the timed region (r01k: cfg3 fed bytes 6.1 k instead of ~25 k MS/s)
-    for _ in range(4 if T == 1 else 1):
-        e2e_pipelined(max(esteps, 2000) if T == 1 else depth + 2)
-    e2e_runs, sync_runs = [], []
-    ssteps = min(esteps, 200)
-    for _ in range(reps):
-        barrier()
-        t0 = time.perf_counter()
-        e2e_pipelined(esteps)
-        torch.cuda.synchronize()
-        e2e_runs.append(time.perf_counter() - t0)
-    for _ in range(reps):
-        barrier()
-        t0 = time.perf_counter()
-        e2e_sync(ssteps)
-        torch.cuda.synchronize()
-        sync_runs.append(time.perf_counter() - t0)
-    if world > 1:
-        tt = torch.tensor(e2e_runs + sync_runs, device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_runs, sync_runs = [float(x) for x in tt[:reps]], [float(x) for x in tt[reps:]]
-    e2e_s = statistics.median(e2e_runs)
-    e2e_sync_s = statistics.median(sync_runs)
-    e2e_value = world * R * F * esteps / e2e_s / 1e6
-    e2e_sync_value = world * R * F * ssteps / e2e_sync_s / 1e6
-    e2e_all = [world * R * F * esteps / x / 1e6 for x in e2e_runs]
-
-    # ---- roofline of the dominant kernel (fused mix + FIR + demod) ----
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak = float(json.load(open(peaks_path))["hbm_gbs"])
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
     variant_used = bank.variant_in_use()
-    kb = chan_kernel_bytes(w, variant_used, frame_bytes)
-    achieved = kb / (chan_ms_avg * 1e-3) / 1e9 if chan_ms_avg > 0 else 0.0
-    traffic, ncu = None, None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        rec = json.load(open(tpath)).get(wname + ("_u8" if u8 else ""), {})
-        traffic = rec.get("chan_kernel_dram_bytes_per_launch")
-        if rec:
-            # what binds the kernel when it is not HBM (one ncu --set full capture, profiles/)
-            ncu = {k: rec[k] for k in ("issue_active_pct", "l1tex_throughput_pct", "fma_pipe_cycles_active_pct",
-                                       "warp_instructions_per_launch", "kernel", "source") if k in rec}
+
+    # ---- host path: the C ABI with HOST buffers, H2D + kernels + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = host_path(ctx, bank, w, raw_keep, M2, steps)
+    del inputs, raw, audio
+    bank.close()
+    torch.cuda.empty_cache()
+
+    # ---- the DspBlock plug-in surface: the reference's Radio::run over the drop-in blocks ----
+    if plugin and e2e is not None and T == 1:
+        pl = plugin_leg(ctx, w, first_stream, t1, t2)
+        if pl:
+            e2e.update(pl)
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = hbm_peak()
+    alg = algorithmic_bytes(w, fb)
+    own = chan_kernel_bytes(w, variant_used, fb)
+    achieved = alg / (chan_ms_avg * 1e-3) / 1e9 if chan_ms_avg > 0 else 0.0
+    cap = stored_traffic(wname + ("_u8" if u8 else ""))
+    names = {1: "chan_kernel_v1: fused NCO mix + channel FIR + demod", 2: "chan_kernel_v2: fused NCO mix + channel FIR",
+             3: "chan_kernel_v3: fused NCO mix + channel FIR", 4: "chan_kernel_v4: fused NCO mix + streaming channel FIR"}
     roofline = {
-        "bound": "hbm",
-        "kernel": f"chan_kernel_v{variant_used}: fused NCO mix + channel FIR" if variant_used >= 2 else "chan_kernel_v1: fused NCO mix + channel FIR + demod",
-        "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-        # SURVEY.md 8d also asks for the fraction of the chip's nominal ~8 TB/s
-        "frac_of_nominal_8000_gbs": achieved / 8000.0,
-        "algorithmic_bytes_per_launch": kb, "kernel_ms": chan_ms_avg, "audio_kernel_ms": audio_ms_avg,
-        # serialised kernel times (CUDA events around each kernel); in the timed region above the
-        # next block's channel kernel starts under this block's demodulator kernel (programmatic
-        # dependent launch), so ms_per_step < kernel_ms + audio_kernel_ms
+        "bound": "hbm", "kernel": names.get(variant_used, str(variant_used)),
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": cap.get("chan_kernel_dram_bytes_per_launch"),
+        "traffic_source": ("stored ncu --set full capture, not measured in this run: " + cap.get("source", TRAFFIC_FILE)) if cap else None,
+        "peak_source": peak_src,
+        "frac_of_nominal_8000_gbs": achieved / 8000.0,          # SURVEY.md 8d also asks for this one
+        "algorithmic_bytes_per_launch": alg,
+        "algorithmic_bytes_formula": "SURVEY.md 8d: 8*F*T + 4*R*F/(D1*D2)" if fb == 8 else "SURVEY.md 8d with 2-byte frames: 2*F*T + 4*R*F/(D1*D2)",
+        "kernel_own_bytes_per_launch": own, "kernel_own_gbs": own / (chan_ms_avg * 1e-3) / 1e9 if chan_ms_avg > 0 else 0.0,
+        "kernel_ms": chan_ms_avg, "audio_kernel_ms": audio_ms_avg,
+        # serialised kernel times (CUDA events around each kernel); in the timed region the next block's
+        # channel kernel starts under this block's demodulator kernel, so ms_per_step < their sum
         "kernel_share_of_step": chan_ms_avg / max(chan_ms_avg + audio_ms_avg, 1e-12),
-        "ncu": ncu,
+        "whole_step_frac": alg * steps / (ms * 1e-3) / 1e9 / peak,
+        "ncu_stored": {k: cap[k] for k in ("issue_active_pct", "l1tex_throughput_pct", "fma_pipe_cycles_active_pct",
+                                            "warp_instructions_per_launch", "kernel", "source") if k in cap} or None,
         "receiver_frames_per_s": R * F / (chan_ms_avg * 1e-3) if chan_ms_avg > 0 else 0.0,
         "note": ("shared-tuner workload: every receiver re-uses the one tuner block from L2/shared memory, "
                  "so DRAM traffic is small by construction and the kernel is FP32-issue bound, not HBM bound "
@@ -470,39 +561,180 @@ def gpu_arm(args, w, wname):
     }
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(w, 1000, 1, max_seconds=args.cpu_seconds)
-        cpu = {"value": r["value"], "unit": "MSamples/s", "cores": r["cores"], "kind": r["kind"],
-               "sample": r["sample"], "host_cores": r["host_cores"]}
-        # the reference as shipped: ONE DSP thread visits every receiver (radio.cxx:56-59)
-        r1 = cpu_reference_run(w, 1000, 1, max_seconds=min(4.0, args.cpu_seconds), threads=1)
-        cpu["single_thread_value"] = r1["value"]
-        cpu["single_thread_sample"] = r1["sample"]
-        cpu.update(stock_flags_run(w, min(3.0, args.cpu_seconds)))
+    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_record(w, args.cpu_seconds, stock=full_cpu)
 
-    if rank == 0:
+    rec = {
+        "value": value, "unit": "MSamples/s", "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+        "config": bench_config(w, wname),
+        "input": "interleaved float IQ" if not u8 else "raw RTL-SDR bytes (u8 IQ, converted in the channel kernel's load)",
+        "l2": f"rotating set of {nbuf} distinct input blocks ({nbuf * block_bytes / 2**20:.0f} MiB > L2 126 MiB)",
+        "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "parity": parity,
+        "tuner_msamples_per_s": ctx.world * T * F * steps / (ms * 1e-3) / 1e6,
+        "kernel_variant": variant_used,
+    }
+    return rec
+
+
+def host_path(ctx, bank, w, raw_blocks, M2, steps):
+    """e2e.value: the synchronous wr_bank_process call on HOST buffers -- what DspBlock::process of the
+    drop-in blocks makes once per tuner block (copy in, kernels, copy out inside the call).  Beside it:
+    the same fed raw RTL-SDR bytes, and the pipelined submit/wait form of the C ABI (several blocks in
+    flight; a host that owns its tuner loop can use it, the unchanged Radio::run cannot)."""
+    torch = ctx.torch
+    F, R, T = w["frames"], w["n_rx"], w["n_streams"]
+    depth = bank.pipeline_depth()
+    small = T == 1
+    pin_u8 = [x.cpu().pin_memory() for x in raw_blocks]
+    pin_f32 = [synth.u8_to_f32_torch(x).pin_memory() for x in pin_u8]
+    pin_out = [torch.zeros(R, M2).pin_memory() for _ in range(depth + 1)]
+    outp = [y.data_ptr() for y in pin_out]
+    # host-timed: regions long enough that the host's timer and the link's wake-up do not show
+    esteps = max(steps, 500) if small else max(min(steps, 10), 4)
+    reps = 5 if small else 3
+
+    def run(ptrs, n, pipelined, u8):
+        bank.run_host_steps(ptrs, F, outp, M2, 0, n, pipelined=pipelined, u8=u8)
+
+    out = {}
+    for name, bufs, u8 in (("f32", pin_f32, False), ("u8", pin_u8, True)):
+        ptrs = [x.data_ptr() for x in bufs]
+        # warm-up: every pipeline slot used once (its HBM buffers are allocated on first use), the
+        # link and the host clocks ramped (~0.2 s of traffic on small blocks)
+        for _ in range(3 if small else 1):
+            run(ptrs, max(esteps, 1000) if small else depth + 2, True, u8)
+        res = {}
+        for mode, pipelined, n in (("sync", False, max(esteps // 2, 4) if small else esteps), ("pipelined", True, esteps)):
+            runs = []
+            for _ in range(reps):
+                ctx.barrier()
+                t0 = time.perf_counter()
+                run(ptrs, n, pipelined, u8)
+                torch.cuda.synchronize()
+                runs.append(time.perf_counter() - t0)
+            runs = ctx.max_over_ranks(runs)
+            res[mode] = ctx.world * R * F * n / statistics.median(runs) / 1e6
+            res[mode + "_all"] = [ctx.world * R * F * n / x / 1e6 for x in runs]
+            res[mode + "_steps"] = n
+        out[name] = res
+    fbytes = 8 * F * T
+    return {
+        "value": out["f32"]["sync"], "unit": "MSamples/s",
+        "h2d_bytes_per_step": fbytes, "d2h_bytes_per_step": 4 * R * M2,
+        "mode": "synchronous wr_bank_process on pinned host buffers, float IQ: the call DspBlock::process makes "
+                "(one block per call; the copy in, the kernels and the copy out overlap inside it by sub-block)",
+        "steps": out["f32"]["sync_steps"], "repeats": reps, "values": out["f32"]["sync_all"],
+        "pipelined_value": out["f32"]["pipelined"], "pipelined_depth": depth,
+        "pipelined_note": "wr_bank_submit / wr_bank_wait, several blocks in flight: not reachable from the unchanged Radio::run",
+        "u8_value": out["u8"]["sync"], "u8_pipelined_value": out["u8"]["pipelined"],
+        "u8_h2d_bytes_per_step": 2 * F * T,
+        "u8_note": "the same calls fed raw RTL-SDR bytes, the reference tuner's native format (rtlsdrtuner.cxx:104-108)",
+    }
+
+
+def plugin_leg(ctx, w, first_stream, t1, t2):
+    """The reference's UNMODIFIED src/radio.cxx (Radio::run, radio.cxx:56-59) over the drop-in
+    DspBlock classes, SpectrumSink attached as FrontEnd does it (radio.cxx:126-128), pageable
+    std::vector buffers: tests/harness/libwr_radio_dropin.so.  One front-end; every receiver's audio
+    block of the first step is compared with the oracle before anything is timed."""
+    so = os.path.join(ROOT, "tests", "harness", "libwr_radio_dropin.so")
+    if not os.path.exists(so) or ctx.world > 1:
+        return None
+    from oracle import wro
+    C = ctypes
+    fp = C.POINTER(C.c_float)
+    L = C.CDLL(so, mode=C.RTLD_LOCAL)
+    L.wrr_create.restype = C.c_void_p
+    L.wrr_create.argtypes = [C.c_uint, C.c_uint, C.c_uint]
+    L.wrr_add_receiver_geo.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
+    L.wrr_set_taps.argtypes = [C.c_void_p, C.c_int, C.c_int, fp, C.c_uint]
+    L.wrr_start.argtypes = [C.c_void_p]
+    L.wrr_run_steps.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint, C.c_uint, C.c_uint]
+    L.wrr_audio.restype = C.c_long
+    L.wrr_audio.argtypes = [C.c_void_p, C.c_int, fp, C.c_long]
+    L.wrr_destroy.argtypes = [C.c_void_p]
+    F, R = w["frames"], w["n_rx"]
+    ifs, modes = synth.workload_ifs(w), synth.workload_modes(w)
+    rig = L.wrr_create(w["fs"], F, 512)
+    try:
+        for r in range(R):
+            if L.wrr_add_receiver_geo(rig, int(ifs[r]), synth.MODE_NAMES[int(modes[r])].encode(),
+                                      w["n1"], w["d1"], w["n2"], w["d2"]) < 0:
+                return None
+        if L.wrr_start(rig) != 0:
+            return {"plugin_value": None, "plugin_note": "the drop-in pipeline did not start"}
+        a1, a2 = np.ascontiguousarray(t1, np.float32), np.ascontiguousarray(t2, np.float32)
+        for r in range(R):
+            L.wrr_set_taps(rig, r, 0, a1.ctypes.data_as(fp), a1.size)
+            L.wrr_set_taps(rig, r, 1, a2.ctypes.data_as(fp), a2.size)
+        nblk = 8
+        blocks = [synth.lattice_noise(F, stream=first_stream, start=b * F) for b in range(nblk)]
+        ptrs = (C.c_void_p * nblk)(*[b.ctypes.data for b in blocks])
+        L.wrr_run_steps(rig, ptrs, nblk, 0, 1)
+        M2 = F // w["d1"] // w["d2"]
+        bad = 0
+        for r in range(R):
+            got = np.empty(M2, np.float32)
+            n = L.wrr_audio(rig, r, got.ctypes.data_as(fp), M2)
+            want = wro.Rx(w["fs"], int(ifs[r]), t1, w["d1"], int(modes[r]), t2, w["d2"]).process(blocks[0])
+            if n != M2 or not np.array_equal(got.view(np.uint32), want.view(np.uint32)):
+                if np.max(np.abs(got - want)) > 3e-7:
+                    raise SystemExit("bench.py: plug-in leg: audio differs from the oracle")
+                bad += 1
+        L.wrr_run_steps(rig, ptrs, nblk, 1, 200)
+        runs = []
+        n = 300
+        for _ in range(5):
+            t0 = time.perf_counter()
+            L.wrr_run_steps(rig, ptrs, nblk, 1, n)
+            runs.append(time.perf_counter() - t0)
+        return {"plugin_value": R * F * n / statistics.median(runs) / 1e6,
+                "plugin_values": [R * F * n / x / 1e6 for x in runs], "plugin_steps": n,
+                "plugin_parity": {"receivers_checked": R, "bit_exact": bad == 0},
+                "plugin_note": "Radio::run() of the reference's unmodified src/radio.cxx over the drop-in blocks: one "
+                               "FrontEnd (replay tuner + SpectrumSink, 512 points) and every receiver, pageable "
+                               "std::vector buffers, synchronous DspBlock::process per block"}
+    finally:
+        L.wrr_destroy(rig)
+
+
+def gpu_arm(args, wname):
+    ctx = Ctx(args)
+    w = synth.WORKLOADS[wname]
+    T = w["n_streams"]
+    steps = args.steps if args.steps is not None else (2000 if T == 1 else 30)
+    warmup = max(args.warmup if args.warmup is not None else 5, 3)
+    subs = args.subs
+    if subs is None:
+        subs = "cfg2,cfg4,cfg5" if wname == "cfg3" else "none"
+    subs = [s for s in subs.split(",") if s and s != "none" and s != wname]
+
+    rec = chain_record(ctx, wname, w, steps, warmup, full_cpu=True, plugin=True)
+    configs = {}
+    for s in subs:
+        if s == "cfg4":
+            import bench_spectrum
+            configs[s] = bench_spectrum.record(ctx, steps=None, warmup=3)
+        else:
+            ws = synth.WORKLOADS[s]
+            ssteps = 400 if ws["n_streams"] == 1 else 20
+            configs[s] = chain_record(ctx, s, ws, ssteps, 5, full_cpu=False, plugin=True)
+            if s == "cfg5":
+                configs[s]["share"] = (f"one GPU's share of BASELINE configs[4] (8192 receivers on 8 GPUs = 16 tuners x 64 "
+                                       f"receivers per GPU); this run holds {ctx.world} such share(s) on {ctx.world} GPU(s)")
+    if ctx.rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "MSamples/s", "n_gpus": world, "steps": steps,
-            "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": rec["value"], "unit": "MSamples/s", "n_gpus": ctx.world, "steps": rec["steps"],
+            "warmup": rec["warmup"], "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": bench_config(w, wname, l2_note, args.input),
-            "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": "MSamples/s", "h2d_bytes_per_step": block_bytes,
-                    "d2h_bytes_per_step": 4 * R * M2, "steps": esteps,
-                    "mode": f"pipelined depth {depth}, copy-in hand-over by a counter in HBM the channel kernel waits on",
-                    "sync_value": e2e_sync_value, "repeats": reps, "values": e2e_all},
-            "gpu_launches": launches,
-            "roofline": roofline,
-            "cpu_baseline": cpu,
-            "hbm_gbs_algorithmic_whole_step": algorithmic_bytes(w, frame_bytes) * steps / (ms * 1e-3) / 1e9,
-            "tuner_msamples_per_s": world * T * F * steps / (ms * 1e-3) / 1e6,
-            "kernel_variant": variant_used,
         }
+        line.update({k: rec[k] for k in rec if k not in line})
+        line["placement"] = ctx.placement
+        if configs:
+            line["configs"] = configs
         print(json.dumps(line), flush=True)
-    bank.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    ctx.close()
 
 
 def claim_stdout():
@@ -560,13 +792,12 @@ def main():
 
 def run(args):
     if args.workload == "cfg4":
-        from webradio_b200 import bench_spectrum
+        import bench_spectrum
         return bench_spectrum.main(args)
-    w = synth.WORKLOADS[args.workload]
     if args.impl == "reference":
-        reference_arm(args, w, args.workload)
+        reference_arm(args, synth.WORKLOADS[args.workload], args.workload)
     else:
-        gpu_arm(args, w, args.workload)
+        gpu_arm(args, args.workload)
 
 
 if __name__ == "__main__":

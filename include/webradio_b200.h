@@ -135,7 +135,11 @@ int wr_rx_set_lookback(wr_bank *b, unsigned rx, const float *prev_iq);
  * reference src/dsp/dspblock.cxx:177-195: synchronous, results host-visible on return).
  *   iq_host    : [n_streams][nframes][2] float
  *   audio_host : receiver r's floor(floor(nframes/d1)/d2) output frames start at r*audio_stride
- * Keeps the tuner block in HBM for wr_bank_read_stage. */
+ * Inside the one synchronous call a block of more than ~0.5 MB is cut into up to four
+ * consecutive sub-blocks, so that the copy in of one runs under the kernels of the one before and
+ * under the copy out of the one before that; the carried state makes the samples the same
+ * (env WR_SYNC_SPLIT=n forces n pieces, 1 = none).  Pinned buffers copy at link speed; pageable
+ * ones work and are staged by the driver. */
 int wr_bank_process(wr_bank *b, const float *iq_host, unsigned nframes,
 		float *audio_host, size_t audio_stride);
 

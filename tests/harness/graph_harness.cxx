@@ -17,6 +17,7 @@
  * Same graph, same inputs, so the parity tests read like the reference's own
  * tests would.
  */
+#include <mutex>
 #include <vector>
 #include <string>
 #include <algorithm>
@@ -101,19 +102,32 @@ struct Graph {
 	vector<Rx> rx;
 	SpectrumSink *spectrum;
 	bool started;
+	unsigned long runs;
 };
 
+// Silences the blocks' LOG_DEBUG chatter by pointing fd 2 at /dev/null for the duration of a call.
+// fd 2 is process-wide and bench.py runs one graph per host thread, so the redirection is counted:
+// the first thread in redirects, the last one out restores (two threads saving and restoring on
+// their own left stderr on /dev/null for good -- and swallowed the caller's own error messages).
 struct QuietStderr {
-	int saved;
-	QuietStderr(bool on) : saved(-1) {
+	bool on;
+	static std::mutex &mu() { static std::mutex m; return m; }
+	static int &depth() { static int d = 0; return d; }
+	static int &saved() { static int s = -1; return s; }
+	QuietStderr(bool want) : on(want) {
 		if (!on) return;
-		fflush(stderr);
-		saved = dup(2);
-		int nul = open("/dev/null", O_WRONLY);
-		if (nul >= 0) { dup2(nul, 2); close(nul); }
+		std::lock_guard<std::mutex> lk(mu());
+		if (depth()++ == 0) {
+			fflush(stderr);
+			saved() = dup(2);
+			int nul = open("/dev/null", O_WRONLY);
+			if (nul >= 0) { dup2(nul, 2); close(nul); }
+		}
 	}
 	~QuietStderr() {
-		if (saved >= 0) { fflush(stderr); dup2(saved, 2); close(saved); }
+		if (!on) return;
+		std::lock_guard<std::mutex> lk(mu());
+		if (--depth() == 0 && saved() >= 0) { fflush(stderr); dup2(saved(), 2); close(saved()); saved() = -1; }
 	}
 };
 
@@ -143,6 +157,7 @@ void *wrh_graph_create(unsigned fs, unsigned block_frames)
 	g->blockFrames = block_frames;
 	g->spectrum = NULL;
 	g->started = false;
+	g->runs = 0;
 	return g;
 }
 
@@ -219,7 +234,9 @@ int wrh_graph_start(void *h)
 int wrh_graph_run(void *h, const float *iq)
 {
 	Graph *g = (Graph*)h;
-	QuietStderr q(g_quiet);
+	// only the first block resizes buffers (and logs it); later blocks run without the two dup2 calls
+	QuietStderr q(g_quiet && g->runs == 0);
+	g->runs++;
 	g->src->feed(iq, (size_t)g->blockFrames * 2);
 	return g->src->run() ? 0 : -1;
 }
@@ -248,6 +265,7 @@ int wrh_graph_detach(void *h, int rx)
 	if (rx < 0 || rx >= (int)g->rx.size())
 		return -1;
 	QuietStderr q(g_quiet);
+	g->runs = 0; // buffers may be resized (and logged) again
 	g->src->disconnect(g->rx[rx].dc);
 	return 0;
 }
@@ -258,6 +276,7 @@ int wrh_graph_attach(void *h, int rx)
 	if (rx < 0 || rx >= (int)g->rx.size())
 		return -1;
 	QuietStderr q(g_quiet);
+	g->runs = 0;
 	g->src->connect(g->rx[rx].dc);
 	return g->rx[rx].dc->isRunning() ? 0 : -1;
 }
@@ -268,6 +287,7 @@ int wrh_graph_restart(void *h)
 {
 	Graph *g = (Graph*)h;
 	QuietStderr q(g_quiet);
+	g->runs = 0;
 	g->src->stop();
 	g->started = g->src->start();
 	return g->started ? 0 : -1;

@@ -85,6 +85,34 @@ int wrr_add_receiver(void *h, int if_hz, const char *mode)
 	return (int)r->rx.size() - 1;
 }
 
+/* The same, at another geometry: tap counts and decimations are set through the drop-in blocks' own
+ * additions (LowPass::setFirLength; the reference fixes 64 taps at compile time, lowpass.cxx:39)
+ * before the pipeline starts.  0 keeps the reference default. */
+int wrr_add_receiver_geo(void *h, int if_hz, const char *mode, unsigned n1, unsigned d1, unsigned n2, unsigned d2)
+{
+	Quiet q;
+	Rig *r = (Rig*)h;
+	Receiver *rx = new Receiver();
+	if (n1) rx->channelFilter()->setFirLength(n1);
+	if (d1) rx->channelFilter()->setDecimation(d1);
+	if (n2) rx->audioFilter()->setFirLength(n2);
+	if (d2) rx->audioFilter()->setDecimation(d2);
+	rx->setFrontEnd(r->fe);
+	rx->downconverter()->setIF(if_hz);
+	if (!rx->demodulator()->setModeString(mode))
+		return -1;
+	r->rx.push_back(rx);
+	return (int)r->rx.size() - 1;
+}
+
+/* injected coefficients (stage 0 = channel filter, 1 = audio filter), on a started pipeline */
+int wrr_set_taps(void *h, int rx, int stage, const float *taps, unsigned n)
+{
+	Rig *r = (Rig*)h;
+	LowPass *lp = stage ? r->rx[rx]->audioFilter() : r->rx[rx]->channelFilter();
+	return lp->setCoefficients(taps, n) ? 0 : -1;
+}
+
 int wrr_start(void *h)
 {
 	Quiet q;
@@ -94,10 +122,21 @@ int wrr_start(void *h)
 /* one Radio::run() (radio.cxx:56-59) over a caller-supplied tuner block */
 int wrr_run(void *h, const float *iq)
 {
-	Quiet q;
 	Rig *r = (Rig*)h;
 	r->tuner->feed(iq, (size_t)r->frames * 2);
 	Radio::run();
+	return 0;
+}
+
+/* `steps` calls of Radio::run() over a rotating set of caller-supplied tuner blocks (bench.py's
+ * plug-in leg: the whole loop stays on the C++ side, as the reference's main() has it) */
+int wrr_run_steps(void *h, const float *const *iq, unsigned n_iq, unsigned first, unsigned steps)
+{
+	Rig *r = (Rig*)h;
+	for (unsigned i = 0; i < steps; i++) {
+		r->tuner->feed(iq[(first + i) % n_iq], (size_t)r->frames * 2);
+		Radio::run();
+	}
 	return 0;
 }
 

@@ -28,10 +28,12 @@ def test_reference_arm_prints_one_json_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["gpu_launches"] == 0
     assert d["higher_is_better"] is True and d["unit"] == "MSamples/s" and d["value"] > 0
-    assert d["config"]["workload"].startswith("cfg2")
+    assert d["config"]["workload"].startswith("cfg3")       # the largest single-GPU config is the line's workload
+    assert "l2" not in d["config"] and "input" not in d["config"]   # nothing arm-specific in `config`
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"]
     assert cb["single_thread_value"] > 0
+    assert cb["seconds"] >= 2.0 and "synth.lattice_noise" in cb["sample"]      # no CPU sample shorter than 2 s
     assert d["e2e"] == {"value": d["value"], "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
@@ -51,3 +53,34 @@ def test_library_chatter_on_fd1_does_not_reach_stdout():
     assert p.returncode == 0, p.stderr
     assert p.stdout == '{"ok": 1}\n'
     assert "NCCL version 0.0" in p.stderr
+
+
+def test_reference_arm_does_not_map_the_product_library():
+    """The CPU arm designs its taps with the oracle: libwebradio_b200.so never enters that process."""
+    code = ("import sys, os; sys.path.insert(0, %r); sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1']\n"
+            "import bench\n"
+            "bench.MIN_CPU_SECONDS = 0.05\n"
+            "bench.reference_arm(bench.parse_args(), bench.synth.WORKLOADS['cfg2'], 'cfg2')\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libwebradio_b200' not in maps, 'product library mapped in the reference arm'\n"
+            "assert 'libwr_ref' in maps or 'libwr_oracle' in maps\n") % ROOT
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+
+
+def test_gpu_and_reference_arm_name_the_same_config():
+    sys.path.insert(0, ROOT)
+    import bench
+    for name, w in bench.synth.WORKLOADS.items():
+        c = bench.bench_config(w, name)
+        assert set(c) == {"workload", "sample_rate", "frames_per_step", "n_receivers", "n_streams", "channel_fir",
+                          "audio_fir", "modes", "parallelism"}
+    # the CPU arms of a large bank run an evenly spaced subset of whole streams
+    ids = bench.cpu_sample_receivers(bench.synth.WORKLOADS["cfg3"])
+    assert len(ids) == 64 and ids[0] == 0 and ids[-1] == 1008 and len(set(ids)) == 64
+    ids5 = bench.cpu_sample_receivers(bench.synth.WORKLOADS["cfg5"])
+    assert ids5 == list(range(64))
+    assert bench.cpu_sample_receivers(bench.synth.WORKLOADS["cfg2"]) == list(range(64))
+    # SURVEY.md 8d algorithmic bytes
+    assert bench.algorithmic_bytes(bench.synth.WORKLOADS["cfg3"]) == 8 * 102400 * 1024 + 4 * 1024 * 2048
+    assert bench.algorithmic_bytes(bench.synth.WORKLOADS["cfg2"]) == 819200 + 524288

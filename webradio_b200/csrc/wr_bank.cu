@@ -201,6 +201,7 @@ struct wr_bank {
 	int demodRegs = 0;
 	bool anyFM = true;          // any receiver in FM mode (as of the last configuration upload)
 	int demodPerSM = -1;        // WR_DEMOD_PER_SM: > 0 = persistent demodulator grid of that many CTAs per SM, 0 = one CTA per tile, < 0 = by bank size
+	unsigned syncSplit = 0;     // WR_SYNC_SPLIT: pieces a synchronous wr_bank_process call is cut into (0 = by size)
 	int waitLate = 1;           // WR_WAIT_LATE: the channel kernel runs under the previous block's demodulator kernel
 	// the device address of a pinned output buffer (OUT_DIRECT): small cache of the runtime's answer
 	struct HostMap { const void *host; void *dev; size_t bytes; } hostMap[8] = {};
@@ -727,6 +728,8 @@ wr_bank *wr_bank_create(int device, unsigned n_streams, unsigned n_receivers, un
 		b->demodPerSM = atoi(e);
 	if (const char *e = getenv("WR_WAIT_LATE"))
 		b->waitLate = atoi(e) != 0;
+	if (const char *e = getenv("WR_SYNC_SPLIT"))
+		b->syncSplit = (unsigned)std::max(0, atoi(e));
 	if ((b->tracePath = getenv("WR_TRACE")) != nullptr) {
 		WR_BANK_ALLOC(cudaMalloc(&b->d_ts, sizeof(unsigned long long) * wrd::kTsWords * kTraceBlocks));
 		WR_BANK_ALLOC(cudaMemset(b->d_ts, 0, sizeof(unsigned long long) * wrd::kTsWords * kTraceBlocks));
@@ -975,8 +978,15 @@ int wr_bank_process_device_u8(wr_bank *b, const uint8_t *iq_dev, size_t stream_s
 	return process_device_any(b, iq_dev, true, stream_stride_frames, nframes, audio_dev, audio_stride, cuda_stream);
 }
 
-static int submit_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframes, float *audio_host, size_t audio_stride)
+// One piece of work for the copy-in / kernels / copy-out pipeline: `nframes` frames of every stream,
+// taken from a host block whose rows (streams) lie `host_pitch` frames apart.  wr_bank_submit hands
+// over whole blocks (host_pitch = nframes); wr_bank_process cuts one block into consecutive
+// sub-blocks, which the carried state turns into exactly the same samples.
+static int submit_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframes, float *audio_host, size_t audio_stride,
+		size_t host_pitch = 0)
 {
+	if (host_pitch == 0)
+		host_pitch = nframes;
 	WR_REQUIRE(b && iq_host && audio_host, WR_EINVAL, "wr_bank_submit: null argument");
 	WR_REQUIRE(nframes <= b->maxF, WR_EINVAL, "wr_bank_submit: %u frames > max_frames %u", nframes, b->maxF);
 	WR_REQUIRE(b->inflight < b->depth, WR_ESTATE, "wr_bank_submit: %d blocks already in flight", b->inflight);
@@ -1017,10 +1027,10 @@ static int submit_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframes
 		}
 	}
 	const unsigned seq = ++b->seq;
-	if (nframes == b->maxF || b->T == 1)
+	if (b->T == 1 || (nframes == b->maxF && host_pitch == nframes))
 		WR_CUDA(cudaMemcpyAsync(s.d_iq, iq_host, fb * (size_t)nframes * b->T, cudaMemcpyHostToDevice, b->h2d));
 	else
-		WR_CUDA(cudaMemcpy2DAsync(s.d_iq, fb * (size_t)b->maxF, iq_host, fb * (size_t)nframes,
+		WR_CUDA(cudaMemcpy2DAsync(s.d_iq, fb * (size_t)b->maxF, iq_host, fb * host_pitch,
 				fb * (size_t)nframes, b->T, cudaMemcpyHostToDevice, b->h2d));
 	if (handIn == IN_FLAG) {
 		if (stream_ops().write((CUstream)b->h2d, (CUdeviceptr)(uintptr_t)(b->d_sync + 0), seq, 0) != CUDA_SUCCESS) {
@@ -1143,10 +1153,44 @@ static int process_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframe
 {
 	WR_REQUIRE(b, WR_EINVAL, "wr_bank_process: null bank");
 	WR_REQUIRE(b->inflight == 0, WR_ESTATE, "wr_bank_process: pipelined blocks still in flight");
-	int rc = submit_any(b, iq_host, u8, nframes, audio_host, audio_stride);
-	if (rc != WR_OK)
-		return rc;
-	return wr_bank_wait(b);
+	// One synchronous call, several pieces in flight inside it: the block is cut into consecutive
+	// sub-blocks so that the copy-in of piece k+1 runs under the kernels of piece k and under the
+	// copy-out of piece k-1.  A piece is a whole number of audio frames (and of the channel kernel's
+	// passes' worth of frames, so that it stays on the same kernel family as a full block).
+	unsigned pieces = b->syncSplit;
+	const unsigned quantum = b->d1 * b->d2;
+	if (pieces == 0) {
+		// by size: pieces of at least 256 KiB of input (copy latency dominates below that)
+		const size_t bytes = (u8 ? 2 : 8) * (size_t)nframes * b->T;
+		pieces = (unsigned)std::min<size_t>(4, std::max<size_t>(1, bytes / (256u << 10)));
+	}
+	pieces = std::min<unsigned>(pieces, (unsigned)b->depth);
+	unsigned per = nframes / std::max(1u, pieces);
+	per -= per % quantum;
+	const unsigned minPiece = std::max(quantum, b->v3.ok ? b->v3.SF : 0u);
+	if (pieces <= 1 || per < minPiece) {
+		int rc = submit_any(b, iq_host, u8, nframes, audio_host, audio_stride);
+		if (rc != WR_OK)
+			return rc;
+		return wr_bank_wait(b);
+	}
+	const size_t fb = u8 ? 2 : 8;
+	int rc = WR_OK;
+	unsigned done = 0, submitted = 0;
+	for (unsigned k = 0; k < pieces && rc == WR_OK; k++) {
+		const unsigned nf = (k + 1 == pieces) ? nframes - done : per;     // the last piece takes the remainder
+		rc = submit_any(b, static_cast<const char*>(iq_host) + fb * done, u8, nf,
+				audio_host + done / quantum, audio_stride, nframes);
+		if (rc == WR_OK)
+			submitted++;
+		done += nf;
+	}
+	for (unsigned k = 0; k < submitted; k++) {
+		const int rw = wr_bank_wait(b);
+		if (rc == WR_OK)
+			rc = rw;
+	}
+	return rc;
 }
 
 int wr_bank_process(wr_bank *b, const float *iq_host, unsigned nframes, float *audio_host, size_t audio_stride)

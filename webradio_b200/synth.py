@@ -26,13 +26,51 @@ def _hash32(x):
 
 def lattice_noise(nframes, seed=0xB200, stream=0, start=0):
     """Interleaved IQ float32[2*nframes] on the RTL-SDR lattice (b-128)/128, b in 0..255."""
-    key = int(_hash32(np.array([(seed * 0x9E3779B1 + stream * 0x85EBCA77 + 1) & 0xFFFFFFFF],
-                               dtype=np.uint32))[0])
+    key = stream_key(seed, stream)
     idx = (np.arange(2 * start, 2 * (start + nframes), dtype=np.uint64)
            & np.uint64(0xFFFFFFFF)).astype(np.uint32)
     h = _hash32(idx ^ np.uint32(key))
     b = (h >> np.uint32(24)).astype(np.float32)
     return ((b - np.float32(128.0)) / np.float32(128.0)).astype(np.float32)
+
+
+def stream_key(seed, stream):
+    """The per-stream hash key of lattice_noise (shared by the numpy and the torch generator)."""
+    return int(_hash32(np.array([(seed * 0x9E3779B1 + stream * 0x85EBCA77 + 1) & 0xFFFFFFFF],
+                                dtype=np.uint32))[0])
+
+
+def lattice_u8_torch(nframes, streams, start=0, seed=0xB200, device="cuda", chunk_elems=1 << 26):
+    """The bytes behind lattice_noise for several streams at once, generated ON THE DEVICE:
+    uint8 tensor [len(streams), nframes, 2], bit-identical to
+    ((lattice_noise(nframes, seed, s, start) * 128) + 128) for every s in `streams` (bench.py checks a
+    slice against the numpy generator in every run).  int64 arithmetic masked to 32 bits stands in
+    for uint32; the products wrap, which leaves their low 32 bits right."""
+    import torch
+    M = 0xFFFFFFFF
+    T = len(streams)
+    out = torch.empty((T, nframes, 2), dtype=torch.uint8, device=device)
+    idx = ((torch.arange(2 * start, 2 * (start + nframes), dtype=torch.int64, device=device)) & M)
+    per = max(1, chunk_elems // max(1, 2 * nframes))
+
+    def h32(x):
+        x = x ^ (x >> 16)
+        x = (x * 0x7FEB352D) & M
+        x = x ^ (x >> 15)
+        x = (x * 0x846CA68B) & M
+        return x ^ (x >> 16)
+
+    for t0 in range(0, T, per):
+        keys = torch.tensor([stream_key(seed, s) for s in streams[t0:t0 + per]], dtype=torch.int64, device=device)
+        h = h32(idx[None, :] ^ keys[:, None])
+        out[t0:t0 + per] = (h >> 24).to(torch.uint8).view(-1, nframes, 2)
+    return out
+
+
+def u8_to_f32_torch(u8):
+    """RtlSdrTuner's conversion (reference src/io/rtlsdrtuner.cxx:106) on a torch tensor; exact."""
+    import torch
+    return ((u8.to(torch.float32) - 128.0) / 128.0).contiguous()
 
 
 def receiver_ifs(n_rx, fs):
@@ -82,6 +120,13 @@ WORKLOADS = {
     "cfg1": dict(fs=2400000, frames=102400, n_rx=1, n_streams=1, n1=64, d1=10, pb1=80000,
                  n2=64, d2=5, pb2=8000, modes="FM",
                  desc="single FM receiver, 2.4 MSPS -> 240 k -> 48 k, 64/64 taps (reference CPU case)"),
+    # cfg1b: BASELINE configs[0] as written says 2.048 MSPS -> 48 kHz, a ratio of 42.67 that the
+    # reference rejects (dspblock.cxx:126-130); SURVEY.md 8d's integer-legal form of it:
+    # 2.048 M -> /8 -> 256 k (pass-band 100 kHz) -> FM -> /4 -> 64 k (pass-band 15 kHz)
+    "cfg1b": dict(fs=2048000, frames=102400, n_rx=1, n_streams=1, n1=64, d1=8, pb1=100000,
+                  n2=64, d2=4, pb2=15000, modes="FM",
+                  desc="single WBFM receiver, synthetic 2.048 MSPS IQ -> 256 k -> 64 k audio, 64/64 taps "
+                       "(integer-legal form of BASELINE configs[0])"),
     "cfg2": dict(fs=2400000, frames=102400, n_rx=64, n_streams=1, n1=127, d1=50, pb1=12500,
                  n2=64, d2=1, pb2=3000, modes="FM",
                  desc="64 NBFM receivers on one 2.4 MSPS tuner, 127-tap FIR, decim 50"),
