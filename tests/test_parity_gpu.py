@@ -162,7 +162,7 @@ def run_bank_vs_oracle(wro, variant, fs, F, n_streams, ifs, modes, n1, d1, n2, d
             try:
                 audio = bank.process(iq)
             except capi.WrError as e:
-                if variant in (2, 3) and "do not support" in str(e):
+                if (variant in (2, 3) and "do not support" in str(e)) or (variant == 4 and "do not serve" in str(e)):
                     pytest.skip(str(e))
                 raise
             for r in check_rx:
@@ -562,6 +562,46 @@ def test_bank_v3_ragged_block_lengths(wro, geom, F):
     fs = 2400000
     R = 6
     run_bank_vs_oracle(wro, 3, fs, F, 2, synth.receiver_ifs(R, fs), [r % 4 for r in range(R)], n1, d1, n2, d2, 3, seed=11)
+
+
+# ------------------------------------------------------------------ v4: streaming FIR over independent streams ----
+
+@pytest.mark.parametrize("warps_per_rx", [0, 2])
+@pytest.mark.parametrize("F,n1,d1,n2,d2,R", [(25600, 255, 50, 64, 1, 40), (20050, 255, 50, 64, 1, 7), (102400, 255, 50, 64, 1, 5),
+                                             (12800, 127, 50, 64, 1, 9), (16000, 127, 40, 64, 5, 12), (21338, 127, 40, 64, 5, 3)])
+def test_bank_v4_streaming_fir(wro, monkeypatch, F, n1, d1, n2, d2, R, warps_per_rx):
+    """The v4 channel kernel (one thread streams over a run of consecutive outputs, wr_kernels_v4.cuh) on
+    independent streams: every receiver, every stage, three blocks -- so the gather prologue (outputs whose
+    windows reach into the carried history), the runs' overlap, ragged ends (blocks that are not a multiple
+    of the decimation, lanes without outputs) and the epilogue's carried state are all exercised; with one
+    and with two warps per receiver."""
+    if warps_per_rx:
+        monkeypatch.setenv("WR_V4_G", str(warps_per_rx))
+    fs = 2400000
+    run_bank_vs_oracle(wro, 4, fs, F, R, synth.receiver_ifs(R, fs), [r % 4 for r in range(R)], n1, d1, n2, d2, 3, seed=F + R)
+
+
+def test_bank_v4_is_what_cfg3_runs(wro, monkeypatch):
+    """Float blocks of independent streams select v4 on their own; raw bytes and shared tuners stay on v3."""
+    monkeypatch.setenv("WR_SYNC_SPLIT", "1")      # (a block this short would otherwise be cut into pieces too short for v4)
+    w = synth.WORKLOADS["cfg3"]
+    R = 160
+    with capi.Bank(R, R, 25600, w["n1"], w["d1"], w["n2"], w["d2"]) as bank:
+        t1 = synth.windowed_sinc(w["n1"], 0.005)
+        t2 = synth.windowed_sinc(w["n2"], 0.06)
+        for r in range(R):
+            bank.set_taps(r, 0, t1)
+            bank.set_taps(r, 1, t2)
+            bank.set_if(r, 1000 * r - 70000, w["fs"])
+        iq = np.stack([synth.lattice_noise(25600, stream=900 + t) for t in range(R)])
+        audio = bank.process(iq)
+        assert bank.variant_in_use() == 4
+        for r in (0, 1, 77, 159):
+            assert_biteq(audio[r], wro.Rx(w["fs"], 1000 * r - 70000, t1, w["d1"], 0, t2, w["d2"]).process(iq[r]), f"rx{r}")
+        u8 = (iq * 128 + 128).astype(np.uint8)
+        audio8 = bank.process_u8(u8)
+        assert bank.variant_in_use() == 3
+        assert audio8.shape == audio.shape
 
 
 # ------------------------------------------------------------------ BASELINE configs 3 and 5 at FULL size ----

@@ -10,8 +10,8 @@
 
 constexpr int ITER = 256;
 
-enum Op { FADD, FMUL, FFMA, FADD2, FFMA2, IADD3, LOP3, SHF, I2FP, FMNMX, IMAD, IMADHI, LDS16, LDS64, LDS128, MIXAF, NOPS };
-static const char *names[] = { "FADD", "FMUL", "FFMA", "FADD2", "FFMA2", "IADD3", "LOP3", "SHF", "I2FP", "FMNMX", "IMAD", "IMAD.HI", "LDS.S16", "LDS.64", "LDS.128", "IADD3+FFMA" };
+enum Op { FADD, FMUL, FFMA, FADD2, FFMA2, IADD3, LOP3, SHF, I2FP, FMNMX, IMAD, IMADHI, LDS16, LDS64, LDS128, MIXAF, P2P2, P2S1, P2S2, P2I1, S1S1, NOPS };
+static const char *names[] = { "FADD", "FMUL", "FFMA", "FADD2", "FFMA2", "IADD3", "LOP3", "SHF", "I2FP", "FMNMX", "IMAD", "IMAD.HI", "LDS.S16", "LDS.64", "LDS.128", "IADD3+FFMA", "FFMA2+FADD2", "FFMA2+FFMA", "FFMA2+2xFFMA", "FFMA2+IADD3", "FFMA+FADD" };
 
 template <int OP, int CH>
 __device__ __forceinline__ void body(float (&f)[CH], unsigned (&u)[CH], unsigned long long (&p)[CH], float c, unsigned ci, uint32_t sbase)
@@ -34,6 +34,12 @@ __device__ __forceinline__ void body(float (&f)[CH], unsigned (&u)[CH], unsigned
 		if (OP == LDS64) { unsigned a, b; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(sbase + (u[k] & 0xFFF8u))); u[k] += a + b; }
 		if (OP == LDS128) { unsigned a, b, cc, d; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(cc), "=r"(d) : "r"(sbase + (u[k] & 0xFFF0u))); u[k] += a + b + cc + d; }
 		if (OP == MIXAF) { asm volatile("add.u32 %0, %0, %1;" : "+r"(u[k]) : "r"(ci)); asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f[k]) : "f"(c)); }
+		// what binds the channel kernels: packed f32x2 next to packed, scalar and integer work (independent chains)
+		if (OP == P2P2) { asm volatile("fma.rn.f32x2 %0, %0, %0, %0;" : "+l"(p[k])); unsigned long long q = (unsigned long long)u[k] << 32 | __float_as_uint(f[k]); asm volatile("add.rn.f32x2 %0, %0, %0;" : "+l"(q)); u[k] = (unsigned)(q >> 32); f[k] = __uint_as_float((unsigned)q); }
+		if (OP == P2S1) { asm volatile("fma.rn.f32x2 %0, %0, %0, %0;" : "+l"(p[k])); asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f[k]) : "f"(c)); }
+		if (OP == P2S2) { asm volatile("fma.rn.f32x2 %0, %0, %0, %0;" : "+l"(p[k])); asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f[k]) : "f"(c)); float g = __uint_as_float(u[k]); asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(g) : "f"(c)); u[k] = __float_as_uint(g); }
+		if (OP == P2I1) { asm volatile("fma.rn.f32x2 %0, %0, %0, %0;" : "+l"(p[k])); asm volatile("add.u32 %0, %0, %1;" : "+r"(u[k]) : "r"(ci)); }
+		if (OP == S1S1) { asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f[k]) : "f"(c)); float g = __uint_as_float(u[k]); asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(g) : "f"(c)); u[k] = __float_as_uint(g); }
 	}
 }
 
@@ -112,7 +118,7 @@ int run(const char *what, int nwarps, long long *d_out, unsigned *d_sink)
 	CK(cudaMemcpy(h, d_out, sizeof(long long) * nwarps, cudaMemcpyDeviceToHost));
 	long long mx = 0;
 	for (int i = 0; i < nwarps; i++) mx = h[i] > mx ? h[i] : mx;
-	const double ops = (double)ITER * CH * (OP == MIXAF ? 2 : 1);
+	const double ops = (double)ITER * CH * ((OP == MIXAF || OP == P2P2 || OP == P2S1 || OP == P2I1 || OP == S1S1) ? 2 : OP == P2S2 ? 3 : 1);
 	// per SMSP: nwarps/4 warps share one scheduler
 	printf("%-12s %-10s warps=%2d chains=%d  cycles/op/warp=%7.3f  cycles per warp-instr per SMSP=%6.3f\n",
 			names[OP], what, nwarps, CH, mx / ops, mx / (ops * (nwarps >= 4 ? nwarps / 4 : 1)));
@@ -152,6 +158,16 @@ int main()
 	run<LDS64, 8>("tput", 32, d_out, d_sink);
 	run<LDS128, 8>("tput", 32, d_out, d_sink);
 	run<MIXAF, 8>("tput", 32, d_out, d_sink);
+	printf("== packed f32x2 next to other work (per warp-INSTRUCTION; a pair/triple counts 2/3)\n");
+	for (int nw : {32, 16, 8}) {
+		run<FFMA2, 8>("tput", nw, d_out, d_sink);
+		run<FFMA, 8>("tput", nw, d_out, d_sink);
+		run<P2P2, 8>("tput", nw, d_out, d_sink);
+		run<P2S1, 8>("tput", nw, d_out, d_sink);
+		run<P2S2, 8>("tput", nw, d_out, d_sink);
+		run<P2I1, 8>("tput", nw, d_out, d_sink);
+		run<S1S1, 8>("tput", nw, d_out, d_sink);
+	}
 	printf("== scheduler priority: one FADD2-chain warp (2048 dependent ops) vs throughput warps on the same SMSP\n");
 	for (int nwork : {1, 2, 6}) {
 		for (int chainw : {0, nwork - 1}) {

@@ -5,6 +5,7 @@
 #include "wr_kernels_v1.cuh"
 #include "wr_kernels_v2.cuh"
 #include "wr_kernels_v3.cuh"
+#include "wr_kernels_v4.cuh"
 
 #include <cuda.h>        // types of the two stream memory operations; the entry points are looked up at run time
 
@@ -218,6 +219,7 @@ struct wr_bank {
 	int variantInUse = 0;
 	wrd::V2Plan v2;
 	wrd::V3Plan v3;
+	wrd::V4Plan v4;
 	unsigned long long launches = 0;
 	// optional per-launch device timing: a ring of event triples drained into accumulators
 	bool timing = false;
@@ -278,6 +280,7 @@ int apply_pending(wr_bank *b, cudaStream_t st)
 			rc = wrd::v3_set_groups(b->v3, b->h_conf.data(), b->R, st);
 			if (rc != WR_OK)
 				return rc;
+			wrd::v4_set_groups(b->v4, b->h_conf.data(), b->R, b->T);
 			b->streamsDirty = false;
 		}
 	}
@@ -358,7 +361,16 @@ void *device_view(wr_bank *b, const void *host, size_t bytes)
 	return m.dev;
 }
 
-// can this block go through the v3 channel kernel (the one that knows the flag hand-over)?
+// can this block go through the v4 channel kernel (streaming FIR; float blocks of independent streams)?
+bool block_uses_v4(const wr_bank *b, unsigned F, bool u8, const void *iq, size_t stream_stride, wrd::V4Launch *shape)
+{
+	wrd::V4Launch tmp;
+	return (b->variant == 4 || b->variant == 0) && !u8
+			&& wrd::v4_shape(b->v4, b->v3, b->R, F, iq, stream_stride, b->variant == 4, shape ? shape : &tmp);
+}
+
+// can this block go through the v3 channel kernel?  (v3 and v4 know the flag hand-over of the
+// pipelined host path)
 bool block_uses_v3(const wr_bank *b, unsigned F)
 {
 	return (b->variant == 3 || b->variant == 0) && wrd::v3_supported(b->v3, F);
@@ -382,12 +394,19 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 		WR_CUDA(cudaEventRecord(tev[0], st));
 	}
 
-	const bool useV3 = block_uses_v3(b, F);
+	wrd::V4Launch shape4;
+	const bool useV4 = block_uses_v4(b, F, u8, iq_dev, stream_stride, &shape4);
+	if (b->variant == 4 && !useV4) {
+		wr::set_error("v4 kernels do not serve this block (n1=%u d1=%u, %u frames, %s input, up to %u receivers per stream)",
+				b->n1, b->d1, F, u8 ? "u8" : "float", b->v4.maxPerStream);
+		return WR_EINVAL;
+	}
+	const bool useV3 = !useV4 && block_uses_v3(b, F);
 	if (b->variant == 3 && !useV3) {
 		wr::set_error("v3 kernels do not support this geometry (n1=%u d1=%u, %u frames)", b->n1, b->d1, F);
 		return WR_EINVAL;
 	}
-	bool useV2 = useV3 || (b->variant == 2) || (b->variant == 0 && wrd::v2_supported(b->v2));
+	bool useV2 = useV4 || useV3 || (b->variant == 2) || (b->variant == 0 && wrd::v2_supported(b->v2));
 	if (b->variant == 2 && !wrd::v2_supported(b->v2)) {
 		wr::set_error("v2 kernels do not support this geometry (n1=%u d1=%u)", b->n1, b->d1);
 		return WR_EINVAL;
@@ -395,7 +414,7 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 	if (useV2 && !b->d_chan)
 		WR_CUDA(cudaMalloc(&b->d_chan, 2 * sizeof(float2) * (size_t)b->R * std::max(1u, b->maxM1)));
 	float2 *const chanBuf = b->d_chan ? b->d_chan + (size_t)cur * b->R * std::max(1u, b->maxM1) : nullptr;
-	if (u8 && !useV3) {
+	if (u8 && !useV3) {     // (useV4 implies float input)
 		// the older kernel families read float blocks: convert once into a scratch block
 		if (!b->d_iqf)
 			WR_CUDA(cudaMalloc(&b->d_iqf, sizeof(float) * 2 * (size_t)b->T * b->maxF));
@@ -439,7 +458,11 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 	ca.wait_late = b->waitLate;
 	ca.poll_ns = b->pollNs;
 
-	if (useV3) {
+	if (useV4) {
+		rc = wrd::v4_launch_chan(b->v4, b->v3, shape4, ca, b->R, st, &b->launches);
+		if (rc != WR_OK)
+			return rc;
+	} else if (useV3) {
 		rc = wrd::v3_launch_chan(b->v3, ca, u8, st, &b->launches);
 		if (rc != WR_OK)
 			return rc;
@@ -522,7 +545,7 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 			// per sample), so they can afford the persistent grid at several times the size
 			// (cfg3, 9216 items: 291.7 -> 287.1 us)
 			const unsigned long long cap = (b->anyFM ? 10ull : 64ull) * (unsigned)b->numSMs;
-			perSM = (useV3 && b->v3.pdl && fit >= 2 && items <= cap) ? 2 : 0;
+			perSM = (useV3 && b->v3.pdl && fit >= 2 && items <= cap) ? 2 : 0;   // (v4's CTA leaves no room: one CTA per item)
 		}
 		dim3 grid(perSM > 0 ? (unsigned)std::min<unsigned long long>(items, (unsigned long long)perSM * (unsigned)b->numSMs) : (unsigned)items);
 		if (cta_ts && grid.x > kCtaTraceDemod)
@@ -536,7 +559,7 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 		attr[0].val.programmaticStreamSerializationAllowed = 1;
 		cfg.attrs = attr;
-		cfg.numAttrs = (useV3 && b->v3.pdl) ? 1 : 0;   // the v3 channel kernel releases its dependents early
+		cfg.numAttrs = ((useV3 && b->v3.pdl) || (useV4 && b->v4.pdl)) ? 1 : 0;   // the v3/v4 channel kernels release their dependents early
 		WR_CUDA(cudaLaunchKernelEx(&cfg, wrd::demod_audio_kernel_v2<wrd::kDemodThreads>, (const wrd::DemodAudioArgs)da));
 		b->launches++;
 	} else {
@@ -567,7 +590,7 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 		b->tCount++;
 	}
 
-	b->variantInUse = useV3 ? 3 : useV2 ? 2 : 1;
+	b->variantInUse = useV4 ? 4 : useV3 ? 3 : useV2 ? 2 : 1;
 	b->chanSide = cur;
 	b->cur = nxt;
 	b->lastM1 = M1;
@@ -771,7 +794,8 @@ wr_bank *wr_bank_create(int device, unsigned n_streams, unsigned n_receivers, un
 	wr_build_sintable(b->h_table.data());
 	b->tableDirty = true;
 
-	if (wrd::v2_init(b->v2, device, n1, d1) != WR_OK || wrd::v3_init(b->v3, device, n1, d1, max_frames) != WR_OK) {
+	if (wrd::v2_init(b->v2, device, n1, d1) != WR_OK || wrd::v3_init(b->v3, device, n1, d1, max_frames) != WR_OK
+			|| wrd::v4_init(b->v4, b->v3, device, n1, d1) != WR_OK) {
 		free_bank(b);
 		return nullptr;
 	}
@@ -1013,7 +1037,7 @@ static int submit_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframes
 	//        its last CTA raises a counter in mapped host memory that wr_bank_wait polls -- or it
 	//        raises a counter in HBM that the copy-out stream waits for.
 	// Hand-over by events (other kernel families): events between the three streams.
-	const bool v3 = block_uses_v3(b, nframes);
+	const bool v3 = block_uses_v4(b, nframes, u8, s.d_iq, b->maxF, nullptr) || block_uses_v3(b, nframes);
 	int handIn = v3 ? b->handIn : IN_EVENT, handOut = v3 ? b->handOut : OUT_EVENT;
 	float *audio_dev = s.d_audio;
 	size_t audio_dev_stride = maxM2;
@@ -1157,7 +1181,7 @@ static int process_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframe
 	// sub-blocks so that the copy-in of piece k+1 runs under the kernels of piece k and under the
 	// copy-out of piece k-1.  A piece is a whole number of audio frames (and of the channel kernel's
 	// passes' worth of frames, so that it stays on the same kernel family as a full block).
-	unsigned pieces = b->syncSplit;
+	unsigned pieces = b->keepChan ? 1u : b->syncSplit;     // (wr_bank_read_stage reads the last launch: keep it the whole block)
 	const unsigned quantum = b->d1 * b->d2;
 	if (pieces == 0) {
 		// by size: pieces of at least 256 KiB of input (copy latency dominates below that)
@@ -1241,6 +1265,13 @@ static int run_host_steps_any(wr_bank *b, const void *const *iq_pinned, bool u8,
 	WR_REQUIRE(b->inflight == 0, WR_ESTATE, "wr_bank_run_host_steps: blocks already in flight");
 	const int depth = pipelined ? std::min<int>(b->depth, (int)n_audio) : 1;
 	int rc;
+	if (!pipelined) {
+		// strictly one block per call: the synchronous entry point itself (wr_bank_process)
+		for (unsigned i = 0; i < steps; i++)
+			if ((rc = process_any(b, iq_pinned[(first + i) % n_iq], u8, nframes, audio_pinned[(first + i) % n_audio], audio_stride)) != WR_OK)
+				return rc;
+		return WR_OK;
+	}
 	for (unsigned i = 0; i < steps; i++) {
 		if (b->inflight == depth && (rc = wr_bank_wait(b)) != WR_OK)
 			return rc;
@@ -1325,7 +1356,7 @@ int wr_bank_set_audio_format(wr_bank *b, int format)
 
 int wr_bank_set_variant(wr_bank *b, int variant)
 {
-	WR_REQUIRE(b && variant >= 0 && variant <= 3, WR_EINVAL, "wr_bank_set_variant: bad variant %d", variant);
+	WR_REQUIRE(b && variant >= 0 && variant <= 4, WR_EINVAL, "wr_bank_set_variant: bad variant %d", variant);
 	b->variant = variant;
 	return WR_OK;
 }
