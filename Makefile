@@ -12,7 +12,7 @@ NVFLAGS  := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-
 # sample path: every product/sum is an explicit _rn intrinsic; -fmad=false is belt and braces
 PARITY   := -fmad=false
 CSRC     := webradio_b200/csrc
-OBJ      := build/wr_bank.o build/wr_stage.o build/wr_spectrum.o build/wr_host.o
+OBJ      := build/wr_bank.o build/wr_stage.o build/wr_spectrum.o build/wr_upload.o build/wr_host.o
 LIB      := webradio_b200/libwebradio_b200.so
 HARNESS  := tests/harness/libwr_blocks_harness.so
 BLOCKSRC := webradio_b200/dsp/dspblock.cxx webradio_b200/dsp/downconverter.cxx webradio_b200/dsp/lowpass.cxx \
@@ -31,6 +31,9 @@ build/wr_stage.o: $(CSRC)/wr_stage.cu $(wildcard $(CSRC)/*.cuh) $(CSRC)/wr_commo
 build/wr_spectrum.o: $(CSRC)/wr_spectrum.cu $(wildcard $(CSRC)/*.cuh) $(CSRC)/wr_common.h include/webradio_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
+build/wr_upload.o: $(CSRC)/wr_upload.cu $(wildcard $(CSRC)/*.cuh) $(CSRC)/wr_common.h include/webradio_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
 build/wr_host.o: $(CSRC)/wr_host.cpp $(CSRC)/wr_common.h include/webradio_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -Xcompiler -ffp-contract=off -x cu -c $< -o $@
@@ -45,7 +48,7 @@ LIB_EXP  := webradio_b200/libwebradio_b200_exp.so
 lib-exp:
 	@mkdir -p build/exp
 	$(NVCC) $(NVFLAGS) $(PARITY) $(EXPFLAGS) -c $(CSRC)/wr_bank.cu -o build/exp/wr_bank.o
-	$(NVCC) $(ARCH) -shared -o $(LIB_EXP) build/exp/wr_bank.o build/wr_stage.o build/wr_spectrum.o build/wr_host.o -lcudart_static -lpthread -ldl -lrt
+	$(NVCC) $(ARCH) -shared -o $(LIB_EXP) build/exp/wr_bank.o build/wr_stage.o build/wr_spectrum.o build/wr_upload.o build/wr_host.o -lcudart_static -lpthread -ldl -lrt
 
 harness: $(HARNESS)
 $(HARNESS): tests/harness/graph_harness.cxx $(BLOCKSRC) $(wildcard webradio_b200/dsp/*.h webradio_b200/io/*.h) $(LIB)

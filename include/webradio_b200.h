@@ -143,6 +143,40 @@ int wr_rx_set_lookback(wr_bank *b, unsigned rx, const float *prev_iq);
 int wr_bank_process(wr_bank *b, const float *iq_host, unsigned nframes,
 		float *audio_host, size_t audio_stride);
 
+/* ------------------------------------------------ shared tuner-block upload ---- */
+/* One DspBlock::run of a tuner pushes the SAME host buffer to every consumer (the SpectrumSink
+ * first, then each receiver: reference src/dsp/dspblock.cxx:207-209, src/radio.cxx:126-128,151-156).
+ * A wr_upload carries that block to one device ONCE: wr_upload_begin page-locks the caller's buffer
+ * where it lies (first sight only; a DspBlock keeps its output vector from block to block) and
+ * starts asynchronous copies in up to four pieces; the *_process_upload calls of the bank and of
+ * the spectrum sink then read the device copy, each starting as soon as the pieces it needs have
+ * landed.  wr_upload_finish returns once the host buffer is no longer needed -- the producer calls
+ * it before it touches its buffer again (end of DspBlock::run).  One caller thread per handle. */
+typedef struct wr_upload wr_upload;
+wr_upload *wr_upload_create(int device, size_t max_frames);
+void wr_upload_destroy(wr_upload *u);
+size_t wr_upload_capacity(const wr_upload *u);
+int wr_upload_device(const wr_upload *u);
+int wr_upload_begin(wr_upload *u, const float *iq_host, unsigned nframes);   /* [nframes][2] floats */
+int wr_upload_finish(wr_upload *u);
+/* wr_bank_process on the upload's device copy (one stream; same results, same sub-block overlap:
+ * the kernels of a sub-block start when its part of the upload has landed, its audio leaves while
+ * the next one is computed); synchronous -- audio_host is complete on return. */
+int wr_bank_process_upload(wr_bank *b, wr_upload *u, unsigned nframes, float *audio_host, size_t audio_stride);
+/* Page-locked host memory for audio_host and friends (copies to pageable memory are staged by the
+ * driver at a fraction of the link speed). */
+void *wr_host_alloc(size_t bytes);
+void wr_host_free(void *p);
+
+/* The FIR histories of one receiver as of the last completed block -- what LowPass keeps in `block`
+ * between calls (reference lowpass.h:64, lowpass.cxx:133-142): stage 0 = the last n1-1 MIXED frames
+ * (2*(n1-1) floats, interleaved IQ), stage 1 = the last n2-1 demodulated samples.  With
+ * wr_rx_get/set_phase and wr_rx_get/set_lookback this is all the state a receiver carries, so a
+ * host can move it from one bank to another (a bank rebuilt because receivers joined or left a
+ * running front-end) without a glitch.  Call between blocks, from the processing thread. */
+int wr_rx_get_history(wr_bank *b, unsigned rx, int stage, float *out, unsigned nfloats);
+int wr_rx_set_history(wr_bank *b, unsigned rx, int stage, const float *in, unsigned nfloats);
+
 /* Same, with input and output already in HBM on the bank's device; asynchronous on
  * cuda_stream (a cudaStream_t; NULL = the bank's own stream). */
 int wr_bank_process_device(wr_bank *b, const float *iq_dev, size_t stream_stride_frames,
@@ -227,9 +261,10 @@ int wr_bank_set_audio_format(wr_bank *b, int format);
 /* Selects the kernel family: 0 = auto (default: the newest one that supports the geometry and
  * the block length), 1 = v1 generic kernels (NCO table read from L2), 2 = v2 kernels (NCO table
  * resident in shared memory, tile per work item), 3 = v3 kernels (streaming ring of mixed
- * slots, packed NCO arithmetic).  For tests and profiling. */
+ * slots, packed NCO arithmetic), 4 = v4 kernels (streaming FIR, one thread per run of outputs:
+ * float blocks of independent streams).  For tests and profiling. */
 int wr_bank_set_variant(wr_bank *b, int variant);
-/* Which family ran the last block: 1, 2 or 3 (0 before the first block). */
+/* Which family ran the last block: 1 ... 4 (0 before the first block). */
 int wr_bank_variant_in_use(const wr_bank *b);
 /* Kernel launches issued by this bank since creation (for bench.py's gpu_launches). */
 unsigned long long wr_bank_launch_count(const wr_bank *b);
@@ -284,6 +319,13 @@ void wr_spectrum_destroy(wr_spectrum *s);
  * Returns the number of rows completed per stream by this call (>= 0) or a negative error. */
 long wr_spectrum_process(wr_spectrum *s, const float *iq_host, unsigned nframes,
 		float *rows_host, size_t row_stride_floats);
+/* SpectrumSink::process on a shared upload (see wr_upload): asynchronous -- the newest complete
+ * frame is transformed behind the upload on the sink's stream, wr_spectrum_get synchronises.
+ * Returns the rows completed (only the last one is kept). */
+long wr_spectrum_process_upload(wr_spectrum *s, wr_upload *u, unsigned nframes);
+/* Raise max_frames (a tuner whose block length grew) WITHOUT losing the carried partial frame or
+ * the last row, which destroying and re-creating the handle would. */
+int wr_spectrum_reserve(wr_spectrum *s, unsigned max_frames);
 /* Device-resident variant (asynchronous on cuda_stream). */
 long wr_spectrum_process_device(wr_spectrum *s, const float *iq_dev, size_t stream_stride_frames,
 		unsigned nframes, float *rows_dev, size_t row_stride_floats, void *cuda_stream);

@@ -108,6 +108,7 @@ struct wro_fir {
 	float *coeff;
 	float *block;     /* [history | current input], as the reference's `block` vector */
 	size_t block_len; /* floats */
+	float *preset;    /* history handed over by wro_fir_set_history, consumed by the next call (test plumbing) */
 };
 
 wro_fir *wro_fir_create(unsigned channels, const float *coeff, unsigned ntaps, unsigned decim)
@@ -149,7 +150,13 @@ size_t wro_fir_process(wro_fir *f, const float *in, size_t nframes, float *out)
 		f->block_len = want;
 	}
 	/* lowpass.cxx:140-142: keep the last ntaps-1 frames, append the new block */
-	memmove(f->block, f->block + f->block_len - hist, sizeof(float) * hist);
+	if (f->preset) {
+		memcpy(f->block, f->preset, sizeof(float) * hist);
+		free(f->preset);
+		f->preset = NULL;
+	} else {
+		memmove(f->block, f->block + f->block_len - hist, sizeof(float) * hist);
+	}
 	memcpy(f->block + hist, in, sizeof(float) * in_len);
 
 	/* lowpass.cxx:145-159: nout = floor(nframes / decim); taps walked last-to-first
@@ -172,10 +179,34 @@ size_t wro_fir_process(wro_fir *f, const float *in, size_t nframes, float *out)
 	return nout;
 }
 
+/* Test plumbing (no reference counterpart): the history a filter carries -- the last ntaps-1 frames
+ * of `block` (lowpass.cxx:140-142) -- read out, or handed to a filter that has not run yet, so that
+ * the CPU stand-in of the C ABI can move a receiver between banks as the CUDA library does. */
+size_t wro_fir_get_history(const wro_fir *f, float *out)
+{
+	const size_t hist = (size_t)f->channels * (f->ntaps - 1);
+	if (f->preset)
+		memcpy(out, f->preset, sizeof(float) * hist);
+	else if (f->block && f->block_len >= hist)
+		memcpy(out, f->block + f->block_len - hist, sizeof(float) * hist);
+	else
+		memset(out, 0, sizeof(float) * hist);
+	return hist;
+}
+
+void wro_fir_set_history(wro_fir *f, const float *in)
+{
+	const size_t hist = (size_t)f->channels * (f->ntaps - 1);
+	free(f->preset);
+	f->preset = (float*)malloc(sizeof(float) * (hist ? hist : 1));
+	memcpy(f->preset, in, sizeof(float) * hist);
+}
+
 void wro_fir_destroy(wro_fir *f)
 {
 	if (!f)
 		return;
+	free(f->preset);
 	free(f->coeff);
 	free(f->block);
 	free(f);

@@ -44,6 +44,8 @@ wro_fir *wro_fir_create(unsigned channels, const float *coeff, unsigned ntaps, u
 void wro_fir_set_taps(wro_fir *f, const float *coeff, unsigned ntaps);
 /* reference lowpass.cxx:131-162; returns output frames = floor(nframes/decim) */
 size_t wro_fir_process(wro_fir *f, const float *in, size_t nframes, float *out);
+size_t wro_fir_get_history(const wro_fir *f, float *out);
+void wro_fir_set_history(wro_fir *f, const float *in);
 void wro_fir_destroy(wro_fir *f);
 
 /* reference demodulator.cxx:77-115; prev[2] = {prev_i, prev_q} is read and updated */

@@ -17,6 +17,7 @@
  * r * audio_stride; carried state per receiver = NCO phase, both FIR histories, prev I/Q.
  */
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -66,24 +67,41 @@ struct wr_spectrum {
 	unsigned n;
 };
 
+struct wr_upload {
+	int device;
+	size_t maxFrames;
+	std::vector<float> data;   /* the "device copy" */
+	unsigned nframes;
+};
+
 /* counters a test can read to see HOW the blocks drove the library */
-static unsigned long long g_bank_process_calls, g_stage_calls, g_banks_created;
+static unsigned long long g_bank_process_calls, g_stage_calls, g_banks_created, g_uploads, g_upload_frames;
 
 extern "C" {
 
 unsigned long long wr_mock_bank_process_calls(void) { return g_bank_process_calls; }
 unsigned long long wr_mock_stage_calls(void) { return g_stage_calls; }
 unsigned long long wr_mock_banks_created(void) { return g_banks_created; }
-void wr_mock_reset_counters(void) { g_bank_process_calls = g_stage_calls = g_banks_created = 0; }
+unsigned long long wr_mock_uploads(void) { return g_uploads; }
+unsigned long long wr_mock_upload_frames(void) { return g_upload_frames; }
+void wr_mock_reset_counters(void) { g_bank_process_calls = g_stage_calls = g_banks_created = g_uploads = g_upload_frames = 0; }
+/* how many devices the stand-in pretends to have (the blocks spread producers over them) */
+extern "C" void wrhost_set_device_count_for_test(int n);
+static int g_devices = 1;
+void wr_mock_set_devices(int n) { g_devices = n > 0 ? n : 1; wrhost_set_device_count_for_test(n > 1 ? n : 0); }
+static std::vector<int> g_bank_devices;
+int wr_mock_bank_device(unsigned i) { return i < g_bank_devices.size() ? g_bank_devices[i] : -1; }
+void wr_mock_clear_bank_devices(void) { g_bank_devices.clear(); }
 /* failure injection: the next `n` bank / stage compute calls report a CUDA error (WR_ECUDA) */
 static int g_fail_bank, g_fail_stage;
 void wr_mock_fail_next(int bank_calls, int stage_calls) { g_fail_bank = bank_calls; g_fail_stage = stage_calls; }
 
-wr_bank *wr_bank_create(int, unsigned n_streams, unsigned n_receivers, unsigned max_frames,
+wr_bank *wr_bank_create(int device, unsigned n_streams, unsigned n_receivers, unsigned max_frames,
 		unsigned n1, unsigned d1, unsigned n2, unsigned d2)
 {
-	if (!n_streams || !n_receivers || !n1 || !d1 || !n2 || !d2)
+	if (!n_streams || !n_receivers || !n1 || !d1 || !n2 || !d2 || device < 0 || device >= g_devices)
 		return NULL;
+	g_bank_devices.push_back(device);
 	wr_bank *b = new wr_bank();
 	b->T = n_streams; b->R = n_receivers; b->maxF = max_frames;
 	b->n1 = n1; b->d1 = d1; b->n2 = n2; b->d2 = d2;
@@ -216,6 +234,61 @@ int wr_bank_process(wr_bank *b, const float *iq_host, unsigned nframes, float *a
 	return WR_OK;
 }
 
+int wr_rx_get_history(wr_bank *b, unsigned rx, int stage, float *out, unsigned nfloats)
+{
+	if (!b || rx >= b->R || !out || nfloats != (stage ? b->n2 - 1 : 2 * (b->n1 - 1)))
+		return WR_EINVAL;
+	wro_fir_get_history(stage ? b->rx[rx].fir2 : b->rx[rx].fir1, out);
+	return WR_OK;
+}
+
+int wr_rx_set_history(wr_bank *b, unsigned rx, int stage, const float *in, unsigned nfloats)
+{
+	if (!b || rx >= b->R || !in || nfloats != (stage ? b->n2 - 1 : 2 * (b->n1 - 1)))
+		return WR_EINVAL;
+	wro_fir_set_history(stage ? b->rx[rx].fir2 : b->rx[rx].fir1, in);
+	return WR_OK;
+}
+
+/* the shared upload: a host copy stands in for the device copy */
+wr_upload *wr_upload_create(int device, size_t max_frames)
+{
+	if (!max_frames || device < 0 || device >= g_devices)
+		return NULL;
+	wr_upload *u = new wr_upload();
+	u->device = device;
+	u->maxFrames = max_frames;
+	u->nframes = 0;
+	return u;
+}
+
+void wr_upload_destroy(wr_upload *u) { delete u; }
+size_t wr_upload_capacity(const wr_upload *u) { return u ? u->maxFrames : 0; }
+int wr_upload_device(const wr_upload *u) { return u ? u->device : -1; }
+
+int wr_upload_begin(wr_upload *u, const float *iq_host, unsigned nframes)
+{
+	if (!u || (!iq_host && nframes) || nframes > u->maxFrames)
+		return WR_EINVAL;
+	g_uploads++;
+	g_upload_frames += nframes;
+	u->data.assign(iq_host, iq_host + 2 * (size_t)nframes);
+	u->nframes = nframes;
+	return WR_OK;
+}
+
+int wr_upload_finish(wr_upload *u) { return u ? WR_OK : WR_EINVAL; }
+
+int wr_bank_process_upload(wr_bank *b, wr_upload *u, unsigned nframes, float *audio_host, size_t audio_stride)
+{
+	if (!b || !u || b->T != 1 || nframes != u->nframes)
+		return WR_EINVAL;
+	return wr_bank_process(b, u->data.data(), nframes, audio_host, audio_stride);
+}
+
+void *wr_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void wr_host_free(void *p) { free(p); }
+
 wr_stage *wr_stage_create(int)
 {
 	wr_stage *s = new wr_stage();
@@ -328,6 +401,15 @@ long wr_spectrum_process(wr_spectrum *s, const float *iq_host, unsigned nframes,
 		return WR_EINVAL;
 	return (long)wro_spectrum_process(s->s, iq_host, nframes, rows_host, rows_host ? (size_t)nframes / s->n + 2 : 0);
 }
+
+long wr_spectrum_process_upload(wr_spectrum *s, wr_upload *u, unsigned nframes)
+{
+	if (!s || !u || nframes != u->nframes)
+		return WR_EINVAL;
+	return (long)wro_spectrum_process(s->s, u->data.data(), nframes, NULL, 0);
+}
+
+int wr_spectrum_reserve(wr_spectrum *s, unsigned max_frames) { return (s && max_frames) ? WR_OK : WR_EINVAL; }
 
 int wr_spectrum_get(wr_spectrum *s, unsigned stream, float *db_host)
 {

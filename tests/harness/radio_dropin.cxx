@@ -16,6 +16,7 @@
 #include <fcntl.h>
 
 #include "radio.h"
+#include "gpubank.h"
 
 namespace {
 
@@ -138,6 +139,25 @@ int wrr_run_steps(void *h, const float *const *iq, unsigned n_iq, unsigned first
 		Radio::run();
 	}
 	return 0;
+}
+
+/* Several front-ends at once, as Radio::run() sees them: every rig's tuner is handed its block, then
+ * ONE Radio::run() visits all front-ends in turn (radio.cxx:56-59). */
+int wrr_run_many(void *const *h, unsigned n, const float *const *iq)
+{
+	for (unsigned i = 0; i < n; i++) {
+		Rig *r = (Rig*)h[i];
+		r->tuner->feed(iq[i], (size_t)r->frames * 2);
+	}
+	Radio::run();
+	return 0;
+}
+
+/* the CUDA device the drop-in blocks placed this front-end on (wrhost::deviceFor) */
+int wrr_device(void *h)
+{
+	Rig *r = (Rig*)h;
+	return wrhost::deviceFor(r->tuner);
 }
 
 /* what a web handler would do (receiverhandler.cxx:125-140) */

@@ -198,3 +198,75 @@ def test_reference_radio_glue_runs_on_the_dropin_blocks():
     finally:
         L.wrr_destroy(rig)
         ref.close()
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN), reason="libwr_radio_dropin.so not built (needs the reference tree)")
+def test_sixteen_front_ends_are_sharded_by_tuner_over_the_gpus():
+    """north_star: receivers shard across the GPUs of one box by assignment, behind the UNCHANGED glue.
+    Sixteen FrontEnds (reference src/radio.cxx:120-156), two receivers each, one Radio::run() per block:
+    every front-end's bank, spectrum sink and tuner-block upload live on the device the front-end was
+    dealt (round-robin over the visible GPUs), audio bit-exact against sixteen reference graphs, spectra
+    within the transform tolerance.  On a single-GPU box everything lands on device 0 and the same
+    checks run."""
+    import torch
+    fp = C.POINTER(C.c_float)
+    L = C.CDLL(DROPIN, mode=C.RTLD_LOCAL)
+    L.wrr_create.restype = C.c_void_p
+    L.wrr_create.argtypes = [C.c_uint, C.c_uint, C.c_uint]
+    L.wrr_add_receiver.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    L.wrr_start.argtypes = [C.c_void_p]
+    L.wrr_run_many.argtypes = [C.POINTER(C.c_void_p), C.c_uint, C.POINTER(C.c_void_p)]
+    L.wrr_audio.restype = C.c_long
+    L.wrr_audio.argtypes = [C.c_void_p, C.c_int, fp, C.c_long]
+    L.wrr_spectrum.argtypes = [C.c_void_p, fp]
+    L.wrr_device.argtypes = [C.c_void_p]
+    L.wrr_destroy.argtypes = [C.c_void_p]
+    frames, nfe = 20480, 16
+    modes = ["FM", "AM"]
+    rigs, refs = [], []
+    try:
+        for t in range(nfe):
+            rig = L.wrr_create(FS, frames, 512)
+            ref = G.Graph("ref", FS, frames)
+            ref.add_spectrum(512)
+            for i, m in enumerate(modes):
+                f = 30000 * t - 200000 + 7777 * i
+                assert L.wrr_add_receiver(rig, f, m.encode()) >= 0
+                ref.add_receiver(if_hz=f, mode=m, capture=0x8)
+            assert L.wrr_start(rig) == 0 and ref.start()
+            rigs.append(rig)
+            refs.append(ref)
+        handles = (C.c_void_p * nfe)(*rigs)
+        for b in range(3):
+            blocks = [synth.structured(frames, FS, [30000 * t - 200000, 30000 * t - 200000 + 7777], [1, 0],
+                                       start=b * frames, stream=t, fm_dev=50000.0) for t in range(nfe)]
+            ptrs = (C.c_void_p * nfe)(*[x.ctypes.data for x in blocks])
+            assert L.wrr_run_many(handles, nfe, ptrs) == 0
+            for t in range(nfe):
+                assert refs[t].run(blocks[t])
+                for i, m in enumerate(modes):
+                    n = L.wrr_audio(rigs[t], i, None, 0)
+                    got = np.empty(n, np.float32)
+                    L.wrr_audio(rigs[t], i, got.ctypes.data_as(fp), n)
+                    want = refs[t].get(i, "audio")
+                    if m == "FM":
+                        assert_fm(got, want, f"front-end {t} rx{i} block {b}", audio=True)
+                    else:
+                        assert_biteq(got, want, f"front-end {t} rx{i} block {b}")
+                db = np.empty(512, np.float32)
+                assert L.wrr_spectrum(rigs[t], db.ctypes.data_as(fp)) == 512
+                want = refs[t].spectrum(512).astype(np.float64)
+                ma, mw = 10 ** (db.astype(np.float64) / 20), 10 ** (want / 20)
+                assert np.max(np.abs(ma - mw)) <= 1e-5 * mw.max(), f"front-end {t} spectrum block {b}"
+        ndev = min(torch.cuda.device_count(), int(os.environ.get("WEBRADIO_B200_DEVICES", "64")))
+        if "WEBRADIO_B200_DEVICE" in os.environ:
+            ndev = 1
+        devs = [L.wrr_device(r) for r in rigs]
+        assert len(set(devs)) == min(ndev, nfe), devs
+        # round-robin: consecutive front-ends sit on consecutive devices
+        assert all((devs[i + 1] - devs[i]) % ndev == 1 % ndev for i in range(nfe - 1)), devs
+    finally:
+        for r in rigs:
+            L.wrr_destroy(r)
+        for r in refs:
+            r.close()

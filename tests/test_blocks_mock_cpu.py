@@ -28,8 +28,11 @@ FS, F = 2400000, 20000
 
 def counters():
     lib = G.load("mock")
-    for f in ("wr_mock_bank_process_calls", "wr_mock_stage_calls", "wr_mock_banks_created"):
+    for f in ("wr_mock_bank_process_calls", "wr_mock_stage_calls", "wr_mock_banks_created", "wr_mock_uploads",
+              "wr_mock_upload_frames"):
         getattr(lib, f).restype = C.c_ulonglong
+    lib.wr_mock_set_devices.argtypes = [C.c_int]
+    lib.wr_mock_bank_device.argtypes = [C.c_uint]
     return lib
 
 
@@ -214,6 +217,65 @@ def test_spectrum_sink_block():
         g.close(); r.close()
 
 
+def test_one_upload_per_tuner_block_shared_by_sink_and_banks():
+    """The tuner block goes to the device ONCE per DspBlock::run of the tuner, whoever asks first: the
+    SpectrumSink (connected first, as FrontEnd does, radio.cxx:126-128), two banks of different
+    geometry and nobody else (strict chains take the host buffer)."""
+    lib = counters()
+    lib.wr_mock_reset_counters()
+    g, r = G.Graph("mock", FS, F), G.Graph("ref", FS, F)
+    try:
+        for x in (g, r):
+            x.add_spectrum(512)
+            for i in range(5):
+                x.add_receiver(if_hz=10000 * i, mode="FM", capture=0x8)
+            x.add_receiver(if_hz=-5, mode="AM", capture=0x8, ch_rate=0, ch_decim=50, au_rate=0, au_decim=1)
+            assert x.start()
+        for b in range(4):
+            iq = synth.lattice_noise(F, stream=9, start=b * F)
+            assert g.run(iq) and r.run(iq)
+            for i in range(6):
+                assert_biteq(g.get(i, "audio"), r.get(i, "audio"), f"rx{i} block {b}")
+            assert_biteq(g.spectrum(512), r.spectrum(512), f"spectrum block {b}")
+        assert lib.wr_mock_uploads() == 4 and lib.wr_mock_upload_frames() == 4 * F
+        assert lib.wr_mock_banks_created() == 2 and lib.wr_mock_bank_process_calls() == 8
+    finally:
+        g.close(); r.close()
+
+
+def test_front_ends_are_dealt_over_the_devices():
+    """Shard by tuner behind the unchanged glue: every producer (front-end) gets a device round-robin at
+    first sight and its bank, its sink and its upload live there; results do not depend
+    on the placement."""
+    lib = counters()
+    lib.wr_mock_reset_counters()
+    lib.wr_mock_clear_bank_devices()
+    lib.wr_mock_set_devices(4)
+    gs = []
+    try:
+        for t in range(6):
+            pairg = [G.Graph(w, FS, F) for w in ("mock", "ref")]
+            for x in pairg:
+                x.add_spectrum(512)
+                for i in range(3):
+                    x.add_receiver(if_hz=1000 * (i + 7 * t), mode=["AM", "FM", "USB"][i], capture=0x8)
+                assert x.start()
+            gs.append(pairg)
+        for b in range(3):
+            for t, (g, r) in enumerate(gs):
+                iq = synth.lattice_noise(F, stream=40 + t, start=b * F)
+                assert g.run(iq) and r.run(iq)
+                for i in range(3):
+                    assert_biteq(g.get(i, "audio"), r.get(i, "audio"), f"front-end {t} rx{i} block {b}")
+                assert_biteq(g.spectrum(512), r.spectrum(512), f"front-end {t} spectrum block {b}")
+        assert lib.wr_mock_banks_created() == 6
+        assert [lib.wr_mock_bank_device(i) for i in range(6)] == [0, 1, 2, 3, 0, 1]
+    finally:
+        for g, r in gs:
+            g.close(); r.close()
+        lib.wr_mock_set_devices(1)
+
+
 def test_profile_counters_count_frames():
     """DSPBLOCK_PROFILE bookkeeping (dspblock.cxx:186-204): every block of a fused chain still counts
     the frames it was handed, exactly as the reference's blocks do."""
@@ -236,10 +298,12 @@ def test_hot_detach_and_reattach(capture):
     lib.wr_mock_reset_counters()
     LC.hot_reattach("mock", capture)
     if capture == 0x8:
-        # fused throughout; each re-attached chain got a bank of its own
+        # fused throughout, and ONE batched call per block however the chains came and went: the
+        # bank of the front-end is rebuilt (state carried) whenever its membership changes
         assert lib.wr_mock_stage_calls() == 0
-        # ... and the restart at the end ONE more, shared by all three
-        assert lib.wr_mock_banks_created() == 4
+        assert lib.wr_mock_bank_process_calls() == 11
+        # start, rx1 leaves, rx1 back, rx0 + rx2 leave, rx2 back, restart with all three
+        assert lib.wr_mock_banks_created() == 6
 
 
 def test_lookback_travels_between_strict_and_fused():

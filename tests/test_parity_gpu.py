@@ -604,6 +604,105 @@ def test_bank_v4_is_what_cfg3_runs(wro, monkeypatch):
         assert audio8.shape == audio.shape
 
 
+# ------------------------------------------------------------------ shared upload, state hand-over ----
+
+@pytest.mark.parametrize("F,n1,d1,n2,d2", [(102400, 64, 10, 64, 5), (102400, 127, 50, 64, 1), (7000, 64, 10, 64, 5)])
+def test_bank_and_spectrum_share_one_upload(wro, F, n1, d1, n2, d2):
+    """wr_upload: the tuner block goes to the device once (page-locked where it lies, in pieces) and the
+    receiver bank and the spectrum sink both read that copy -- same audio as wr_bank_process, same
+    spectrum as wr_spectrum_process, block after block (state, the sink's partial frame, the buffer the
+    upload alternates between)."""
+    fs, R, N = 2400000, 5, 4096
+    rng = np.random.default_rng(F + n1)
+    taps1 = [(rng.uniform(-1, 1, n1) / n1 * 4).astype(np.float32) for _ in range(R)]
+    taps2 = [(rng.uniform(-1, 1, n2) / n2 * 4).astype(np.float32) for _ in range(R)]
+    ifs = synth.receiver_ifs(R, fs)
+    banks = [capi.Bank(1, R, F, n1, d1, n2, d2) for _ in range(2)]
+    sps = [capi.Spectrum(N, N, 1, max_frames=F) for _ in range(2)]
+    up = capi.Upload(F)
+    try:
+        for b in banks:
+            for r in range(R):
+                b.set_taps(r, 0, taps1[r])
+                b.set_taps(r, 1, taps2[r])
+                b.set_if(r, int(ifs[r]), fs)
+                b.set_mode(r, r % 4)
+        for blk in range(4):
+            nf = F if blk != 2 else F - 3 * d1 * d2      # a shorter block in between
+            iq = synth.structured(nf, fs, ifs[:3], [0, 1, 2], start=blk * F, stream=blk)
+            assert up.begin(iq) == nf
+            n_up = sps[0].process_upload(up, nf)         # the sink first, as FrontEnd connects it
+            got = banks[0].process_upload(up, nf)
+            up.finish()
+            want = banks[1].process(iq)
+            n_ref = sps[1].process(iq.reshape(1, nf, 2), rows=False)
+            assert n_up == n_ref
+            assert_biteq(got, want, f"audio through the shared upload, block {blk}")
+            assert_biteq(sps[0].get(0), sps[1].get(0), f"spectrum through the shared upload, block {blk}")
+    finally:
+        for x in banks + sps + [up]:
+            x.close()
+
+
+@pytest.mark.parametrize("n1,d1,n2,d2", [(64, 10, 64, 5), (127, 50, 64, 1), (255, 50, 64, 1)])
+def test_receiver_state_moves_between_banks(wro, n1, d1, n2, d2):
+    """wr_rx_get/set_history (+ phase and look-back sample): a receiver taken out of one bank after two
+    blocks and put into a bank of another size continues without a glitch -- what the drop-in blocks
+    do when receivers join or leave a running front-end."""
+    fs, F = 2400000, 20000
+    rng = np.random.default_rng(n1 + d1)
+    t1 = (rng.uniform(-1, 1, n1) / n1 * 4).astype(np.float32)
+    t2 = (rng.uniform(-1, 1, n2) / n2 * 4).astype(np.float32)
+
+    def conf(b, r, f, m):
+        b.set_taps(r, 0, t1)
+        b.set_taps(r, 1, t2)
+        b.set_if(r, f, fs)
+        b.set_mode(r, m)
+
+    cont = capi.Bank(1, 1, F, n1, d1, n2, d2)
+    first = capi.Bank(1, 1, F, n1, d1, n2, d2)
+    second = capi.Bank(1, 3, F, n1, d1, n2, d2)
+    try:
+        conf(cont, 0, 123456, capi.FM)
+        conf(first, 0, 123456, capi.FM)
+        for r, (f, m) in enumerate([(-5000, capi.AM), (123456, capi.FM), (99, capi.USB)]):
+            conf(second, r, f, m)
+        blocks = [synth.structured(F, fs, [123456], [1], start=b * F, fm_dev=40000.0) for b in range(4)]
+        want = [cont.process(x)[0] for x in blocks]
+        for b in range(2):
+            assert_biteq(first.process(blocks[b])[0], want[b], f"block {b}")
+        second.set_phase(1, first.get_phase(0))
+        second.set_lookback(1, first.get_lookback(0))
+        for stage in (0, 1):
+            h = first.get_history(0, stage)
+            assert h.size == ((n2 - 1) if stage else 2 * (n1 - 1))
+            second.set_history(1, stage, h)
+        for b in range(2, 4):
+            assert_biteq(second.process(blocks[b])[1], want[b], f"block {b} in the second bank")
+    finally:
+        for x in (cont, first, second):
+            x.close()
+
+
+def test_spectrum_reserve_keeps_the_partial_frame(wro):
+    """A tuner block longer than the sink was sized for (SpectrumSink used to destroy and re-create its
+    handle, losing the partial frame -- the reference's inoffset, spectrumsink.h:62): wr_spectrum_reserve."""
+    N = 4096
+    sp = capi.Spectrum(N, N, 1, max_frames=3000)
+    osp = wro.Spectrum(N)
+    try:
+        x = synth.structured(3000 + 6000, 2400000, [300000], [0])
+        sp.process(x[:6000].reshape(1, 3000, 2), rows=False)
+        osp.process(x[:6000], rows=False)
+        sp.reserve(6000)
+        sp.process(x[6000:].reshape(1, 6000, 2), rows=False)
+        osp.process(x[6000:], rows=False)
+        spectrum_close(sp.get(0), osp.get(), "row that straddles the two blocks")
+    finally:
+        sp.close()
+
+
 # ------------------------------------------------------------------ BASELINE configs 3 and 5 at FULL size ----
 
 def _full_size_bank(w, taps_seed):

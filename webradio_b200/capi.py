@@ -36,6 +36,9 @@ SYMBOLS = [
     "wr_stage_fir_reset", "wr_stage_demod", "wr_stage_atan2f", "wr_stage_palette",
     "wr_spectrum_create", "wr_spectrum_destroy", "wr_spectrum_process", "wr_spectrum_process_device",
     "wr_spectrum_get", "wr_spectrum_get_palette", "wr_spectrum_launch_count", "wr_spectrum_sync",
+    "wr_upload_create", "wr_upload_destroy", "wr_upload_capacity", "wr_upload_device", "wr_upload_begin", "wr_upload_finish",
+    "wr_bank_process_upload", "wr_spectrum_process_upload", "wr_spectrum_reserve", "wr_host_alloc", "wr_host_free",
+    "wr_rx_get_history", "wr_rx_set_history",
 ]
 
 _lib = None
@@ -128,6 +131,23 @@ def lib():
     L.wr_spectrum_launch_count.restype = C.c_ulonglong
     L.wr_spectrum_launch_count.argtypes = [vp]
     L.wr_spectrum_sync.argtypes = [vp]
+    L.wr_upload_create.restype = vp
+    L.wr_upload_create.argtypes = [i, sz]
+    L.wr_upload_destroy.argtypes = [vp]
+    L.wr_upload_capacity.restype = sz
+    L.wr_upload_capacity.argtypes = [vp]
+    L.wr_upload_device.argtypes = [vp]
+    L.wr_upload_begin.argtypes = [vp, vp, u]
+    L.wr_upload_finish.argtypes = [vp]
+    L.wr_bank_process_upload.argtypes = [vp, vp, u, vp, sz]
+    L.wr_spectrum_process_upload.restype = C.c_long
+    L.wr_spectrum_process_upload.argtypes = [vp, vp, u]
+    L.wr_spectrum_reserve.argtypes = [vp, u]
+    L.wr_host_alloc.restype = vp
+    L.wr_host_alloc.argtypes = [sz]
+    L.wr_host_free.argtypes = [vp]
+    L.wr_rx_get_history.argtypes = [vp, u, i, _fp, u]
+    L.wr_rx_set_history.argtypes = [vp, u, i, _fp, u]
     _lib = L
     return L
 
@@ -235,6 +255,23 @@ class Bank:
         """The FM discriminator's look-back sample (prev_i, prev_q); applies at the next block."""
         v = (C.c_float * 2)(float(prev_iq[0]), float(prev_iq[1]))
         _check(self.L.wr_rx_set_lookback(self.h, rx, v), "wr_rx_set_lookback")
+
+    def get_history(self, rx, stage):
+        """The FIR history a receiver carries: stage 0 the last n1-1 mixed IQ frames, stage 1 the last n2-1 demodulated samples."""
+        n = (self.n2 - 1) if stage else 2 * (self.n1 - 1)
+        out = np.empty(max(n, 1), np.float32)
+        _check(self.L.wr_rx_get_history(self.h, rx, stage, out.ctypes.data_as(_fp), n), "wr_rx_get_history")
+        return out[:n]
+
+    def set_history(self, rx, stage, hist):
+        a, p = _f32(hist)
+        _check(self.L.wr_rx_set_history(self.h, rx, stage, p, a.size), "wr_rx_set_history")
+
+    def process_upload(self, upload, nframes):
+        m2 = self.out_frames(nframes)
+        out = np.zeros((self.R, max(m2, 1)), np.float32)
+        _check(self.L.wr_bank_process_upload(self.h, upload.h, nframes, out.ctypes.data, out.shape[1]), "wr_bank_process_upload")
+        return out[:, :m2]
 
     def get_lookback(self, rx):
         v = (C.c_float * 2)()
@@ -414,6 +451,33 @@ def atan2f_host(y, x):
     return out
 
 
+class Upload:
+    """One tuner block carried to the device once and shared by a bank and a spectrum sink."""
+
+    def __init__(self, max_frames, device=0):
+        self.L = lib()
+        self.h = self.L.wr_upload_create(device, max_frames)
+        if not self.h:
+            raise WrError("wr_upload_create failed: " + last_error())
+        self.keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.wr_upload_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def begin(self, iq):
+        a, _ = _f32(iq)
+        self.keep = a            # the host buffer must outlive the copies
+        _check(self.L.wr_upload_begin(self.h, a.ctypes.data, a.size // 2), "wr_upload_begin")
+        return a.size // 2
+
+    def finish(self):
+        _check(self.L.wr_upload_finish(self.h), "wr_upload_finish")
+
+
 class Spectrum:
     def __init__(self, fft_size, hop=None, n_streams=1, max_frames=None, device=0):
         self.L = lib()
@@ -444,6 +508,13 @@ class Spectrum:
     def process_device(self, iq_ptr, stride, nframes, rows_ptr, row_stride, cuda_stream=None):
         return _check(self.L.wr_spectrum_process_device(self.h, iq_ptr, stride, nframes, rows_ptr, row_stride,
                                                         cuda_stream), "wr_spectrum_process_device")
+
+    def process_upload(self, upload, nframes):
+        return _check(self.L.wr_spectrum_process_upload(self.h, upload.h, nframes), "wr_spectrum_process_upload")
+
+    def reserve(self, max_frames):
+        _check(self.L.wr_spectrum_reserve(self.h, max_frames), "wr_spectrum_reserve")
+        self.max_frames = max(self.max_frames, max_frames)
 
     def get(self, stream=0):
         out = np.empty(self.N, np.float32)

@@ -6,6 +6,7 @@
 #include "wr_kernels_v2.cuh"
 #include "wr_kernels_v3.cuh"
 #include "wr_kernels_v4.cuh"
+#include "wr_upload.cuh"
 
 #include <cuda.h>        // types of the two stream memory operations; the entry points are looked up at run time
 
@@ -1006,22 +1007,24 @@ int wr_bank_process_device_u8(wr_bank *b, const uint8_t *iq_dev, size_t stream_s
 // taken from a host block whose rows (streams) lie `host_pitch` frames apart.  wr_bank_submit hands
 // over whole blocks (host_pitch = nframes); wr_bank_process cuts one block into consecutive
 // sub-blocks, which the carried state turns into exactly the same samples.
+// `iq_dev` != nullptr: the frames are (or will be, once `dev_ready` has fired) in HBM already --
+// the shared upload of wr_bank_process_upload; nothing is copied in.
 static int submit_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframes, float *audio_host, size_t audio_stride,
-		size_t host_pitch = 0)
+		size_t host_pitch = 0, const float *iq_dev = nullptr, cudaEvent_t dev_ready = nullptr)
 {
 	if (host_pitch == 0)
 		host_pitch = nframes;
-	WR_REQUIRE(b && iq_host && audio_host, WR_EINVAL, "wr_bank_submit: null argument");
+	WR_REQUIRE(b && (iq_host || iq_dev) && audio_host, WR_EINVAL, "wr_bank_submit: null argument");
 	WR_REQUIRE(nframes <= b->maxF, WR_EINVAL, "wr_bank_submit: %u frames > max_frames %u", nframes, b->maxF);
 	WR_REQUIRE(b->inflight < b->depth, WR_ESTATE, "wr_bank_submit: %d blocks already in flight", b->inflight);
 	if (!wr::use_device(b->device))
 		return WR_ENODEV;
 	const unsigned long long t_enter = b->d_ts ? host_ns() : 0;
 	Slot &s = b->slot[b->head];
-	if (!s.d_iq) {
+	if (!s.d_iq && !iq_dev)
 		WR_CUDA(cudaMalloc(&s.d_iq, sizeof(float) * 2 * (size_t)b->T * b->maxF));
+	if (!s.d_audio)
 		WR_CUDA(cudaMalloc(&s.d_audio, sizeof(float) * (size_t)b->R * std::max(1u, b->maxM2)));
-	}
 	const unsigned M2 = nframes / b->d1 / b->d2;
 	const unsigned maxM2 = std::max(1u, b->maxM2);
 	const size_t fb = u8 ? 2 : sizeof(float) * 2;   // bytes per frame on the wire and in HBM
@@ -1037,8 +1040,8 @@ static int submit_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframes
 	//        its last CTA raises a counter in mapped host memory that wr_bank_wait polls -- or it
 	//        raises a counter in HBM that the copy-out stream waits for.
 	// Hand-over by events (other kernel families): events between the three streams.
-	const bool v3 = block_uses_v4(b, nframes, u8, s.d_iq, b->maxF, nullptr) || block_uses_v3(b, nframes);
-	int handIn = v3 ? b->handIn : IN_EVENT, handOut = v3 ? b->handOut : OUT_EVENT;
+	const bool v3 = block_uses_v4(b, nframes, u8, iq_dev ? (const void*)iq_dev : (const void*)s.d_iq, b->maxF, nullptr) || block_uses_v3(b, nframes);
+	int handIn = (v3 && !iq_dev) ? b->handIn : IN_EVENT, handOut = v3 ? b->handOut : OUT_EVENT;
 	float *audio_dev = s.d_audio;
 	size_t audio_dev_stride = maxM2;
 	if (handOut == OUT_DIRECT) {
@@ -1051,12 +1054,17 @@ static int submit_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframes
 		}
 	}
 	const unsigned seq = ++b->seq;
-	if (b->T == 1 || (nframes == b->maxF && host_pitch == nframes))
+	if (iq_dev) {
+		if (dev_ready)
+			WR_CUDA(cudaStreamWaitEvent(b->compute, dev_ready, 0));
+	} else if (b->T == 1 || (nframes == b->maxF && host_pitch == nframes))
 		WR_CUDA(cudaMemcpyAsync(s.d_iq, iq_host, fb * (size_t)nframes * b->T, cudaMemcpyHostToDevice, b->h2d));
 	else
 		WR_CUDA(cudaMemcpy2DAsync(s.d_iq, fb * (size_t)b->maxF, iq_host, fb * host_pitch,
 				fb * (size_t)nframes, b->T, cudaMemcpyHostToDevice, b->h2d));
-	if (handIn == IN_FLAG) {
+	if (iq_dev) {
+		// (ordered by the event above)
+	} else if (handIn == IN_FLAG) {
 		if (stream_ops().write((CUstream)b->h2d, (CUdeviceptr)(uintptr_t)(b->d_sync + 0), seq, 0) != CUDA_SUCCESS) {
 			wr::set_error("wr_bank_submit: cuStreamWriteValue32 failed");
 			return WR_ECUDA;
@@ -1069,7 +1077,8 @@ static int submit_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframes
 		WR_CUDA(cudaEventRecord(s.in_ready, b->h2d));
 		WR_CUDA(cudaStreamWaitEvent(b->compute, s.in_ready, 0));
 	}
-	int rc = launch_block(b, s.d_iq, u8, b->maxF, nframes, audio_dev, audio_dev_stride, b->compute, seq, handIn, handOut);
+	int rc = launch_block(b, iq_dev ? (const void*)iq_dev : (const void*)s.d_iq, u8, b->maxF, nframes, audio_dev, audio_dev_stride,
+			b->compute, seq, handIn, handOut);
 	if (rc != WR_OK)
 		return rc;
 	if (handOut != OUT_DIRECT) {
@@ -1220,6 +1229,82 @@ static int process_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframe
 int wr_bank_process(wr_bank *b, const float *iq_host, unsigned nframes, float *audio_host, size_t audio_stride)
 {
 	return process_any(b, iq_host, false, nframes, audio_host, audio_stride);
+}
+
+int wr_bank_process_upload(wr_bank *b, wr_upload *u, unsigned nframes, float *audio_host, size_t audio_stride)
+{
+	WR_REQUIRE(b && u && audio_host, WR_EINVAL, "wr_bank_process_upload: null argument");
+	WR_REQUIRE(b->T == 1, WR_EINVAL, "wr_bank_process_upload: the bank has %u streams, an upload carries one", b->T);
+	WR_REQUIRE(u->device == b->device, WR_EINVAL, "wr_bank_process_upload: upload on device %d, bank on %d", u->device, b->device);
+	WR_REQUIRE(nframes == u->nframes && nframes <= b->maxF, WR_EINVAL, "wr_bank_process_upload: %u frames asked, %u uploaded, bank holds %u",
+			nframes, u->nframes, b->maxF);
+	WR_REQUIRE(b->inflight == 0, WR_ESTATE, "wr_bank_process_upload: pipelined blocks still in flight");
+	if (!wr::use_device(b->device))
+		return WR_ENODEV;
+	// the bank's own sub-blocks (whole audio frames), each started as soon as the upload's piece
+	// that completes it has landed; the audio of one leaves while the next is computed
+	const unsigned quantum = b->d1 * b->d2;
+	unsigned pieces = b->keepChan ? 1u : std::min<unsigned>(u->npieces ? u->npieces : 1u, (unsigned)b->depth);
+	unsigned per = nframes / std::max(1u, pieces);
+	per -= per % quantum;
+	const unsigned minPiece = std::max(quantum, b->v3.ok ? b->v3.SF : 0u);
+	if (pieces <= 1 || per < minPiece) {
+		pieces = 1;
+		per = nframes;
+	}
+	int rc = WR_OK;
+	unsigned done = 0, submitted = 0;
+	for (unsigned k = 0; k < pieces && rc == WR_OK; k++) {
+		const unsigned nf = (k + 1 == pieces) ? nframes - done : per;
+		rc = submit_any(b, nullptr, false, nf, audio_host + done / quantum, audio_stride, nframes,
+				u->dev() + 2 * (size_t)done, u->ready(done + nf));
+		if (rc == WR_OK)
+			submitted++;
+		done += nf;
+	}
+	for (unsigned k = 0; k < submitted; k++) {
+		const int rw = wr_bank_wait(b);
+		if (rc == WR_OK)
+			rc = rw;
+	}
+	return rc;
+}
+
+int wr_rx_get_history(wr_bank *b, unsigned rx, int stage, float *out, unsigned nfloats)
+{
+	WR_REQUIRE(b && out && rx < b->R && (stage == 0 || stage == 1), WR_EINVAL, "wr_rx_get_history: bad argument");
+	const unsigned want = stage ? b->n2 - 1 : 2 * (b->n1 - 1);
+	WR_REQUIRE(nfloats == want, WR_EINVAL, "wr_rx_get_history: %u floats asked, the stage carries %u", nfloats, want);
+	if (!wr::use_device(b->device))
+		return WR_ENODEV;
+	WR_CUDA(cudaStreamSynchronize(b->compute));
+	if (want == 0)
+		return WR_OK;
+	const void *src = stage ? (const void*)(b->d_demod[b->cur] + (size_t)rx * b->dstride)
+			: (const void*)(b->d_hist1[b->cur] + (size_t)rx * (b->n1 - 1));
+	WR_CUDA(cudaMemcpy(out, src, sizeof(float) * want, cudaMemcpyDeviceToHost));
+	return WR_OK;
+}
+
+int wr_rx_set_history(wr_bank *b, unsigned rx, int stage, const float *in, unsigned nfloats)
+{
+	WR_REQUIRE(b && in && rx < b->R && (stage == 0 || stage == 1), WR_EINVAL, "wr_rx_set_history: bad argument");
+	const unsigned want = stage ? b->n2 - 1 : 2 * (b->n1 - 1);
+	WR_REQUIRE(nfloats == want, WR_EINVAL, "wr_rx_set_history: %u floats given, the stage carries %u", nfloats, want);
+	WR_REQUIRE(b->inflight == 0, WR_ESTATE, "wr_rx_set_history: blocks in flight");
+	if (!wr::use_device(b->device))
+		return WR_ENODEV;
+	// state earlier setters asked for (resets, phases) first, so that this one has the last word
+	int rc = apply_pending(b, b->compute);
+	if (rc != WR_OK)
+		return rc;
+	WR_CUDA(cudaStreamSynchronize(b->compute));
+	if (want == 0)
+		return WR_OK;
+	void *dst = stage ? (void*)(b->d_demod[b->cur] + (size_t)rx * b->dstride)
+			: (void*)(b->d_hist1[b->cur] + (size_t)rx * (b->n1 - 1));
+	WR_CUDA(cudaMemcpy(dst, in, sizeof(float) * want, cudaMemcpyHostToDevice));
+	return WR_OK;
 }
 
 int wr_bank_process_u8(wr_bank *b, const uint8_t *iq_host, unsigned nframes, float *audio_host, size_t audio_stride)

@@ -9,6 +9,7 @@
 #include "wr_common.h"
 #include "wr_fft.cuh"
 #include "wr_device.cuh"
+#include "wr_upload.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -451,6 +452,47 @@ long wr_spectrum_process(wr_spectrum *s, const float *iq_host, unsigned nframes,
 				sizeof(float) * (size_t)nrows * s->N, s->T, cudaMemcpyDeviceToHost, s->st));
 	WR_CUDA(cudaStreamSynchronize(s->st));
 	return nrows;
+}
+
+long wr_spectrum_process_upload(wr_spectrum *s, wr_upload *u, unsigned nframes)
+{
+	WR_REQUIRE(s && u, WR_EINVAL, "wr_spectrum_process_upload: null argument");
+	WR_REQUIRE(s->T == 1, WR_EINVAL, "wr_spectrum_process_upload: the sink has %u streams, an upload carries one", s->T);
+	WR_REQUIRE(u->device == s->device, WR_EINVAL, "wr_spectrum_process_upload: upload on device %d, sink on %d", u->device, s->device);
+	WR_REQUIRE(nframes == u->nframes && nframes <= s->maxF, WR_EINVAL, "wr_spectrum_process_upload: %u frames asked, %u uploaded, sink holds %u",
+			nframes, u->nframes, s->maxF);
+	if (!wr::use_device(s->device))
+		return WR_ENODEV;
+	// Asynchronous: the transform of the newest frame runs behind the upload's last piece on the
+	// sink's own stream; wr_spectrum_get synchronises.  The upload is told, so that it does not
+	// overwrite this side before the kernels have read it.
+	if (nframes)
+		WR_CUDA(cudaStreamWaitEvent(s->st, u->ready(nframes), 0));
+	long nrows = run(s, u->dev(), u->maxFrames, nframes, nullptr, 0, s->st);
+	if (nrows < 0)
+		return nrows;
+	WR_CUDA(cudaEventRecord(u->readDone[u->cur], s->st));
+	u->readPending[u->cur] = true;
+	return nrows;
+}
+
+int wr_spectrum_reserve(wr_spectrum *s, unsigned max_frames)
+{
+	WR_REQUIRE(s && max_frames > 0, WR_EINVAL, "wr_spectrum_reserve: bad argument");
+	if (max_frames <= s->maxF)
+		return WR_OK;
+	if (!wr::use_device(s->device))
+		return WR_ENODEV;
+	// only the staging buffers of the host path depend on the block length; the carried partial
+	// frame (SpectrumSink's inoffset, reference spectrumsink.h:62) and the last row stay
+	WR_CUDA(cudaStreamSynchronize(s->st));
+	cudaFree(s->d_in);
+	cudaFree(s->d_rows);
+	s->d_in = nullptr;
+	s->d_rows = nullptr;
+	s->maxF = max_frames;
+	s->maxRows = (unsigned)(((size_t)s->N - 1 + max_frames - s->N) / s->hop + 1);
+	return WR_OK;
 }
 
 int wr_spectrum_get(wr_spectrum *s, unsigned stream, float *db_host)

@@ -1,0 +1,151 @@
+// wr_upload.cu -- wr_upload_* and wr_host_* of include/webradio_b200.h: the tuner block goes to the
+// device ONCE per DspBlock::run of its producer, straight from the producer's own std::vector
+// (page-locked in place on first sight), in pieces, so that consumers start on the first piece while
+// the rest is still on the wire.
+#include "wr_common.h"
+#include "wr_upload.cuh"
+
+#include <algorithm>
+
+namespace {
+
+void free_upload(wr_upload *u)
+{
+	if (!u)
+		return;
+	cudaSetDevice(u->device);
+	if (u->st)
+		cudaStreamSynchronize(u->st);
+	for (int b = 0; b < 2; b++) {
+		if (u->readPending[b] && u->readDone[b])
+			cudaEventSynchronize(u->readDone[b]);
+		cudaFree(u->d_iq[b]);
+		for (int j = 0; j < wr_upload::kPieces; j++)
+			if (u->landed[b][j]) cudaEventDestroy(u->landed[b][j]);
+		if (u->readDone[b]) cudaEventDestroy(u->readDone[b]);
+	}
+	if (u->regPtr)
+		cudaHostUnregister(const_cast<void*>(u->regPtr));
+	if (u->st)
+		cudaStreamDestroy(u->st);
+	cudaGetLastError();
+	delete u;
+}
+
+} // namespace
+
+extern "C" {
+
+void *wr_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+		wr::set_error("wr_host_alloc(%zu): %s", bytes, cudaGetErrorString(cudaGetLastError()));
+		return nullptr;
+	}
+	return p;
+}
+
+void wr_host_free(void *p)
+{
+	if (p)
+		cudaFreeHost(p);
+	cudaGetLastError();
+}
+
+wr_upload *wr_upload_create(int device, size_t max_frames)
+{
+	if (max_frames == 0) {
+		wr::set_error("wr_upload_create: max_frames is 0");
+		return nullptr;
+	}
+	if (!wr::check_device(device))
+		return nullptr;
+	wr_upload *u = new wr_upload();
+	u->device = device;
+	u->maxFrames = max_frames;
+	cudaError_t e = cudaStreamCreateWithFlags(&u->st, cudaStreamNonBlocking);
+	for (int b = 0; b < 2 && e == cudaSuccess; b++) {
+		e = cudaMalloc(&u->d_iq[b], sizeof(float) * 2 * max_frames);
+		for (int j = 0; j < wr_upload::kPieces && e == cudaSuccess; j++)
+			e = cudaEventCreateWithFlags(&u->landed[b][j], cudaEventDisableTiming);
+		if (e == cudaSuccess)
+			e = cudaEventCreateWithFlags(&u->readDone[b], cudaEventDisableTiming);
+	}
+	if (e != cudaSuccess) {
+		wr::set_error("wr_upload_create: %s", cudaGetErrorString(e));
+		free_upload(u);
+		return nullptr;
+	}
+	return u;
+}
+
+void wr_upload_destroy(wr_upload *u) { free_upload(u); }
+
+size_t wr_upload_capacity(const wr_upload *u) { return u ? u->maxFrames : 0; }
+int wr_upload_device(const wr_upload *u) { return u ? u->device : -1; }
+
+int wr_upload_begin(wr_upload *u, const float *iq_host, unsigned nframes)
+{
+	WR_REQUIRE(u && (iq_host || nframes == 0), WR_EINVAL, "wr_upload_begin: null argument");
+	WR_REQUIRE(nframes <= u->maxFrames, WR_EINVAL, "wr_upload_begin: %u frames > capacity %zu", nframes, u->maxFrames);
+	if (!wr::use_device(u->device))
+		return WR_ENODEV;
+	const size_t bytes = sizeof(float) * 2 * (size_t)nframes;
+	// Page-lock the producer's buffer where it lies: a DspBlock keeps its output vector from block to
+	// block (reference dspblock.cxx:177-184 resizes it only when the block length changes), so this
+	// happens once; a buffer that moved is registered anew.  If the driver refuses, the copies below
+	// still work (staged by the driver, slower).
+	if (nframes && (iq_host != u->regPtr || bytes > u->regBytes) && !u->regFailed) {
+		if (u->regPtr) {
+			cudaStreamSynchronize(u->st);
+			cudaHostUnregister(const_cast<void*>(u->regPtr));
+			u->regPtr = nullptr;
+			u->regBytes = 0;
+		}
+		if (cudaHostRegister(const_cast<float*>(iq_host), bytes, cudaHostRegisterPortable) == cudaSuccess) {
+			u->regPtr = iq_host;
+			u->regBytes = bytes;
+		} else {
+			cudaGetLastError();
+			u->regFailed = true;     // e.g. memory that is already page-locked by its owner: fine, copy as it is
+		}
+	}
+	const int side = u->cur ^ 1;
+	// an asynchronous reader (the spectrum kernel) may still be on this side from two blocks ago
+	if (u->readPending[side]) {
+		WR_CUDA(cudaStreamWaitEvent(u->st, u->readDone[side], 0));
+		u->readPending[side] = false;
+	}
+	// pieces of at least 256 KiB, whole multiples of 256 frames
+	unsigned np = (unsigned)std::min<size_t>(wr_upload::kPieces, std::max<size_t>(1, bytes / (256u << 10)));
+	unsigned per = np ? (nframes / np) & ~255u : 0;
+	if (per == 0)
+		np = 1;
+	unsigned done = 0;
+	for (unsigned j = 0; j < np; j++) {
+		const unsigned nf = (j + 1 == np) ? nframes - done : per;
+		if (nf)
+			WR_CUDA(cudaMemcpyAsync(u->d_iq[side] + 2 * (size_t)done, iq_host + 2 * (size_t)done,
+					sizeof(float) * 2 * (size_t)nf, cudaMemcpyHostToDevice, u->st));
+		WR_CUDA(cudaEventRecord(u->landed[side][j], u->st));
+		done += nf;
+		u->pieceEnd[j] = done;
+	}
+	u->npieces = np;
+	u->nframes = nframes;
+	u->cur = side;
+	return WR_OK;
+}
+
+int wr_upload_finish(wr_upload *u)
+{
+	WR_REQUIRE(u, WR_EINVAL, "wr_upload_finish: null handle");
+	if (!wr::use_device(u->device))
+		return WR_ENODEV;
+	if (u->npieces)
+		WR_CUDA(cudaEventSynchronize(u->landed[u->cur][u->npieces - 1]));
+	return WR_OK;
+}
+
+} // extern "C"

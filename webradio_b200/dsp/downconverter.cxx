@@ -21,6 +21,7 @@ DownConverter::~DownConverter()
 {
 	if (bank)
 		wrhost::release(bank, bankSlot);
+	wrhost::forget(this);   // the device copy of a chain that had no producer
 	if (stage)
 		wr_stage_destroy(stage);
 	delete filter;
@@ -85,13 +86,14 @@ bool DownConverter::process(const vector<sample_t> &inBuffer, vector<sample_t> &
 		// fused path: the first receiver of the bank to see this producer block runs the
 		// kernels for all of them; the mixed IQ is never materialised (outBuffer keeps its size
 		// but not meaningful contents -- nothing but the fused chain consumes it)
+		// (a chain without a producer is its own clock: every call is a new block)
 		DspBlock *src = upstream();
-		return bank->ensureProcessed(src ? src->runSerial() : 0, inBuffer.data(), nframes);
+		return bank->ensureProcessed(src ? src->runSerial() : runSerial(), inBuffer.data(), nframes, this);
 	}
 
 	// strict path: this block alone, one kernel (reference downconverter.cxx:91-114)
 	if (!stage) {
-		stage = wr_stage_create(wrhost::defaultDevice());
+		stage = wr_stage_create(wrhost::deviceFor(upstream()));
 		if (!stage) {
 			LOG_ERROR("DownConverter: %s\n", wr_last_error());
 			return false;

@@ -9,6 +9,7 @@
 #include <inttypes.h>
 
 #include "debug.h"
+#include "gpubank.h"
 
 static std::atomic<uint64_t> g_topologySerial(1);
 
@@ -16,7 +17,7 @@ uint64_t DspBlock::topologySerial() { return g_topologySerial.load(); }
 
 DspBlock::DspBlock(const string &name, const string &type) :
 	_outputSampleRate(DEFAULT_SAMPLE_RATE), _outputChannels(DEFAULT_CHANNELS),
-	_producer(NULL), _isRunning(false), _runSerial(0),
+	_producer(NULL), _isRunning(false), _runSerial(0), _uploadPending(false), _everUploaded(false),
 	_name(name), _type(type),
 	_inputSampleRate(DEFAULT_SAMPLE_RATE), _inputChannels(DEFAULT_CHANNELS),
 	_decimation(1), _interpolation(1)
@@ -28,6 +29,8 @@ DspBlock::~DspBlock()
 	// reference dspblock.cxx:51-55
 	if (_isRunning)
 		stop();
+	if (_everUploaded)
+		wrhost::forget(this);
 	// Blocks may be deleted in either order (the reference's destructor never looks at its
 	// consumers unless it is running).  The upstream() link added here must not change that: a
 	// consumer that goes away takes itself off its producer's list, so the loop below only ever
@@ -83,10 +86,14 @@ uint64_t DspBlock::nsPerFrameAll() const
 	return sum;
 }
 
+// The reference reads CLOCK_PROCESS_CPUTIME_ID around every process() (dspblock.cxx:186-204): a
+// system call each, 500 of them per tuner block with 64 receivers -- a fifth of a millisecond spent
+// on measuring -- and CPU time says nothing about a block that waits for the GPU.  The monotonic
+// clock (a vDSO read, tens of nanoseconds) keeps the counters and their getters.
 static inline uint64_t cpuTimeNs()
 {
 	timespec t;
-	clock_gettime(CLOCK_PROCESS_CPUTIME_ID, &t);
+	clock_gettime(CLOCK_MONOTONIC, &t);
 	return (uint64_t)t.tv_sec * 1000000000ull + (uint64_t)t.tv_nsec;
 }
 #endif
@@ -151,6 +158,11 @@ void DspBlock::stop()
 		_isRunning = false;
 		deinit();
 	}
+	if (_everUploaded) {
+		// the buffer is page-locked in place for the device copies: undo that before it is freed
+		wrhost::forget(this);
+		_uploadPending = _everUploaded = false;
+	}
 	vector<sample_t>().swap(_buffer);
 }
 
@@ -185,10 +197,15 @@ bool DspBlock::run(const vector<sample_t> &inBuffer)
 	_spent.framesOut += outframes;
 #endif
 
-	for (size_t i = 0; i < _consumers.size(); i++)
-		if (!_consumers[i]->run(_buffer))
-			return false;
-	return true;
+	bool ok = true;
+	for (size_t i = 0; ok && i < _consumers.size(); i++)
+		ok = _consumers[i]->run(_buffer);
+	if (_uploadPending) {
+		// a consumer copies this buffer to its device asynchronously: it is ours again only now
+		wrhost::blockDone(this);
+		_uploadPending = false;
+	}
+	return ok;
 }
 
 // reference dspblock.cxx:214-231: ignored while running

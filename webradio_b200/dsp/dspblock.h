@@ -71,6 +71,9 @@ public:
 	uint64_t runSerial() const { return _runSerial; }
 	// increments on every connect()/disconnect() anywhere in the process
 	static uint64_t topologySerial();
+	// a consumer has started an asynchronous device copy of this block's output buffer
+	// (wrhost::uploadFor): run() waits for it before it returns, stop() drops it before the buffer goes
+	void noteUpload() { _uploadPending = _everUploaded = true; }
 
 protected:
 	// hooks a concrete block implements
@@ -104,6 +107,7 @@ private:
 	vector<sample_t> _buffer;   // this block's output, handed to every consumer
 	bool _isRunning;
 	uint64_t _runSerial;
+	bool _uploadPending, _everUploaded;
 
 	// identity and negotiated format
 	const string _name;

@@ -61,21 +61,36 @@ void SpectrumSink::deinit()
 	}
 }
 
-// reference spectrumsink.cxx:88-123
+// reference spectrumsink.cxx:88-123.  The block is read from the device copy its producer's
+// consumers share (wrhost::uploadFor: the receiver bank of the same front-end uses it too), on the
+// producer's device; the transform runs behind the copy and getSpectrum() waits for it.
 bool SpectrumSink::process(const vector<sample_t> &inBuffer, vector<sample_t> &outBuffer)
 {
 	(void)outBuffer;
 	const unsigned int nframes = (unsigned int)(inBuffer.size() / inputChannels());
 	std::lock_guard<std::mutex> lk(lock);
-	if (!spectrum || nframes > capacityFrames) {
-		if (spectrum)
-			wr_spectrum_destroy(spectrum);
+	DspBlock *src = upstream();
+	if (!spectrum) {
 		capacityFrames = nframes > 0 ? nframes : 1;
-		spectrum = wr_spectrum_create(wrhost::defaultDevice(), _fftSize, _fftSize, 1, capacityFrames);
+		spectrum = wr_spectrum_create(wrhost::deviceFor(src), _fftSize, _fftSize, 1, capacityFrames);
 		if (!spectrum) {
 			LOG_ERROR("SpectrumSink: %s\n", wr_last_error());
 			return false;
 		}
+	} else if (nframes > capacityFrames) {
+		// a longer block than before: more room, the partial frame and the last spectrum stay
+		if (wr_spectrum_reserve(spectrum, nframes) != WR_OK) {
+			LOG_ERROR("SpectrumSink: %s\n", wr_last_error());
+			return false;
+		}
+		capacityFrames = nframes;
+	}
+	if (src) {
+		wr_upload *up = wrhost::uploadFor(src, this, src->runSerial(), inBuffer.data(), nframes);
+		if (up && wr_spectrum_process_upload(spectrum, up, nframes) >= 0)
+			return true;
+		LOG_ERROR("SpectrumSink: %s\n", wr_last_error());
+		return false;
 	}
 	if (wr_spectrum_process(spectrum, inBuffer.data(), nframes, NULL, 0) < 0) {
 		LOG_ERROR("SpectrumSink: %s\n", wr_last_error());
