@@ -22,14 +22,26 @@ namespace {
 
 class ReplayTuner : public Tuner {
 public:
-	ReplayTuner(const string &name) : Tuner(name, "ReplayTuner"), cur(NULL), len(0) {}
+	ReplayTuner(const string &name) : Tuner(name, "ReplayTuner"), cur(NULL), len(0), head(0) {}
 	void feed(const float *p, size_t n) { cur = p; len = n; }
+	// RtlSdrTuner's hand-over (reference src/io/rtlsdrtuner.cxx:265-285): a ring of block-sized vectors
+	// filled elsewhere, each SWAPPED into the block's output buffer -- no copy, and the buffer the
+	// consumers see changes from block to block
+	void ringFill(const float *p, size_t n) { ring.push_back(vector<sample_t>(p, p + n)); }
+	bool ringMode() const { return !ring.empty(); }
 private:
 	bool init() { _outputSampleRate = inputSampleRate(); _outputChannels = inputChannels(); return true; }
 	void deinit() {}
 	bool process(const vector<sample_t> &in, vector<sample_t> &out)
 	{
 		(void)in;
+		if (!ring.empty()) {
+			if (ring[head].size() != out.size())
+				return false;
+			out.swap(ring[head]);
+			head = (head + 1) % ring.size();
+			return true;
+		}
 		if (!cur || len != out.size())
 			return false;
 		memcpy(out.data(), cur, len * sizeof(float));
@@ -37,6 +49,8 @@ private:
 	}
 	const float *cur;
 	size_t len;
+	vector<vector<sample_t> > ring;
+	size_t head;
 };
 
 ReplayTuner *g_lastTuner = NULL;
@@ -159,6 +173,28 @@ int wrr_device(void *h)
 	Rig *r = (Rig*)h;
 	return wrhost::deviceFor(r->tuner);
 }
+
+/* the tuner's ring of blocks (see ReplayTuner::ringFill); wrr_run_ring runs `steps` Radio::run() over it */
+int wrr_ring_fill(void *h, const float *iq)
+{
+	Rig *r = (Rig*)h;
+	r->tuner->ringFill(iq, (size_t)r->frames * 2);
+	return 0;
+}
+
+int wrr_run_ring(void *h, unsigned steps)
+{
+	Rig *r = (Rig*)h;
+	if (!r->tuner->ringMode())
+		return -1;
+	for (unsigned i = 0; i < steps; i++)
+		Radio::run();
+	return 0;
+}
+
+/* AudioStreamManager stand-in: keep the last audio block of every receiver (tests) or return at once
+ * as the reference does without a client (timed runs) */
+void wrr_capture(int on) { AudioStreamManager::capture() = on != 0; }
 
 /* what a web handler would do (receiverhandler.cxx:125-140) */
 int wrr_retune(void *h, int rx, int if_hz, const char *mode, unsigned chan_passband)

@@ -16,13 +16,17 @@ public:
 	AudioStreamManager(const string &name = "<undefined>") : SampleSink(name, "AudioStreamManager"), blocks(0) {}
 	vector<float> last;
 	unsigned long blocks;
+	// the reference's manager returns at once while no HTTP client is connected (audiostream.cxx:65-73):
+	// capture(false) makes the stand-in do the same (bench.py's timed region)
+	static bool &capture() { static bool on = true; return on; }
 private:
 	bool init() { return true; }
 	void deinit() {}
 	bool process(const vector<sample_t> &in, vector<sample_t> &out)
 	{
 		(void)out;
-		last.assign(in.begin(), in.end());
+		if (capture())
+			last.assign(in.begin(), in.end());
 		blocks++;
 		return true;
 	}

@@ -1193,9 +1193,11 @@ static int process_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframe
 	unsigned pieces = b->keepChan ? 1u : b->syncSplit;     // (wr_bank_read_stage reads the last launch: keep it the whole block)
 	const unsigned quantum = b->d1 * b->d2;
 	if (pieces == 0) {
-		// by size: pieces of at least 256 KiB of input (copy latency dominates below that)
+		// by size.  Every piece costs about ten runtime calls (~15 us of host time), so a block of
+		// under a few MB is cut in two at most (measured on cfg2, 819 KB: 1 piece 88 k, 2 pieces
+		// 96 k, 3 pieces 85 k, 4 pieces 79 k MS/s); large blocks in four
 		const size_t bytes = (u8 ? 2 : 8) * (size_t)nframes * b->T;
-		pieces = (unsigned)std::min<size_t>(4, std::max<size_t>(1, bytes / (256u << 10)));
+		pieces = bytes >= (8u << 20) ? 4u : bytes >= (512u << 10) ? 2u : 1u;
 	}
 	pieces = std::min<unsigned>(pieces, (unsigned)b->depth);
 	unsigned per = nframes / std::max(1u, pieces);
@@ -1244,7 +1246,8 @@ int wr_bank_process_upload(wr_bank *b, wr_upload *u, unsigned nframes, float *au
 	// the bank's own sub-blocks (whole audio frames), each started as soon as the upload's piece
 	// that completes it has landed; the audio of one leaves while the next is computed
 	const unsigned quantum = b->d1 * b->d2;
-	unsigned pieces = b->keepChan ? 1u : std::min<unsigned>(u->npieces ? u->npieces : 1u, (unsigned)b->depth);
+	unsigned pieces = b->keepChan ? 1u : b->syncSplit ? b->syncSplit : std::min<unsigned>(u->npieces ? u->npieces : 1u, (unsigned)b->depth);
+	pieces = std::min<unsigned>(pieces, (unsigned)b->depth);
 	unsigned per = nframes / std::max(1u, pieces);
 	per -= per % quantum;
 	const unsigned minPiece = std::max(quantum, b->v3.ok ? b->v3.SF : 0u);

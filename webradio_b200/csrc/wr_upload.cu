@@ -24,8 +24,9 @@ void free_upload(wr_upload *u)
 			if (u->landed[b][j]) cudaEventDestroy(u->landed[b][j]);
 		if (u->readDone[b]) cudaEventDestroy(u->readDone[b]);
 	}
-	if (u->regPtr)
-		cudaHostUnregister(const_cast<void*>(u->regPtr));
+	for (int i = 0; i < wr_upload::kRegs; i++)
+		if (u->reg[i].ptr)
+			cudaHostUnregister(const_cast<void*>(u->reg[i].ptr));
 	if (u->st)
 		cudaStreamDestroy(u->st);
 	cudaGetLastError();
@@ -93,23 +94,44 @@ int wr_upload_begin(wr_upload *u, const float *iq_host, unsigned nframes)
 		return WR_ENODEV;
 	const size_t bytes = sizeof(float) * 2 * (size_t)nframes;
 	// Page-lock the producer's buffer where it lies: a DspBlock keeps its output vector from block to
-	// block (reference dspblock.cxx:177-184 resizes it only when the block length changes), so this
-	// happens once; a buffer that moved is registered anew.  If the driver refuses, the copies below
-	// still work (staged by the driver, slower).
-	if (nframes && (iq_host != u->regPtr || bytes > u->regBytes) && !u->regFailed) {
-		if (u->regPtr) {
-			cudaStreamSynchronize(u->st);
-			cudaHostUnregister(const_cast<void*>(u->regPtr));
-			u->regPtr = nullptr;
-			u->regBytes = 0;
+	// block (reference dspblock.cxx:177-184 resizes it only when the block length changes) or swaps a
+	// few ring buffers through it (rtlsdrtuner.cxx:265-285), so each buffer is registered once.  If the
+	// driver refuses, the copies below still work (staged by the driver, slower).
+	if (nframes && u->regFailures < 4) {
+		int hit = -1, lru = 0;
+		for (int i = 0; i < wr_upload::kRegs; i++) {
+			if (u->reg[i].ptr == iq_host && u->reg[i].bytes >= bytes)
+				hit = i;
+			if (u->reg[i].used < u->reg[lru].used)
+				lru = i;
 		}
-		if (cudaHostRegister(const_cast<float*>(iq_host), bytes, cudaHostRegisterPortable) == cudaSuccess) {
-			u->regPtr = iq_host;
-			u->regBytes = bytes;
-		} else {
-			cudaGetLastError();
-			u->regFailed = true;     // e.g. memory that is already page-locked by its owner: fine, copy as it is
+		if (hit < 0) {
+			wr_upload::Reg &r = u->reg[lru];
+			if (r.ptr) {
+				cudaStreamSynchronize(u->st);
+				cudaHostUnregister(const_cast<void*>(r.ptr));
+				r.ptr = nullptr;
+				r.bytes = 0;
+			}
+			// (a longer buffer at a known address: drop the old registration first)
+			for (int i = 0; i < wr_upload::kRegs; i++)
+				if (u->reg[i].ptr == iq_host) {
+					cudaStreamSynchronize(u->st);
+					cudaHostUnregister(const_cast<void*>(u->reg[i].ptr));
+					u->reg[i].ptr = nullptr;
+					u->reg[i].bytes = 0;
+				}
+			if (cudaHostRegister(const_cast<float*>(iq_host), bytes, cudaHostRegisterPortable) == cudaSuccess) {
+				r.ptr = iq_host;
+				r.bytes = bytes;
+				hit = lru;
+			} else {
+				cudaGetLastError();
+				u->regFailures++;    // e.g. memory its owner page-locked already: fine, copied as it is
+			}
 		}
+		if (hit >= 0)
+			u->reg[hit].used = ++u->regClock;
 	}
 	const int side = u->cur ^ 1;
 	// an asynchronous reader (the spectrum kernel) may still be on this side from two blocks ago
@@ -117,8 +139,9 @@ int wr_upload_begin(wr_upload *u, const float *iq_host, unsigned nframes)
 		WR_CUDA(cudaStreamWaitEvent(u->st, u->readDone[side], 0));
 		u->readPending[side] = false;
 	}
-	// pieces of at least 256 KiB, whole multiples of 256 frames
-	unsigned np = (unsigned)std::min<size_t>(wr_upload::kPieces, std::max<size_t>(1, bytes / (256u << 10)));
+	// two pieces from 512 KiB, four from 8 MiB (every piece costs runtime calls on both sides), whole
+	// multiples of 256 frames
+	unsigned np = bytes >= (8u << 20) ? 4u : bytes >= (512u << 10) ? 2u : 1u;
 	unsigned per = np ? (nframes / np) & ~255u : 0;
 	if (per == 0)
 		np = 1;

@@ -17,9 +17,12 @@ struct wr_upload {
 	int cur = 0;                               // side of the block begun last
 	unsigned nframes = 0, npieces = 0;
 	unsigned pieceEnd[kPieces] = {};           // frames [0, pieceEnd[j]) are covered by pieces 0..j
-	const void *regPtr = nullptr;              // host range registered with the driver (page-locked in place)
-	size_t regBytes = 0;
-	bool regFailed = false;
+	// host ranges page-locked in place: a tuner that swaps ring buffers into its output (reference
+	// rtlsdrtuner.cxx:265-285) shows a handful of different buffers in turn
+	static constexpr int kRegs = 16;
+	struct Reg { const void *ptr; size_t bytes; unsigned long used; } reg[kRegs] = {};
+	unsigned long regClock = 0;
+	unsigned regFailures = 0;
 
 	const float *dev() const { return d_iq[cur]; }
 	// the event after which frames [0, upto) of the current block are in HBM

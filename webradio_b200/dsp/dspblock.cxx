@@ -153,15 +153,16 @@ void DspBlock::stop()
 {
 	for (size_t i = 0; i < _consumers.size(); i++)
 		_consumers[i]->stop();
+	if (_everUploaded) {
+		// this block's buffers are page-locked in place for the device copies: undo that before
+		// deinit() or the swap below frees them
+		wrhost::forget(this);
+		_uploadPending = _everUploaded = false;
+	}
 	if (_isRunning) {
 		LOG_DEBUG("stopping %s\n", label().c_str());
 		_isRunning = false;
 		deinit();
-	}
-	if (_everUploaded) {
-		// the buffer is page-locked in place for the device copies: undo that before it is freed
-		wrhost::forget(this);
-		_uploadPending = _everUploaded = false;
 	}
 	vector<sample_t>().swap(_buffer);
 }
