@@ -235,6 +235,198 @@ __global__ void __launch_bounds__(256, 2) spectrum_kernel_v2(const SpecArgs a)
 	}
 }
 
+// ---- v3: persistent, the frames arrive by bulk copies (TMA) behind mbarriers ---------------------
+// One 256-thread CTA per SM walks a run of consecutive FFT frames of one stream.  The frames'
+// samples are fetched by cp.async.bulk, hop frames (a "chunk") at a time, into a ring of N/hop + 1
+// chunks in shared memory: while frame m is transformed, the chunk that completes frame m+1 is
+// already landing, and as soon as pass 1 has consumed the oldest chunk its slot is handed to the
+// copy for frame m+2.  Overlapping frames (hop = N/2, BASELINE config 4) share their common half
+// in shared memory instead of fetching it twice.  The transform is v2's (radix-R1 in registers,
+// radix-16, radix-16; wr_fft.cuh), so are window and dB epilogue.
+struct SpecArgs3 {
+	SpecArgs a;
+	unsigned row0;           // first row this launch computes (rows in front of it straddle the carry buffer: v2)
+	unsigned rowsPerRun;     // consecutive rows of one stream a CTA takes at a time
+	unsigned runsPerStream;
+	unsigned nStreams;
+};
+
+__device__ __forceinline__ void spec_mbar_init(uint32_t bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void spec_mbar_wait(uint32_t bar, unsigned parity)
+{
+	asm volatile("{\n\t.reg .pred p;\n"
+			"WR_SPEC_WAIT%=:\n\t"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+			"@!p bra WR_SPEC_WAIT%=;\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void spec_bulk_load(uint32_t dst, const void *src, unsigned bytes, uint32_t bar)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+	// (a single copy may carry at most 2^20 - 16 bytes; chunks here are at most 64 KiB)
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			:: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int R1, int C>     // C = N / hop: chunks per frame (1: hop = N, 2: hop = N/2)
+__global__ void __launch_bounds__(256) spectrum_kernel_v3(const SpecArgs3 g)
+{
+	extern __shared__ __align__(16) float2 wr_fft_smem[];
+	const SpecArgs &a = g.a;
+	constexpr unsigned N = R1 * 256, HOP = N / C, NSLOT = C + 1;
+	float2 *sm = wr_fft_smem;                               // work buffer, R1 rows of kRowPitch
+	float2 *tw2 = wr_fft_smem + R1 * kRowPitch;             // pass-2 twiddles
+	float2 *ring = tw2 + 256;                               // NSLOT chunks of HOP samples
+	__shared__ __align__(8) unsigned long long wr_spec_bars[NSLOT];
+	const unsigned tid = threadIdx.x;
+	const uint32_t bar32 = (uint32_t)__cvta_generic_to_shared(wr_spec_bars);
+	const uint32_t ring32 = (uint32_t)__cvta_generic_to_shared(ring);
+	if (tid == 0) {
+		for (unsigned i = 0; i < NSLOT; i++)
+			spec_mbar_init(bar32 + 8u * i, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	tw2[tid] = __ldg(a.twiddle + ((((tid & 15) * (tid >> 4)) & 255) * R1));
+	// the window of this thread's R1 samples and its pass-1 twiddle base are the same for every frame
+	float win[R1];
+	#pragma unroll
+	for (int j = 0; j < R1; j++)
+		win[j] = __ldg(a.window + tid + 256u * j);
+	const float2 w1 = __ldg(a.twiddle + tid);
+	__syncthreads();
+
+	const unsigned nrows3 = a.nrows - g.row0;
+	const unsigned totalRuns = g.runsPerStream * g.nStreams;
+	unsigned phases = 0;                                    // bit s: parity of the next completion of slot s to wait for
+	for (unsigned run = blockIdx.x; run < totalRuns; run += gridDim.x) {
+		const unsigned t = run / g.runsPerStream;
+		const unsigned r0 = (run - t * g.runsPerStream) * g.rowsPerRun;
+		const unsigned nr = min(g.rowsPerRun, nrows3 - r0);
+		const unsigned mFirst = g.row0 + r0;
+		// chunk c of this run starts at frame (mFirst + c) * HOP of [carry | in]; all of it lies in `in`
+		const float2 *src = a.in + (size_t)t * a.in_stride + ((size_t)mFirst * HOP - a.ncarry);
+		const unsigned nchunks = nr + C - 1;
+		// prologue: the chunks of the first frame and the one that completes the second
+		if (tid == 0) {
+			for (unsigned c = 0; c < NSLOT && c < nchunks; c++)
+				spec_bulk_load(ring32 + (c % NSLOT) * HOP * 8u, src + (size_t)c * HOP, HOP * 8u, bar32 + 8u * (c % NSLOT));
+		}
+		for (unsigned f = 0; f < nr; f++) {
+			const unsigned m = mFirst + f;
+			// ---- pass 1: the frame's chunks have landed; window fused into the read ----
+			float2 v[R1];
+			#pragma unroll
+			for (unsigned c = 0; c < (unsigned)C; c++) {
+				const unsigned slot = (f + c) % NSLOT;
+				// each slot is waited for once per chunk it receives; chunk f + c is new to this frame
+				// only if c == C - 1 (or this is the run's first frame)
+				if (c == (unsigned)C - 1 || f == 0) {
+					spec_mbar_wait(bar32 + 8u * slot, (phases >> slot) & 1u);
+					phases ^= 1u << slot;
+				}
+				const float2 *chunk = ring + slot * HOP;
+				#pragma unroll
+				for (int j = 0; j < R1 / C; j++)
+					v[c * (R1 / C) + j] = chunk[tid + 256u * j];
+			}
+			#pragma unroll
+			for (int j = 0; j < R1; j++) {
+				// inbuf[n] *= window[n] (spectrumsink.cxx:110-113): both components in one packed multiply
+				asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&v[j]))
+						: "l"(*reinterpret_cast<const unsigned long long*>(&v[j])), "l"(pack2(win[j], win[j])));
+			}
+			wrfft::RegDft<R1>::run(v);
+			// every thread is done with the previous frame's pass 3 (work buffer) and with this
+			// frame's oldest chunk (ring)
+			__syncthreads();
+			if (tid == 0 && f + NSLOT < nchunks) {
+				const unsigned c = f + NSLOT;               // the chunk that completes frame f + 2
+				spec_bulk_load(ring32 + (c % NSLOT) * HOP * 8u, src + (size_t)c * HOP, HOP * 8u, bar32 + 8u * (c % NSLOT));
+			}
+			{
+				float2 cur = w1;
+				sm[tid] = v[0];
+				#pragma unroll
+				for (int k1 = 1; k1 < R1; k1++) {
+					sm[k1 * kRowPitch + tid] = wrfft::cmul(v[k1], cur);
+					cur = wrfft::cmul(cur, w1);
+				}
+			}
+			__syncthreads();
+			// ---- pass 2: radix-16 over the stride-16 index of every 256-point row ----
+			// (a thread's butterflies are loaded TOGETHER before the first is computed: with one CTA of
+			// eight warps per SM nobody else hides the shared-memory latency)
+			constexpr unsigned NB = (R1 * 16 + 255) / 256;
+			{
+				float2 u[NB][16];
+				#pragma unroll
+				for (unsigned i = 0; i < NB; i++) {
+					const unsigned bf = tid + 256 * i;
+					if (bf < R1 * 16) {
+						const float2 *row = sm + (bf >> 4) * kRowPitch + (bf & 15);
+						#pragma unroll
+						for (int q = 0; q < 16; q++)
+							u[i][q] = row[16 * q];
+					}
+				}
+				#pragma unroll
+				for (unsigned i = 0; i < NB; i++) {
+					const unsigned bf = tid + 256 * i;
+					if (bf < R1 * 16) {
+						const unsigned b = bf & 15, k1 = bf >> 4;
+						float2 *row = sm + k1 * kRowPitch + b;
+						wrfft::RegDft<16>::run(u[i]);
+						#pragma unroll
+						for (int ka = 0; ka < 16; ka++)
+							row[16 * ka] = ka ? wrfft::cmul(u[i][ka], tw2[16 * ka + b]) : u[i][0];
+					}
+				}
+			}
+			__syncthreads();
+			// ---- pass 3: radix-16 over the contiguous index; dB + fft-shift fused into the store ----
+			float *rowout = a.rows ? a.rows + (size_t)t * a.row_stride + (size_t)m * N : nullptr;
+			float *last = (m == a.nrows - 1) ? a.last + (size_t)t * N : nullptr;
+			{
+				float2 u[NB][16];
+				#pragma unroll
+				for (unsigned i = 0; i < NB; i++) {
+					const unsigned bf = tid + 256 * i;
+					if (bf < R1 * 16) {
+						const float2 *row = sm + (bf % R1) * kRowPitch + 16 * (bf / R1);
+						#pragma unroll
+						for (int q = 0; q < 16; q++)
+							u[i][q] = row[q];
+					}
+				}
+				#pragma unroll
+				for (unsigned i = 0; i < NB; i++) {
+					const unsigned bf = tid + 256 * i;
+					if (bf < R1 * 16) {
+						wrfft::RegDft<16>::run(u[i]);
+						#pragma unroll
+						for (int kb = 0; kb < 16; kb++) {
+							const unsigned k = bf + R1 * 16 * kb;
+							const unsigned o = (k + N / 2) & (N - 1);
+							const float p = fmaf(u[i][kb].x, u[i][kb].x, u[i][kb].y * u[i][kb].y);
+							float l2;
+							asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(p));
+							const float db = fmaf(3.01029995663981195f, l2, -a.scaledb);
+							if (rowout) rowout[o] = db;
+							if (last) last[o] = db;
+						}
+					}
+				}
+			}
+		}
+		// the next run reuses ring and work buffer
+		__syncthreads();
+	}
+}
+
 // the browser's palette index for one row (wr_device.cuh: waterfall_index)
 __global__ void spectrum_palette_kernel(const float *__restrict__ db, unsigned char *__restrict__ out, unsigned n)
 {
@@ -269,6 +461,8 @@ struct wr_spectrum {
 	bool haveLast = false;
 	cudaStream_t lastStream = nullptr; // stream of the most recent launch
 	bool forceV1 = false;              // env WR_FFT_V1=1: radix-4 shared-memory kernel for every size
+	bool noV3 = false;                 // env WR_FFT_V3=0: never the persistent bulk-copy kernel
+	int numSMs = 148;
 	unsigned long long launches = 0;
 };
 
@@ -321,8 +515,51 @@ long run(wr_spectrum *s, const float *iq_dev, size_t in_stride, unsigned nframes
 		// without a row buffer only the newest transform is observable (getSpectrum), so only
 		// that one is computed; the reference transforms every frame and discards all but the last
 		a.first_row = rows_dev ? 0 : nrows - 1;
-		dim3 grid(nrows - a.first_row, s->T);
-		if (s->N >= 512 && !s->forceV1) {
+		unsigned nrows2 = nrows - a.first_row;      // rows the one-frame-per-CTA kernels take
+		// Many rows per stream (a waterfall): the persistent kernel that streams frames through
+		// shared memory by bulk copies takes every row that lies entirely in this call's block; rows
+		// that begin in the carry buffer stay with the one-frame-per-CTA kernel.
+		const unsigned row0 = (s->ncarry + s->hop - 1) / s->hop;
+		const bool aligned = !((uintptr_t)iq_dev & 15u) && !(in_stride & 1u) && !(s->ncarry & 1u);
+		if (rows_dev && !s->forceV1 && !s->noV3 && s->N >= 512 && (s->hop == s->N || 2 * s->hop == s->N)
+				&& aligned && nrows > row0 + 1) {
+			SpecArgs3 g;
+			g.a = a;
+			g.row0 = row0;
+			const unsigned nrows3 = nrows - row0;
+			const unsigned long long total = (unsigned long long)nrows3 * s->T;
+			const unsigned want = (unsigned)std::max<unsigned long long>(4, (total + 7ull * s->numSMs - 1) / (7ull * s->numSMs));
+			g.rowsPerRun = std::min(want, nrows3);
+			g.runsPerStream = (nrows3 + g.rowsPerRun - 1) / g.rowsPerRun;
+			const unsigned C = s->N / s->hop, R1 = s->N / 256;
+			const size_t smem = sizeof(float2) * ((size_t)R1 * kRowPitch + 256 + (size_t)(C + 1) * s->hop);
+			const unsigned long long runs = (unsigned long long)g.runsPerStream * s->T;
+			g.nStreams = s->T;
+			// persistent: one CTA per SM (two when two fit), each walking the run list with stride gridDim.x
+			const dim3 grid3((unsigned)std::min<unsigned long long>(runs, (unsigned long long)s->numSMs * (smem <= 100 * 1024 ? 2 : 1)));
+			void (*k3)(const SpecArgs3) = nullptr;
+			switch (R1 * 10 + C) {
+			case 21: k3 = spectrum_kernel_v3<2, 1>; break;
+			case 22: k3 = spectrum_kernel_v3<2, 2>; break;
+			case 41: k3 = spectrum_kernel_v3<4, 1>; break;
+			case 42: k3 = spectrum_kernel_v3<4, 2>; break;
+			case 81: k3 = spectrum_kernel_v3<8, 1>; break;
+			case 82: k3 = spectrum_kernel_v3<8, 2>; break;
+			case 161: k3 = spectrum_kernel_v3<16, 1>; break;
+			case 162: k3 = spectrum_kernel_v3<16, 2>; break;
+			case 321: k3 = spectrum_kernel_v3<32, 1>; break;
+			default: k3 = spectrum_kernel_v3<32, 2>; break;
+			}
+			WR_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			k3<<<grid3, 256, smem, st>>>(g);
+			s->launches++;
+			WR_CUDA(cudaGetLastError());
+			nrows2 = row0;                          // what is left for the kernels below
+		}
+		dim3 grid(nrows2, s->T);
+		if (nrows2 == 0) {
+			// nothing left
+		} else if (s->N >= 512 && !s->forceV1) {
 			const size_t smem = sizeof(float2) * ((size_t)(s->N / 256) * kRowPitch + 256);
 			switch (s->N / 256) {
 			case 2: spectrum_kernel_v2<2><<<grid, 256, smem, st>>>(a); break;
@@ -336,8 +573,10 @@ long run(wr_spectrum *s, const float *iq_dev, size_t in_stride, unsigned nframes
 			size_t smem = sizeof(float2) * 2 * (size_t)s->N;
 			spectrum_kernel_v1<<<grid, threads, smem, st>>>(a);
 		}
-		s->launches++;
-		WR_CUDA(cudaGetLastError());
+		if (nrows2) {
+			s->launches++;
+			WR_CUDA(cudaGetLastError());
+		}
 		s->haveLast = true;
 		s->lastStream = st;
 	}
@@ -415,6 +654,9 @@ wr_spectrum *wr_spectrum_create(int device, unsigned fft_size, unsigned hop, uns
 			(int)(sizeof(float2) * (32 * kRowPitch + 256))));
 	if (const char *e = getenv("WR_FFT_V1"))
 		s->forceV1 = atoi(e) != 0;
+	if (const char *e = getenv("WR_FFT_V3"))
+		s->noV3 = atoi(e) == 0;
+	WR_SPEC_ALLOC(cudaDeviceGetAttribute(&s->numSMs, cudaDevAttrMultiProcessorCount, device));
 #undef WR_SPEC_ALLOC
 	return s;
 }

@@ -97,37 +97,53 @@ int wr_upload_begin(wr_upload *u, const float *iq_host, unsigned nframes)
 	// block (reference dspblock.cxx:177-184 resizes it only when the block length changes) or swaps a
 	// few ring buffers through it (rtlsdrtuner.cxx:265-285), so each buffer is registered once.  If the
 	// driver refuses, the copies below still work (staged by the driver, slower).
-	if (nframes && u->regFailures < 4) {
+	if (nframes) {
+		const char *lo = reinterpret_cast<const char*>(iq_host), *hi = lo + bytes;
 		int hit = -1, lru = 0;
 		for (int i = 0; i < wr_upload::kRegs; i++) {
-			if (u->reg[i].ptr == iq_host && u->reg[i].bytes >= bytes)
-				hit = i;
+			wr_upload::Reg &r = u->reg[i];
+			if (r.ptr) {
+				const char *rlo = reinterpret_cast<const char*>(r.ptr), *rhi = rlo + r.bytes;
+				if (rlo == lo && rhi >= hi) {
+					hit = i;
+				} else if (rlo < hi && lo < rhi) {
+					// overlaps a registered range without being it: that buffer is gone (freed, moved,
+					// grown) -- its registration must go before the runtime sees a half-locked source
+					cudaStreamSynchronize(u->st);
+					cudaHostUnregister(const_cast<void*>(r.ptr));
+					cudaGetLastError();
+					r.ptr = nullptr;
+					r.bytes = 0;
+					r.used = 0;
+				}
+			}
 			if (u->reg[i].used < u->reg[lru].used)
 				lru = i;
 		}
-		if (hit < 0) {
-			wr_upload::Reg &r = u->reg[lru];
-			if (r.ptr) {
-				cudaStreamSynchronize(u->st);
-				cudaHostUnregister(const_cast<void*>(r.ptr));
-				r.ptr = nullptr;
-				r.bytes = 0;
-			}
-			// (a longer buffer at a known address: drop the old registration first)
+		if (hit < 0 && u->regFailures < 4) {
+			bool again = false;
 			for (int i = 0; i < wr_upload::kRegs; i++)
-				if (u->reg[i].ptr == iq_host) {
-					cudaStreamSynchronize(u->st);
-					cudaHostUnregister(const_cast<void*>(u->reg[i].ptr));
-					u->reg[i].ptr = nullptr;
-					u->reg[i].bytes = 0;
-				}
-			if (cudaHostRegister(const_cast<float*>(iq_host), bytes, cudaHostRegisterPortable) == cudaSuccess) {
-				r.ptr = iq_host;
-				r.bytes = bytes;
-				hit = lru;
+				again = again || (u->seen[i].ptr == iq_host && u->seen[i].bytes == bytes);
+			if (!again) {
+				u->seen[u->seenNext] = { iq_host, bytes };
+				u->seenNext = (u->seenNext + 1) % wr_upload::kRegs;
 			} else {
-				cudaGetLastError();
-				u->regFailures++;    // e.g. memory its owner page-locked already: fine, copied as it is
+				wr_upload::Reg &r = u->reg[lru];
+				if (r.ptr) {
+					cudaStreamSynchronize(u->st);
+					cudaHostUnregister(const_cast<void*>(r.ptr));
+					cudaGetLastError();
+					r.ptr = nullptr;
+					r.bytes = 0;
+				}
+				if (cudaHostRegister(const_cast<float*>(iq_host), bytes, cudaHostRegisterPortable) == cudaSuccess) {
+					r.ptr = iq_host;
+					r.bytes = bytes;
+					hit = lru;
+				} else {
+					cudaGetLastError();
+					u->regFailures++;    // e.g. memory its owner page-locked already: fine, copied as it is
+				}
 			}
 		}
 		if (hit >= 0)

@@ -23,6 +23,11 @@ struct wr_upload {
 	struct Reg { const void *ptr; size_t bytes; unsigned long used; } reg[kRegs] = {};
 	unsigned long regClock = 0;
 	unsigned regFailures = 0;
+	// buffers seen once: a buffer is page-locked only when it comes back (a transient caller buffer,
+	// e.g. a test's array, is copied as it is -- registering it would cost more than the copy and
+	// leave a registration behind that its owner knows nothing about)
+	struct Seen { const void *ptr; size_t bytes; } seen[kRegs] = {};
+	unsigned seenNext = 0;
 
 	const float *dev() const { return d_iq[cur]; }
 	// the event after which frames [0, upto) of the current block are in HBM
