@@ -21,7 +21,10 @@ BENCH = {"bench_cfg1": "bench_cfg1", "bench_cfg2": "bench_cfg2", "bench_cfg3": "
          "bench_cfg5": "bench_cfg5", "bench_cfg2_u8": "bench_cfg2_u8", "bench_cfg3_u8": "bench_cfg3_u8",
          "bench_cfg2_v1": "bench_cfg2_v1kernels", "bench_cfg2_v2": "bench_cfg2_v2kernels",
          "bench_cfg3_v2": "bench_cfg3_v2kernels", "bench_ref": "bench_reference_cfg2",
-         "bench_cfg5_u8": "bench_cfg5_u8"}
+         "bench_cfg5_u8": "bench_cfg5_u8", "bench": "bench_default", "bench_n2": "bench_default_n2",
+         "bench_n8": "bench_default_n8"}
+if os.path.exists(os.path.join(src, "bench_ref.json")) and prefix != "r01":
+    BENCH["bench_ref"] = "bench_reference"
 for a, b in BENCH.items():
     p = os.path.join(src, a + ".json")
     if os.path.exists(p) and os.path.getsize(p):
@@ -35,7 +38,8 @@ if os.path.exists(os.path.join(src, "nproc.txt")):
     shutil.copy(os.path.join(src, "nproc.txt"), os.path.join(dst, f"{prefix}_host_cpu.txt"))
 
 # launch list
-p = os.path.join(src, "launches_cfg2.csv")
+LW = "cfg3" if os.path.exists(os.path.join(src, "launches_cfg3.csv")) else "cfg2"
+p = os.path.join(src, f"launches_{LW}.csv")
 if os.path.exists(p):
     rows = list(csv.reader(open(p)))
     h = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
@@ -46,9 +50,9 @@ if os.path.exists(p):
         if len(r) > mv:
             d.setdefault(r[kn], []).append(float(r[mv].replace(",", "")))
     tot = sum(sum(v) for v in d.values())
-    with open(os.path.join(dst, f"{prefix}_launches_cfg2.txt"), "w") as f:
-        f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 300 : python bench.py --steps 20 --warmup 3 "
-                "--no-cpu-baseline (cfg2)\nper-kernel device time, ns (cold-cache, serialised under ncu: compare SHARES, "
+    with open(os.path.join(dst, f"{prefix}_launches_{LW}.txt"), "w") as f:
+        f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 400 : python bench.py --steps 20 --warmup 3 "
+                f"--no-cpu-baseline{' --no-e2e --subs none' if LW == 'cfg3' else ''} ({LW})\nper-kernel device time, ns (cold-cache, serialised under ncu: compare SHARES, "
                 "not absolutes)\n\nlaunches     avg_ns     min_ns     max_ns   share  kernel\n")
         for k, v in d.items():
             f.write(f"{len(v):8d} {sum(v) / len(v):10.0f} {min(v):10.0f} {max(v):10.0f} {100 * sum(v) / tot:6.1f}%  {k[:110]}\n")
