@@ -118,9 +118,8 @@ float lo3_base_host(int s, const Lo3Coef &k)
 {
 	const float t = fmaf(lo3_F(s), WR_LO3_TSCALE, WR_LO3_TBIAS);
 	const float y = t * t;
-	float w = fmaf(y, -1.0f, 1.0f);
-	w = w + k.eps;
-	const float u = t * w;
+	const float z = fmaf(-y, t, t);                // t - t^3: zero at t = 0 and +-1 with a single rounding
+	const float u = fmaf(t, k.eps, z);
 	return u * lo3_poly(y);
 }
 
@@ -135,7 +134,7 @@ int lo3_slot_host(int s)
 bool lo3_compress(const float *table, int16_t *delta, Lo3Coef *coef)
 {
 	Lo3Coef k;
-	// index 32768 (s = -32768, t = -1): 1 - y = 0, so base = (-1 * eps) * poly(1)
+	// index 32768 (s = -32768, t = -1): t - t^3 = 0, so base = (-1 * eps) * poly(1)
 	const float t = table[32768];
 	k.eps = (t < 0.0f) ? (t / (-1.0f * lo3_poly(1.0f))) : 0.0f;
 	if (!(k.eps < 1e-3f))

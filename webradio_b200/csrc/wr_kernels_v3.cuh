@@ -143,6 +143,18 @@ __device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b)
 	return r;
 }
 
+// -a in both halves; ptxas folds it into the operand modifier of the packed instruction that uses it
+__device__ __forceinline__ f2_t f2_neg(f2_t a)
+{
+	float lo, hi;
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+	lo = -lo;
+	hi = -hi;
+	f2_t d;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+	return d;
+}
+
 __device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b)
 {
 	f2_t r;
@@ -195,7 +207,7 @@ __device__ __forceinline__ void mbar_wait_fir(uint32_t bar, unsigned parity) { m
 
 // Packed constants of the table reconstruction, built once per thread.
 struct Lo3Regs {
-	f2_t tscale, tbias, slotk, slotm, neg1, one, eps, c0, c1, c2, c3;
+	f2_t tscale, tbias, slotk, slotm, eps, c0, c1, c2, c3;
 	uint32_t cbase;   // shared-space address of slot 0 minus 2 * WR_LO3_SLOTBITS (mod 2^32)
 	uint32_t hi;      // 0x4B00: exponent bytes of the float index
 };
@@ -207,8 +219,6 @@ __device__ __forceinline__ Lo3Regs lo3_regs(float eps, uint32_t dmid32, uint32_t
 	k.tbias = f2_pack(WR_LO3_TBIAS, WR_LO3_TBIAS);
 	k.slotk = f2_pack(WR_LO3_SLOTK, WR_LO3_SLOTK);
 	k.slotm = f2_pack(WR_LO3_SLOTM, WR_LO3_SLOTM);
-	k.neg1 = f2_pack(-1.0f, -1.0f);
-	k.one = f2_pack(1.0f, 1.0f);
 	k.eps = f2_pack(eps, eps);
 	k.c0 = f2_pack(WR_LO3_C0, WR_LO3_C0);
 	k.c1 = f2_pack(WR_LO3_C1, WR_LO3_C1);
@@ -232,9 +242,8 @@ __device__ __forceinline__ void lo3_sincos(uint32_t qb, const Lo3Regs &k, float 
 	const f2_t SL = f2_fma(F, k.slotk, k.slotm);
 	const f2_t T = f2_fma(F, k.tscale, k.tbias);
 	const f2_t Y = f2_mul(T, T);
-	f2_t W = f2_fma(Y, k.neg1, k.one);
-	W = f2_add(W, k.eps);
-	const f2_t U = f2_mul(T, W);
+	const f2_t Z = f2_fma(f2_neg(Y), T, T);        // t - t^3
+	const f2_t U = f2_fma(T, k.eps, Z);
 	f2_t P = f2_fma(Y, k.c3, k.c2);
 	P = f2_fma(Y, P, k.c1);
 	P = f2_fma(Y, P, k.c0);
@@ -255,7 +264,7 @@ __device__ __forceinline__ void lo3_sincos(uint32_t qb, const Lo3Regs &k, float 
 template <int J>
 __device__ __forceinline__ void lo3_sincos_n(const uint32_t (&qb)[J], const Lo3Regs &k, float (&sn)[J], float (&cs)[J])
 {
-	f2_t F[J], T[J], Y[J], W[J], P[J];
+	f2_t F[J], T[J], Y[J], W[J], P[J];             // (W: t - t^3, then the eps term)
 	uint32_t as[J], ac[J];
 	int ds[J], dc[J];
 	#pragma unroll
@@ -286,19 +295,17 @@ __device__ __forceinline__ void lo3_sincos_n(const uint32_t (&qb)[J], const Lo3R
 		Y[j] = f2_mul(T[j], T[j]);
 	#pragma unroll
 	for (int j = 0; j < J; j++) {
-		W[j] = f2_fma(Y[j], k.neg1, k.one);
+		W[j] = f2_fma(f2_neg(Y[j]), T[j], T[j]);
 		P[j] = f2_fma(Y[j], k.c3, k.c2);
 	}
 	#pragma unroll
 	for (int j = 0; j < J; j++) {
-		W[j] = f2_add(W[j], k.eps);
+		W[j] = f2_fma(T[j], k.eps, W[j]);
 		P[j] = f2_fma(Y[j], P[j], k.c1);
 	}
 	#pragma unroll
-	for (int j = 0; j < J; j++) {
-		W[j] = f2_mul(T[j], W[j]);
+	for (int j = 0; j < J; j++)
 		P[j] = f2_fma(Y[j], P[j], k.c0);
-	}
 	#pragma unroll
 	for (int j = 0; j < J; j++) {
 		float bs, bc;

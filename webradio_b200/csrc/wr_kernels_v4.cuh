@@ -515,6 +515,7 @@ struct V4Plan {
 	size_t smemMax = 0;
 	unsigned maxPerStream = 1;   // most receivers that share one tuner stream (v4_set_groups)
 	unsigned G = 0;              // WR_V4_G: warps per receiver (0 = by bank size)
+	bool ownScratch = true;      // WR_V4_SCRATCH=0: the prologue always borrows the ring (28 KB less shared memory on cfg3)
 	bool pdl = true;
 };
 
@@ -546,6 +547,8 @@ inline int v4_init(V4Plan &p, const V3Plan &v3, int device, unsigned n1, unsigne
 		p.G = (unsigned)std::max(0, atoi(e));
 	if (const char *e = getenv("WR_V3_PDL"))
 		p.pdl = atoi(e) != 0;
+	if (const char *e = getenv("WR_V4_SCRATCH"))
+		p.ownScratch = atoi(e) != 0;
 	cudaDeviceProp prop;
 	WR_CUDA(cudaGetDeviceProperties(&prop, device));
 	p.numSMs = prop.multiProcessorCount;
@@ -609,7 +612,7 @@ inline bool v4_shape(const V4Plan &p, const V3Plan &v3, unsigned R, unsigned F, 
 	// the ring serves as scratch (it must be large enough) and is filled afterwards
 	size_t perWarp = (size_t)NS * p.stageBytes + p.tapBytes + p.scratchBytes;
 	unsigned scratch = p.scratchBytes;
-	if (perWarp * warps > avail) {
+	if (perWarp * warps > avail || (!p.ownScratch && (size_t)NS * p.stageBytes >= p.scratchBytes)) {
 		scratch = 0;
 		perWarp = (size_t)NS * p.stageBytes + p.tapBytes;
 		if ((size_t)NS * p.stageBytes < p.scratchBytes)

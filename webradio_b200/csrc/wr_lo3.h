@@ -8,8 +8,8 @@
 //                                                                     s = index as signed 16 bit
 //     t    = fma(F, 2^-15, -257)                = s / 32768, exact           (angle = pi t)
 //     y    = t * t
-//     w    = fma(y, -1, 1) + eps                (zero crossings at t = 0, +-1; eps: see below)
-//     base = (t * w) * (c0 + y (c1 + y (c2 + y c3)))        minimax fit of sin(pi t) / (t (1 - t^2))
+//     u    = fma(t, eps, fma(-y, t, t))         (t - t^3: zero crossings at t = 0, +-1; eps: see below)
+//     base = u * (c0 + y (c1 + y (c2 + y c3)))              minimax fit of sin(pi t) / (t (1 - t^2))
 //     table[index] == int_as_float(float_as_int(base) + delta[index])        BIT-EXACT
 //
 // and the padded position of an entry in shared memory comes out of the same register pair:
@@ -18,7 +18,7 @@
 //
 // (strictly increasing in s; one padding entry per ~31 keeps a warp's arithmetic progression of
 // lookups off a single bank, see wr_kernels_v2.cuh).  eps makes the one entry that is not ~sin
-// representable: sinf((float)pi) = -8.74e-8 at index 32768, where 1 - y = 0.
+// representable: sinf((float)pi) = -8.74e-8 at index 32768, where t - t^3 = 0.
 // The host computes eps and every delta at start-up and VERIFIES all 65536 entries; a table that
 // cannot be reproduced exactly disables the v3 kernels (v2/v1 take over).
 #pragma once
