@@ -74,6 +74,14 @@ int wr_lo_compress_check(const float *table);
 /* Same check for the packed-arithmetic compression the v3 kernels use
  * (webradio_b200/csrc/wr_lo3.h).  -1 means the v3 kernels stand aside for v2/v1. */
 int wr_lo3_compress_check(const float *table);
+/* Diagnostic (host only, no device needed): how the streaming channel kernel (v4, banks of
+ * independent tuner streams) cuts n_receivers x n_outputs channel-rate outputs into runs for a
+ * persistent grid on n_sms SMs: every receiver into runs_per_receiver runs, the first long_runs
+ * of run_len + 1 outputs and the rest of run_len, dealt 32 to a warp in order; `rounds` is what
+ * the busiest warp works through, `grid` the CTAs launched, `warps` the warps of a CTA.
+ * Returns 1, or 0 if v4 does not serve the geometry / block. */
+int wr_plan_runs(unsigned ntaps, unsigned decimation, unsigned n_receivers, unsigned n_outputs, unsigned n_sms,
+		unsigned *runs_per_receiver, unsigned *run_len, unsigned *long_runs, unsigned *rounds, unsigned *grid, unsigned *warps);
 
 /* Frequency-sampling low-pass design: replaces LowPass::init (window) + LowPass::recalculate
  * (reference src/dsp/lowpass.cxx:102-110,164-189).  Host code (cold path, K0 in SURVEY.md 2a).

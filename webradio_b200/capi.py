@@ -23,7 +23,7 @@ _fp = C.POINTER(C.c_float)
 # every symbol include/webradio_b200.h declares (tests/test_abi.py checks the export list)
 SYMBOLS = [
     "wr_version", "wr_last_error", "wr_device_count", "wr_phase_step", "wr_build_sintable",
-    "wr_lowpass_design", "wr_lo_compress_check", "wr_lo3_compress_check", "wr_atan2f_host",
+    "wr_lowpass_design", "wr_lo_compress_check", "wr_lo3_compress_check", "wr_plan_runs", "wr_atan2f_host",
     "wr_bank_create", "wr_bank_destroy", "wr_bank_set_sintable", "wr_rx_set_stream",
     "wr_rx_set_phase_step", "wr_rx_set_taps", "wr_bank_design_taps", "wr_rx_get_taps", "wr_rx_set_mode", "wr_rx_reset", "wr_rx_set_phase", "wr_rx_get_phase", "wr_rx_set_lookback", "wr_rx_get_lookback",
     "wr_bank_process", "wr_bank_process_device", "wr_bank_submit", "wr_bank_wait",
@@ -65,6 +65,7 @@ def lib():
     L.wr_lowpass_design.argtypes = [u, u, u, _fp]
     L.wr_lo_compress_check.argtypes = [_fp]
     L.wr_lo3_compress_check.argtypes = [_fp]
+    L.wr_plan_runs.argtypes = [u, u, u, u, u] + [C.POINTER(C.c_uint)] * 6
     L.wr_bank_create.restype = vp
     L.wr_bank_create.argtypes = [i, u, u, u, u, u, u, u]
     L.wr_bank_destroy.argtypes = [vp]

@@ -599,6 +599,29 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 	return WR_OK;
 }
 
+} // namespace
+
+extern "C" int wr_plan_runs(unsigned ntaps, unsigned decimation, unsigned n_receivers, unsigned n_outputs, unsigned n_sms,
+		unsigned *runs_per_receiver, unsigned *run_len, unsigned *long_runs, unsigned *rounds, unsigned *grid, unsigned *warps)
+{
+	wrd::V4Plan p;
+	wrd::V4Launch L;
+	if (!n_sms || !wrd::v4_pick(p, ntaps, decimation))
+		return 0;
+	p.numSMs = (int)n_sms;
+	if (!wrd::v4_cut(p, n_receivers, n_outputs, wrd::kV4Warps, &L))
+		return 0;
+	if (runs_per_receiver) *runs_per_receiver = L.runsPerRx;
+	if (run_len) *run_len = L.runLen;
+	if (long_runs) *long_runs = L.longRuns;
+	if (rounds) *rounds = L.rounds;
+	if (grid) *grid = L.grid;
+	if (warps) *warps = L.warps;
+	return 1;
+}
+
+namespace {
+
 void free_bank(wr_bank *b)
 {
 	if (!b)

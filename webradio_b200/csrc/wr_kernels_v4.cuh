@@ -13,8 +13,14 @@
 // accumulator; for a fixed output the frames arrive in increasing tap index, so every accumulator
 // sees exactly the reference's sequence of separately rounded products and sums
 // (lowpass.cxx:151-159).  A mixed sample is produced once, used from registers and never stored.
-//   * A warp = 32 consecutive runs of one receiver (lane L owns outputs [L*K, (L+1)*K)); a
-//     receiver takes G warps, K = ceil(M1 / (32 G)).  Warps are independent of each other: no
+//   * Every receiver's M1 outputs are cut into the same number n_r of runs (of K or K+1 outputs), and
+//     the R * n_r runs of the bank are dealt to the lanes of the grid in order: lane L of warp slot s
+//     owns run 32 s + L.  n_r is chosen by the host so that ONE round of runs fills every lane
+//     of the persistent grid (v4_shape) -- cfg3: 1024 receivers x 37 runs = 148 CTAs x 8 warps x
+//     32 lanes exactly, K = 55/56 -- instead of whole receivers per warp, which left a quarter
+//     of the schedulers half empty (1024 receivers over 148 SMs = 6.9 warps per SM).  n_r >= 32,
+//     so the 32 consecutive runs of a warp belong to at most TWO receivers: both tap sets are
+//     staged, a lane reads the one of its receiver.  Warps are independent of each other: no
 //     block-wide barrier after start-up, no slot hand-over, no spinning.
 //   * Raw IQ: each warp keeps an NS-deep ring of stages in shared memory, a stage = SFR frames of
 //     each of the warp's 32 runs (32 rows of 80 bytes).  The rows are 25.6 KB apart in HBM, so
@@ -29,12 +35,13 @@
 //     window began) needs at each position of a period; all lanes of a warp are at the same
 //     position, so a tap load is a broadcast.  In one period every tap is used exactly once.
 //   * What the runs overlap: a run's last N1-1 frames are also the first frames of the next run
-//     (its outputs' windows begin there).  They are mixed twice -- (N1-1)/(K*D1) = 6.6 % at
-//     cfg3's K = 64 -- which buys independence; keeping them instead would take 65 KB per
-//     receiver in flight (32 x 254 frames).
+//     (its outputs' windows begin there).  They are mixed twice -- (N1-1)/(K*D1) = 9 % at
+//     cfg3's K = 56 -- which buys independence; keeping them instead would take 65 KB per
+//     warp in flight (32 x 254 frames).
 //   * The first outputs of a block, whose windows reach into the carried history, are computed by
-//     a short gather prologue from [history | first frames]; the carried history of the NEXT
-//     block (the last N1-1 mixed frames) is produced by an epilogue.  The steady state therefore
+//     a short gather prologue from [history | first frames] (staged in the warp's ring before it
+//     is filled); the carried history of the NEXT block (the last N1-1 mixed frames) is produced
+//     by an epilogue.  Both belong to the warp that owns the receiver's first run.  The steady state therefore
 //     has no special cases: frames outside the block read as zero (cp.async src-size).
 // Geometry: N1 odd (so that a run starts on a 16-byte boundary), D1 even and a multiple of the
 // stage length.  Shared-tuner banks (cfg2, cfg5) stay with v3, whose mixers share the raw
@@ -44,8 +51,6 @@
 #include "wr_kernels_v3.cuh"
 
 namespace wrd {
-
-constexpr int kV4MaxWarps = 16;
 
 template <int N1, int D1>
 struct V4Geo {
@@ -73,10 +78,11 @@ struct V4Args {
 	float eps;
 	float negzero;            // -0.0f, opaque to the compiler (mul2_rn_exact)
 	unsigned prmtHi;          // 0x4B00, opaque to the compiler
-	unsigned G;               // warps per receiver
-	unsigned K;               // outputs per run
-	unsigned nUnits;          // R * G
-	unsigned scratchBytes;    // per-warp scratch of the prologue behind the taps (0: the ring serves, and is filled after the prologue)
+	unsigned runsPerRx;       // n_r >= 32: runs a receiver's outputs are cut into
+	unsigned runLen;          // K: outputs of a short run ...
+	unsigned longRuns;        // ... the first `longRuns` runs of a receiver have K + 1
+	unsigned totalRuns;       // R * n_r
+	unsigned R;
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
@@ -296,93 +302,109 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 
 	const Lo3Regs lo = lo3_regs(v.eps, smem32 + kV3MidOffset, v.prmtHi);
 	const f2_t nz = f2_pack(v.negzero, v.negzero);
-	// per warp: [ring: NS stages | taps | scratch of the prologue (absent when it does not fit: the ring serves)]
-	const unsigned perWarp = NS * G::kStageBytes + G::kTapBytes + v.scratchBytes;
+	// per warp: [ring: NS stages (also the prologue's scratch, before it is filled) | taps of two receivers]
+	static_assert(NS * G::kStageBytes >= G::kScratchFrames * 8u, "the ring must hold the prologue's [history | first frames]");
+	const unsigned perWarp = NS * G::kStageBytes + 2u * G::kTapBytes;
 	const uint32_t ring32 = smem32 + kV3TableBytes + warp * perWarp;
-	const uint32_t taps32 = ring32 + NS * G::kStageBytes;
-	const uint32_t scr32 = v.scratchBytes ? taps32 + G::kTapBytes : ring32;
-	const unsigned K = v.K;
+	const uint32_t tapsA32 = ring32 + NS * G::kStageBytes;
 	bool tableReady = false;
+	const unsigned Kmax = v.runLen + (v.longRuns ? 1u : 0u);
 
-	// units of this warp: receiver-major, spread over the CTAs
-	const unsigned W = gridDim.x * nWarps;
-	for (unsigned unit = warp * gridDim.x + blockIdx.x; unit < v.nUnits; unit += W) {
-		const unsigned rx = unit / v.G, g = unit - rx * v.G;
+	// rounds of this warp slot: 32 consecutive runs each, slots spread over the CTAs
+	const unsigned stride = gridDim.x * nWarps * 32u;
+	for (unsigned gbase = (warp * gridDim.x + blockIdx.x) * 32u; gbase < v.totalRuns; gbase += stride) {
+		// ---- this lane's run: receiver rx, run j of n_r (lanes past the last run shadow lane 0 and store nothing) ----
+		const bool live = gbase + lane < v.totalRuns;
+		const unsigned rxA = gbase / v.runsPerRx, jA = gbase - rxA * v.runsPerRx;   // lane 0's
+		unsigned rx = rxA, j = jA + (live ? lane : 0u);
+		if (j >= v.runsPerRx) {                                 // (n_r >= 32: at most one step)
+			rx++;
+			j -= v.runsPerRx;
+		}
+		const unsigned lastLive = min(gbase + 31u, v.totalRuns - 1u) - gbase;
+		const bool hasB = jA + lastLive >= v.runsPerRx;         // the warp's runs reach into receiver rxA + 1
+		const unsigned k0 = j * v.runLen + min(j, v.longRuns);   // first output of the run
+		const unsigned Kl = live ? v.runLen + (j < v.longRuns ? 1u : 0u) : 0u;
 		const RxConf cf = a.conf[rx];
 		const uint32_t ph0 = a.st_in[rx].phase;
 		const int32_t step = cf.step;
 		const char *__restrict__ src = reinterpret_cast<const char*>(a.iq) + (size_t)cf.stream * a.stream_stride * 8u;
-		const unsigned L = g * 32u + lane;                       // this lane's run
-		const unsigned k0 = L * K;                               // its first output
+		const uint32_t taps32 = tapsA32 + (rx - rxA) * G::kTapBytes;
 		__syncwarp();
 
 		// ---- the stream: block coordinate c0 = k0*D1 is input frame c0 - (N1-1) ----
 		Run r;
 		const long long f0 = (long long)k0 * D1 - (N1 - 1);      // first frame of this lane's run (negative: history, reads as zero)
-		const long long f0w = (long long)(g * 32u) * K * D1 - (N1 - 1);            // ... of the warp's first run
-		const long long f0l = (long long)(g * 32u + 31u) * K * D1 - (N1 - 1);      // ... of its last run
-		const unsigned nPeriods = K + (unsigned)AP;              // the last one only up to stage SFIN
+		const unsigned nPeriods = Kmax + (unsigned)AP;           // the last one only up to stage SFIN
 		r.nStages = (nPeriods - 1) * S + (unsigned)G::SFIN + 1;
-		r.nLo = f0w < 0 ? (unsigned)((-f0w + SFR - 1) / SFR) : 0u;
-		const long long room = ((long long)a.F - f0l) / SFR;
-		r.nHi = room <= 0 ? 0u : (unsigned)(room < (long long)r.nStages ? room : (long long)r.nStages);
+		{
+			// stages [nLo, nHi) lie inside the block for EVERY run of the warp
+			const unsigned loL = f0 < 0 ? (unsigned)((-f0 + SFR - 1) / SFR) : 0u;
+			const long long room = ((long long)a.F - f0) / SFR;
+			const unsigned hiL = room <= 0 ? 0u : (unsigned)(room < (long long)r.nStages ? room : (long long)r.nStages);
+			r.nLo = __reduce_max_sync(0xFFFFFFFFu, loL);
+			r.nHi = __reduce_min_sync(0xFFFFFFFFu, hiL);
+		}
 		r.src = src;
 		r.F = a.F;
 		#pragma unroll
 		for (int i = 0; i < NCH; i++) {
 			// chunk lane + 32 i of a stage's 160: row c / 5, 16-byte column c % 5; it lands at byte 16 c of the slot
 			const unsigned c = lane + 32u * (unsigned)i;
-			r.cf0[i] = f0w + (long long)(c / NCH) * K * D1 + 2 * (long long)(c % NCH);
-			r.cptr[i] = src + r.cf0[i] * 8;
+			const long long f0r = __shfl_sync(0xFFFFFFFFu, f0, c / NCH);
+			const char *srcr = reinterpret_cast<const char*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)src, c / NCH));
+			r.cf0[i] = f0r + 2 * (long long)(c % NCH);
+			r.cptr[i] = srcr + r.cf0[i] * 8;
 		}
 		r.nf = 0;
 		r.ringBytes = NS * G::kStageBytes;
 		r.st32 = ring32 + lane * G::kRowBytes;
 		r.stEnd = r.st32 + r.ringBytes;
 		r.laneOff = 16u * lane - lane * G::kRowBytes;
-		const bool ringIsScratch = (v.scratchBytes == 0);
-		if (!ringIsScratch || g != 0) {
-			// fill the ring now: the copies fly while the taps are staged and the prologue runs
-			v4_fetch<N1, D1, 0>(r, ring32 + lane * G::kRowBytes);
-			if (NS > 2) v4_fetch<N1, D1, 1>(r, ring32 + G::kStageBytes + lane * G::kRowBytes);
-			if (NS > 3) v4_fetch<N1, D1, 2>(r, ring32 + 2 * G::kStageBytes + lane * G::kRowBytes);
-		}
 
-		// ---- the receiver's taps, rows of one period: row a, stage s, frame i <- tap a*D1 + s*SFR + i ----
-		{
+		// ---- the taps of the warp's receiver(s), rows of one period: row a, stage s, frame i <- tap a*D1 + s*SFR + i ----
+		#pragma unroll 1
+		for (unsigned x = 0; x < (hasB ? 2u : 1u); x++) {
 			constexpr int NE = ROWS * S * TS, PER = (NE + 31) / 32;
+			const float *tp = a.taps1 + (size_t)(rxA + x) * N1;
 			float tv[PER];
 			#pragma unroll
 			for (int e = 0; e < PER; e++) {
 				const unsigned idx = lane + 32u * (unsigned)e;
 				const unsigned aa = idx / (S * TS), rest = idx - aa * (S * TS), ss = rest / TS, ii = rest - ss * TS;
-				const unsigned j = aa * D1 + ss * SFR + ii;
-				tv[e] = (idx < (unsigned)NE && ii < (unsigned)SFR && j < (unsigned)N1) ? __ldg(a.taps1 + (size_t)rx * N1 + j) : 0.0f;
+				const unsigned jt = aa * D1 + ss * SFR + ii;
+				tv[e] = (idx < (unsigned)NE && ii < (unsigned)SFR && jt < (unsigned)N1) ? __ldg(tp + jt) : 0.0f;
 			}
 			#pragma unroll
 			for (int e = 0; e < PER; e++)
 				if (lane + 32u * (unsigned)e < (unsigned)NE)
-					sts32(taps32 + 4u * (lane + 32u * (unsigned)e), tv[e]);
+					sts32(tapsA32 + x * G::kTapBytes + 4u * (lane + 32u * (unsigned)e), tv[e]);
 		}
 		if (!tableReady) {
 			mbar_wait(bar32, 0);      // first use of the NCO table: the bulk copies must have landed
 			tableReady = true;
 		}
 		__syncwarp();
-		// ---- prologue (first warp of a receiver): the outputs whose windows reach into the history ----
-		if (g == 0) {
+		// ---- prologue (the warp that owns a receiver's first run): the outputs whose windows reach into the history ----
+		#pragma unroll 1
+		for (unsigned x = (jA == 0 ? 0u : 1u); x < (hasB ? 2u : 1u); x++) {
+			const unsigned rxp = rxA + x;
+			const uint32_t tapsP32 = tapsA32 + x * G::kTapBytes;
+			const uint32_t php = a.st_in[rxp].phase;
+			const RxConf cfp = a.conf[rxp];
+			const char *__restrict__ srcp = reinterpret_cast<const char*>(a.iq) + (size_t)cfp.stream * a.stream_stride * 8u;
 			// [history (N1-1) | mixed frames 0 ...], float2 each; four entries per lane and round, loads first
 			for (unsigned c0 = 0; c0 < G::kScratchFrames; c0 += 128) {
-				float2 x[4];
+				float2 xx[4];
 				#pragma unroll
 				for (int u = 0; u < 4; u++) {
 					const unsigned c = c0 + lane + 32u * (unsigned)u;
 					if (c < (unsigned)(N1 - 1))
-						x[u] = a.hist_in[(size_t)rx * (N1 - 1) + c];
+						xx[u] = a.hist_in[(size_t)rxp * (N1 - 1) + c];
 					else if (c < G::kScratchFrames && c - (unsigned)(N1 - 1) < a.F)
-						x[u] = __ldg(reinterpret_cast<const float2*>(src) + (c - (unsigned)(N1 - 1)));
+						xx[u] = __ldg(reinterpret_cast<const float2*>(srcp) + (c - (unsigned)(N1 - 1)));
 					else
-						x[u] = make_float2(0.0f, 0.0f);
+						xx[u] = make_float2(0.0f, 0.0f);
 				}
 				#pragma unroll
 				for (int u = 0; u < 4; u++) {
@@ -390,22 +412,22 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 					if (c >= (unsigned)(N1 - 1) && c < G::kScratchFrames) {
 						const unsigned f = c - (unsigned)(N1 - 1);
 						float sn, cs;
-						lo3_sincos(((ph0 + f * (uint32_t)step) << 1) + 0x80000000u, lo, sn, cs);
-						x[u] = mix(x[u], cs, sn);
+						lo3_sincos(((php + f * (uint32_t)cfp.step) << 1) + 0x80000000u, lo, sn, cs);
+						xx[u] = mix(xx[u], cs, sn);
 					}
 					if (c < G::kScratchFrames)
-						sts64(scr32 + 8u * c, x[u]);
+						sts64(ring32 + 8u * c, xx[u]);
 				}
 			}
 			__syncwarp();
 			if (lane < (unsigned)G::KSKIP && lane < a.M1) {
 				f2_t acc = 0ull;
-				uint32_t x32 = scr32 + 8u * lane * (unsigned)D1;
+				uint32_t x32 = ring32 + 8u * lane * (unsigned)D1;
 				#pragma unroll 1
 				for (int aa = 0; aa < ROWS; aa++) {
 					#pragma unroll 1
 					for (int ss = 0; ss < S; ss++) {
-						const uint32_t t32 = taps32 + 4u * (unsigned)((aa * S + ss) * TS);
+						const uint32_t t32 = tapsP32 + 4u * (unsigned)((aa * S + ss) * TS);
 						#pragma unroll
 						for (int ii = 0; ii < SFR; ii++)
 							if (aa * D1 + ss * SFR + ii < N1)
@@ -415,17 +437,15 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 				}
 				float2 y;
 				f2_unpack(acc, y.x, y.y);
-				a.chan[(size_t)rx * a.chan_stride + lane] = y;
+				a.chan[(size_t)rxp * a.chan_stride + lane] = y;
 			}
 			__syncwarp();
-			if (ringIsScratch) {
-				v4_fetch<N1, D1, 0>(r, ring32 + lane * G::kRowBytes);
-				if (NS > 2) v4_fetch<N1, D1, 1>(r, ring32 + G::kStageBytes + lane * G::kRowBytes);
-				if (NS > 3) v4_fetch<N1, D1, 2>(r, ring32 + 2 * G::kStageBytes + lane * G::kRowBytes);
-			}
 		}
-		// v4_fetch takes its sources relative to the period being computed: the ring fill above read
-		// stages 0 .. NS-2 of period 0 with SOFF = 0 .. NS-2, exactly where cptr points
+		// ---- fill the ring: stages 0 .. NS-2 of period 0 (v4_fetch takes its sources relative to the
+		// period being computed, SOFF = 0 .. NS-2 is exactly where cptr points) ----
+		v4_fetch<N1, D1, 0>(r, ring32 + lane * G::kRowBytes);
+		if (NS > 2) v4_fetch<N1, D1, 1>(r, ring32 + G::kStageBytes + lane * G::kRowBytes);
+		if (NS > 3) v4_fetch<N1, D1, 2>(r, ring32 + 2 * G::kStageBytes + lane * G::kRowBytes);
 
 		#pragma unroll
 		for (int i = 0; i < ROWS; i++)
@@ -445,8 +465,8 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 				v4_period<N1, D1, NS, 0, S>(r, lo, taps32, nz, fin);
 			else
 				v4_period<N1, D1, NS, 0, G::SFIN + 1>(r, lo, taps32, nz, fin);
-			// the output that began AP periods ago is complete
-			if (kdone - k0 < K && kdone < a.M1 && kdone >= (unsigned)G::KSKIP) {
+			// the output that began AP periods ago is complete (the first KSKIP of a receiver are the prologue's)
+			if (kdone - k0 < Kl && kdone >= (unsigned)G::KSKIP) {
 				float2 y;
 				f2_unpack(fin, y.x, y.y);
 				out[kdone] = y;
@@ -457,21 +477,26 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 				r.cptr[i] += D1 * 8;
 		}
 		cp_async_wait<0>();
-		// ---- epilogue (first warp of a receiver): the carried state of the next block ----
-		if (g == 0) {
+		// ---- epilogue (the warp that owns a receiver's first run): the carried state of the next block ----
+		#pragma unroll 1
+		for (unsigned x = (jA == 0 ? 0u : 1u); x < (hasB ? 2u : 1u); x++) {
+			const unsigned rxp = rxA + x;
+			const uint32_t php = a.st_in[rxp].phase;
+			const RxConf cfp = a.conf[rxp];
+			const char *__restrict__ srcp = reinterpret_cast<const char*>(a.iq) + (size_t)cfp.stream * a.stream_stride * 8u;
 			for (unsigned i0 = 0; i0 < (unsigned)(N1 - 1); i0 += 64) {
 				// the last N1-1 mixed frames of [history | block]
-				float2 x[2];
+				float2 xx[2];
 				#pragma unroll
 				for (int u = 0; u < 2; u++) {
 					const unsigned i = i0 + lane + 32u * (unsigned)u;
 					const long long f = (long long)a.F - (N1 - 1) + i;
 					if (i >= (unsigned)(N1 - 1))
-						x[u] = make_float2(0.0f, 0.0f);
+						xx[u] = make_float2(0.0f, 0.0f);
 					else if (f < 0)
-						x[u] = a.hist_in[(size_t)rx * (N1 - 1) + (unsigned)(f + (N1 - 1))];
+						xx[u] = a.hist_in[(size_t)rxp * (N1 - 1) + (unsigned)(f + (N1 - 1))];
 					else
-						x[u] = __ldg(reinterpret_cast<const float2*>(src) + f);
+						xx[u] = __ldg(reinterpret_cast<const float2*>(srcp) + f);
 				}
 				#pragma unroll
 				for (int u = 0; u < 2; u++) {
@@ -480,15 +505,15 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 					if (i < (unsigned)(N1 - 1)) {
 						if (f >= 0) {
 							float sn, cs;
-							lo3_sincos(((ph0 + (uint32_t)f * (uint32_t)step) << 1) + 0x80000000u, lo, sn, cs);
-							x[u] = mix(x[u], cs, sn);
+							lo3_sincos(((php + (uint32_t)f * (uint32_t)cfp.step) << 1) + 0x80000000u, lo, sn, cs);
+							xx[u] = mix(xx[u], cs, sn);
 						}
-						a.hist_out[(size_t)rx * (N1 - 1) + i] = x[u];
+						a.hist_out[(size_t)rxp * (N1 - 1) + i] = xx[u];
 					}
 				}
 			}
 			if (lane == 0)
-				a.st_out[rx].phase = phase_at(ph0, step, a.F);
+				a.st_out[rxp].phase = phase_at(php, cfp.step, a.F);
 		}
 	}
 	if (a.ts && blockIdx.x == 0 && tid == 0)
@@ -503,19 +528,21 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 
 typedef void (*V4Kernel)(const ChanArgs, const V4Args);
 
+constexpr int kV4Warps = 8;           // warps per CTA: two per scheduler (up to 255 registers per thread), ring of three stages
+
 struct V4Plan {
 	bool ok = false;
-	V4Kernel kernelW8 = nullptr;   // up to 8 warps per CTA (255 registers per thread), ring of three stages
-	V4Kernel kernelW16 = nullptr;  // up to kV4MaxWarps warps (128 registers), ring of two stages
-	int regsW8 = 0, regsW16 = 0;
+	V4Kernel kernel = nullptr;
+	int regs = 0;
 	int numSMs = 0;
 	unsigned n1 = 0, d1 = 0;
 	unsigned kskip = 0;          // outputs the prologue computes
-	unsigned stageBytes = 0, tapBytes = 0, scratchBytes = 0;
+	unsigned ap = 0;             // periods a run spends beyond its own outputs
+	unsigned stageBytes = 0, tapBytes = 0;
 	size_t smemMax = 0;
 	unsigned maxPerStream = 1;   // most receivers that share one tuner stream (v4_set_groups)
-	unsigned G = 0;              // WR_V4_G: warps per receiver (0 = by bank size)
-	bool ownScratch = true;      // WR_V4_SCRATCH=0: the prologue always borrows the ring (28 KB less shared memory on cfg3)
+	unsigned runs = 0;           // WR_V4_RUNS: runs per receiver (0 = fill the grid; 32 = one receiver per warp)
+	unsigned kmin = 0;           // WR_V4_KMIN: shortest run (0 = default)
 	bool pdl = true;
 };
 
@@ -523,44 +550,46 @@ template <int N1, int D1>
 inline void v4_fill(V4Plan &p)
 {
 	using G = V4Geo<N1, D1>;
-	p.kernelW8 = chan_kernel_v4<N1, D1, 8, 3>;
-	p.kernelW16 = chan_kernel_v4<N1, D1, kV4MaxWarps, 2>;
+	p.kernel = chan_kernel_v4<N1, D1, kV4Warps, 3>;
 	p.kskip = G::KSKIP;
+	p.ap = G::AP;
 	p.stageBytes = G::kStageBytes;
 	p.tapBytes = G::kTapBytes;
-	p.scratchBytes = (G::kScratchFrames * 8u + 15u) & ~15u;
 }
 
-// v4 serves the long-filter geometries of the BASELINE configs; it needs the v3 plan's table.
-inline int v4_init(V4Plan &p, const V3Plan &v3, int device, unsigned n1, unsigned d1)
+// the geometries v4 is instantiated for (the long filters of the BASELINE configs)
+inline bool v4_pick(V4Plan &p, unsigned n1, unsigned d1)
 {
-	p.ok = false;
 	p.n1 = n1;
 	p.d1 = d1;
 	if (n1 == 255 && d1 == 50) v4_fill<255, 50>(p);
 	else if (n1 == 127 && d1 == 50) v4_fill<127, 50>(p);
 	else if (n1 == 127 && d1 == 40) v4_fill<127, 40>(p);
-	else return WR_OK;
-	if (!v3.d_delta)
+	else return false;
+	if (const char *e = getenv("WR_V4_RUNS"))
+		p.runs = (unsigned)std::max(0, atoi(e));
+	if (const char *e = getenv("WR_V4_KMIN"))
+		p.kmin = (unsigned)std::max(0, atoi(e));
+	return true;
+}
+
+// v4 needs the v3 plan's table.
+inline int v4_init(V4Plan &p, const V3Plan &v3, int device, unsigned n1, unsigned d1)
+{
+	p.ok = false;
+	if (!v4_pick(p, n1, d1) || !v3.d_delta)
 		return WR_OK;
-	if (const char *e = getenv("WR_V4_G"))
-		p.G = (unsigned)std::max(0, atoi(e));
 	if (const char *e = getenv("WR_V3_PDL"))
 		p.pdl = atoi(e) != 0;
-	if (const char *e = getenv("WR_V4_SCRATCH"))
-		p.ownScratch = atoi(e) != 0;
 	cudaDeviceProp prop;
 	WR_CUDA(cudaGetDeviceProperties(&prop, device));
 	p.numSMs = prop.multiProcessorCount;
 	cudaFuncAttributes fa;
-	WR_CUDA(cudaFuncGetAttributes(&fa, p.kernelW8));
-	p.regsW8 = fa.numRegs;
+	WR_CUDA(cudaFuncGetAttributes(&fa, p.kernel));
+	p.regs = fa.numRegs;
 	// the opt-in limit covers static and dynamic shared memory together (the kernel's mbarrier is static)
 	p.smemMax = prop.sharedMemPerBlockOptin - ((fa.sharedSizeBytes + 255) & ~(size_t)255);
-	WR_CUDA(cudaFuncSetAttribute(p.kernelW8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemMax));
-	WR_CUDA(cudaFuncGetAttributes(&fa, p.kernelW16));
-	p.regsW16 = fa.numRegs;
-	WR_CUDA(cudaFuncSetAttribute(p.kernelW16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemMax));
+	WR_CUDA(cudaFuncSetAttribute(p.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemMax));
 	p.ok = true;
 	return WR_OK;
 }
@@ -575,11 +604,46 @@ inline void v4_set_groups(V4Plan &p, const RxConf *h_conf, unsigned R, unsigned 
 }
 
 struct V4Launch {
-	unsigned G, K, NS, warps, scratch;
-	bool w8;
+	unsigned warps;
+	unsigned runsPerRx, runLen, longRuns;   // n_r runs per receiver: `longRuns` of runLen + 1 outputs, then runLen
+	unsigned rounds;                        // rounds of 32 runs the busiest warp slot works through
+	unsigned grid;
 };
 
-// How a block of F frames would be cut; false if v4 does not serve it.
+// How R receivers x M1 outputs are cut into runs for a grid of numSMs x warps x 32 lanes: as
+// many runs per receiver as ONE round of the grid holds (more rounds only when the bank has more
+// receivers than that leaves room for 32 runs each), never shorter than kmin outputs.
+// A run of K outputs costs K + ap periods, so fewer, longer runs are cheaper per output -- but
+// a grid whose lanes are not all busy wastes more: the kernel's time is rounds * (K + ap).
+inline bool v4_cut(const V4Plan &p, unsigned R, unsigned M1, unsigned warps, V4Launch *out)
+{
+	const unsigned kmin = std::max(p.kskip + 1, p.kmin ? p.kmin : 2 * (p.ap + 1));
+	const unsigned nrMax = M1 / kmin;
+	if (!R || nrMax < 32u)
+		return false;
+	const unsigned long long lanes = (unsigned long long)p.numSMs * warps * 32u;
+	unsigned nr = p.runs;
+	if (nr == 0) {
+		unsigned long long q = 1;
+		while ((q * lanes) / R < 32u)
+			q++;
+		nr = (unsigned)std::min<unsigned long long>(nrMax, (q * lanes) / R);
+	}
+	nr = std::min(std::max(nr, 32u), nrMax);
+	const unsigned long long total = (unsigned long long)R * nr;
+	if (total > 0x7FFFFFFFull)
+		return false;
+	const unsigned long long warpRounds = (total + 31) / 32;
+	out->warps = warps;
+	out->runsPerRx = nr;
+	out->runLen = M1 / nr;
+	out->longRuns = M1 % nr;
+	out->grid = (unsigned)std::min<unsigned long long>((unsigned long long)p.numSMs, (warpRounds + warps - 1) / warps);
+	out->rounds = (unsigned)((warpRounds + (unsigned long long)out->grid * warps - 1) / ((unsigned long long)out->grid * warps));
+	return true;
+}
+
+// How a block of F frames would be launched; false if v4 does not serve it.
 inline bool v4_shape(const V4Plan &p, const V3Plan &v3, unsigned R, unsigned F, const void *iq, size_t stream_stride, bool forced, V4Launch *out)
 {
 	if (!p.ok || !v3.ok)          // (v3.ok: the table survived the compression)
@@ -591,38 +655,16 @@ inline bool v4_shape(const V4Plan &p, const V3Plan &v3, unsigned R, unsigned F, 
 	const unsigned M1 = F / p.d1;
 	if (F < p.n1 - 1 || M1 < 32u * 2u * p.kskip)
 		return false;
-	// warps per receiver: one, unless the bank is too small to give every SM a few warps that way
-	unsigned G = p.G;
-	if (G == 0) {
-		G = 1;
-		while ((unsigned long long)R * G < 4ull * (unsigned)p.numSMs && (M1 + 32u * 2u * G - 1) / (32u * 2u * G) >= 4u * p.kskip)
-			G *= 2;
-	}
-	unsigned K = (M1 + 32u * G - 1) / (32u * G);
-	if (K < p.kskip + 1)
-		return false;
-	const unsigned long long units = (unsigned long long)R * G;
-	if (units < (unsigned long long)p.numSMs && !forced)     // not enough work for a persistent grid of independent warps
-		return false;
-	unsigned warps = (unsigned)std::min<unsigned long long>(kV4MaxWarps, (units + p.numSMs - 1) / p.numSMs);
-	const bool w8 = warps <= 8;
-	const unsigned NS = w8 ? 3u : 2u;
+	unsigned warps = kV4Warps;
 	const size_t avail = p.smemMax - kV3TableBytes;
-	// with its own scratch the prologue runs while the first stages are already in flight; without,
-	// the ring serves as scratch (it must be large enough) and is filled afterwards
-	size_t perWarp = (size_t)NS * p.stageBytes + p.tapBytes + p.scratchBytes;
-	unsigned scratch = p.scratchBytes;
-	if (perWarp * warps > avail || (!p.ownScratch && (size_t)NS * p.stageBytes >= p.scratchBytes)) {
-		scratch = 0;
-		perWarp = (size_t)NS * p.stageBytes + p.tapBytes;
-		if ((size_t)NS * p.stageBytes < p.scratchBytes)
-			return false;
-		while (warps > 1 && perWarp * warps > avail)
-			warps--;
-		if (perWarp * warps > avail)
-			return false;
-	}
-	out->G = G; out->K = K; out->NS = NS; out->warps = warps; out->scratch = scratch; out->w8 = w8;
+	const size_t perWarp = (size_t)3 * p.stageBytes + 2 * (size_t)p.tapBytes;
+	while (warps > 1 && perWarp * warps > avail)
+		warps--;
+	if (perWarp * warps > avail || !v4_cut(p, R, M1, warps, out))
+		return false;
+	// not enough work for a persistent grid of independent warps: a warp per SM at least
+	if ((unsigned long long)R * out->runsPerRx < 32ull * (unsigned)p.numSMs && !forced)
+		return false;
 	return true;
 }
 
@@ -633,15 +675,15 @@ inline int v4_launch_chan(V4Plan &p, const V3Plan &v3, const V4Launch &L, ChanAr
 	v.eps = v3.coef.eps;
 	v.negzero = -0.0f;
 	v.prmtHi = 0x4B00u;
-	v.G = L.G;
-	v.K = L.K;
-	v.nUnits = R * L.G;
-	v.scratchBytes = L.scratch;
-	const size_t smem = kV3TableBytes + (size_t)L.warps * ((size_t)L.NS * p.stageBytes + p.tapBytes + L.scratch);
-	const unsigned grid = (unsigned)std::min<unsigned long long>((v.nUnits + L.warps - 1) / L.warps, (unsigned long long)p.numSMs);
+	v.runsPerRx = L.runsPerRx;
+	v.runLen = L.runLen;
+	v.longRuns = L.longRuns;
+	v.totalRuns = R * L.runsPerRx;
+	v.R = R;
+	const size_t smem = kV3TableBytes + (size_t)L.warps * ((size_t)3 * p.stageBytes + 2 * (size_t)p.tapBytes);
 	cudaLaunchConfig_t cfg = {};
 	cudaLaunchAttribute attr[1];
-	cfg.gridDim = dim3(grid);
+	cfg.gridDim = dim3(L.grid);
 	cfg.blockDim = dim3(L.warps * 32);
 	cfg.dynamicSmemBytes = smem;
 	cfg.stream = st;
@@ -649,13 +691,13 @@ inline int v4_launch_chan(V4Plan &p, const V3Plan &v3, const V4Launch &L, ChanAr
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = p.pdl ? 1 : 0;
-	cudaError_t e = cudaLaunchKernelEx(&cfg, L.w8 ? p.kernelW8 : p.kernelW16, (const ChanArgs)ca, (const V4Args)v);
+	cudaError_t e = cudaLaunchKernelEx(&cfg, p.kernel, (const ChanArgs)ca, (const V4Args)v);
 	(*launches)++;
 	if (e == cudaSuccess)
 		e = cudaGetLastError();
 	if (e != cudaSuccess) {
 		wr::set_error("chan_kernel_v4 launch (grid %u, %u warps, %zu bytes of shared memory): %s",
-				grid, L.warps, smem, cudaGetErrorString(e));
+				L.grid, L.warps, smem, cudaGetErrorString(e));
 		return WR_ECUDA;
 	}
 	return WR_OK;
