@@ -1,8 +1,14 @@
 """The oracle's restatements of the steps either side of the path: byte-to-sample
 conversion, waterfall palette index, encoder sample format.  These rows come from reference files
 that cannot be built or run here (librtlsdr, LAME, a browser), so they are pinned against values
-derived by hand from the reference expressions -- "parity unpinned" beyond that, see DESIGN.md."""
+derived from the reference expressions in exact rational arithmetic with hand-written IEEE rounding
+(scripts/make_palette_fixture.py -> tests/golden/palette_edges.npz, lame_scale.npz): every palette
+edge +-3 ULP, clamps, non-finite bins; random bit patterns, subnormals and overflow for the scale."""
+import os
+
 import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 from helpers import u8_to_iq
 
@@ -36,3 +42,18 @@ def test_lame_scale(wro):
     got = wro.lame_scale(x)
     assert np.array_equal(got, (x.astype(np.float64) * 32768.0).astype(np.float32))
     assert got[2] == 16384.0 and got[3] == -32768.0 and got[5] == 1.0
+
+
+def test_waterfall_index_against_the_rational_fixture(wro):
+    """html/waterfall.js:95-101 + waterfallhandler.cxx:62-68 in exact arithmetic: 257 edges x 7 neighbours."""
+    d = np.load(os.path.join(GOLDEN, "palette_edges.npz"))
+    assert len(d["db"]) >= 257 * 7 and len(set(d["index"].tolist())) == 256
+    assert np.array_equal(wro.waterfall_index(d["db"]), d["index"])
+
+
+def test_lame_scale_against_the_rational_fixture(wro):
+    """src/web/mp3encoder.cxx:66-68 in exact arithmetic, bit for bit (signed zeros, subnormals, overflow)."""
+    d = np.load(os.path.join(GOLDEN, "lame_scale.npz"))
+    got = wro.lame_scale(d["x"])
+    assert np.array_equal(got.view(np.uint32), d["y"].view(np.uint32))
+    assert np.isinf(d["y"]).sum() > 100 and (np.abs(d["x"]) < 1.2e-38).sum() > 10

@@ -9,6 +9,8 @@ Tolerances
     against the installed libm, so FM is BIT-EXACT too on a glibc box (helpers.fm_exact()); only on a
     box with a different libm do the FM checks fall back to helpers.FM_MAX_ULP / FM_AUDIO_TOL.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -476,6 +478,17 @@ def test_waterfall_palette_index(wro):
         st.close()
 
 
+def test_waterfall_palette_index_against_the_rational_fixture():
+    """The device palette kernel against tests/golden/palette_edges.npz -- indices derived from
+    html/waterfall.js:95-101 in exact rational arithmetic (scripts/make_palette_fixture.py), no oracle in between."""
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "palette_edges.npz"))
+    st = capi.Stage()
+    try:
+        assert np.array_equal(st.palette(d["db"]), d["index"])
+    finally:
+        st.close()
+
+
 def test_spectrum_palette_of_latest_row(wro):
     sp = capi.Spectrum(512, max_frames=4096)
     try:
@@ -725,14 +738,15 @@ def test_bank_cfg3_full_size(wro):
     """BASELINE config 3 at FULL size: 1024 independent AM streams x 102400 frames, 255 taps, decim 50,
     fed as raw bytes (210 MB per block on the host instead of 839 MB).  Two blocks.  Size-independent
     property: streams 512..1023 repeat streams 0..511 and the receivers on them share IF and taps, so
-    their audio must be bit-identical; 6 receivers spread over the bank are checked against the oracle."""
+    their audio must be bit-identical; 32 receivers spread over the bank are checked against the oracle."""
     w = synth.WORKLOADS["cfg3"]
     R, T, F = w["n_rx"], w["n_streams"], w["frames"]
     bank, t1, t2, ifs, modes = _full_size_bank(w, 31)
     try:
         for r in range(R // 2, R):
             bank.set_if(r, int(ifs[r - R // 2]), w["fs"])
-        picks = [0, 1, 255, 511, 700, 1023]
+        picks = sorted(set([0, 1, 255, 511, 512, 700, 1022, 1023] + list(range(17, R, 41))))[:32]
+        assert len(picks) == 32
         orx = {r: wro.Rx(w["fs"], int(ifs[r % (R // 2)]), t1, w["d1"], int(modes[r]), t2, w["d2"]) for r in picks}
         rng = np.random.default_rng(32)
         for b in range(2):
@@ -745,6 +759,40 @@ def test_bank_cfg3_full_size(wro):
                 assert_biteq(audio[r], orx[r].process(u8_to_iq(u8[r]).ravel()), f"cfg3 full rx{r} b{b}")
             del u8, half
         assert bank.variant_in_use() == 3
+    finally:
+        bank.close()
+
+
+def test_bank_cfg3_full_size_float_one_launch(wro):
+    """BASELINE config 3 at FULL size as bench.py runs it: float IQ resident in HBM, ONE launch per block of
+    the streaming channel kernel (v4: every receiver cut into 37 runs of 55/56 outputs, a warp's 32 runs
+    straddling two receivers).  Two blocks (carried NCO phase and both FIR histories); 40 receivers
+    against the oracle -- the first and last of the bank, both sides of warp boundaries (run 32 s falls
+    into receiver (32 s) // 37), and a spread over the rest."""
+    import torch
+    w = synth.WORKLOADS["cfg3"]
+    R, T, F = w["n_rx"], w["n_streams"], w["frames"]
+    bank, t1, t2, ifs, modes = _full_size_bank(w, 33)
+    try:
+        picks = sorted(set([0, 1, 2, 6, 7, 36, 37, 863, 864, 865, 1021, 1022, 1023] + list(range(11, R, 37))))[:40]
+        assert len(picks) == 40
+        orx = {r: wro.Rx(w["fs"], int(ifs[r]), t1, w["d1"], int(modes[r]), t2, w["d2"]) for r in picks}
+        m2 = F // w["d1"] // w["d2"]
+        stream = torch.cuda.current_stream()
+        g = torch.Generator(device="cuda").manual_seed(34)
+        for b in range(2):
+            # the RTL-SDR lattice (b - 128) / 128, generated on the device; only the picked streams come back
+            d_iq = (torch.randint(0, 256, (T, F, 2), device="cuda", generator=g, dtype=torch.int16).float() - 128.0) / 128.0
+            d_audio = torch.zeros(R, m2, device="cuda")
+            bank.process_device(d_iq.data_ptr(), F, F, d_audio.data_ptr(), m2, stream.cuda_stream)
+            bank.sync()
+            torch.cuda.synchronize()
+            audio = d_audio.cpu().numpy()
+            for r in picks:
+                assert_biteq(audio[r], orx[r].process(d_iq[r].cpu().numpy().ravel()), f"cfg3 float full rx{r} b{b}")
+            del d_iq, d_audio
+        assert bank.variant_in_use() == 4
+        assert bank.get_phase(5) == (capi.phase_step(int(ifs[5]), w["fs"]) * F * 2) & 0x7FFFFFFF
     finally:
         bank.close()
 
