@@ -186,7 +186,11 @@ int wr_rx_get_history(wr_bank *b, unsigned rx, int stage, float *out, unsigned n
 int wr_rx_set_history(wr_bank *b, unsigned rx, int stage, const float *in, unsigned nfloats);
 
 /* Same, with input and output already in HBM on the bank's device; asynchronous on
- * cuda_stream (a cudaStream_t; NULL = the bank's own stream). */
+ * cuda_stream (a cudaStream_t; NULL = the bank's own stream, wr_bank_stream).  The bank's stream
+ * is non-blocking: it does NOT synchronise with the legacy default stream, whose handle is also
+ * NULL and which therefore cannot be named here -- a caller that produces iq_dev or consumes
+ * audio_dev with its own kernels passes the stream those kernels run in, or works in
+ * wr_bank_stream(b). */
 int wr_bank_process_device(wr_bank *b, const float *iq_dev, size_t stream_stride_frames,
 		unsigned nframes, float *audio_dev, size_t audio_stride, void *cuda_stream);
 

@@ -341,13 +341,15 @@ def test_bank_device_resident_path(wro):
             b.set_mode(r, "AM")
             rx.append(wro.Rx(fs, int(ifs[r]), taps1, 10, "AM", taps2, 5))
         m2 = F // 50
-        stream = torch.cuda.current_stream()
+        # a torch stream of its own: handle 0 (torch's default stream) would mean "the bank's stream" to the C ABI
+        stream = torch.cuda.Stream()
         for blk in range(3):
             iq = np.stack([synth.lattice_noise(F, stream=t, start=blk * F) for t in range(T)])
-            d_iq = torch.from_numpy(iq).cuda()
-            d_audio = torch.zeros(R, m2, device="cuda")
-            b.process_device(d_iq.data_ptr(), F, F, d_audio.data_ptr(), m2, stream.cuda_stream)
-            got = d_audio.cpu().numpy()
+            with torch.cuda.stream(stream):
+                d_iq = torch.from_numpy(iq).cuda()
+                d_audio = torch.zeros(R, m2, device="cuda")
+                b.process_device(d_iq.data_ptr(), F, F, d_audio.data_ptr(), m2, stream.cuda_stream)
+                got = d_audio.cpu().numpy()
             for r in range(R):
                 assert_biteq(got[r], rx[r].process(iq[r % T]), f"device path rx{r} b{blk}")
         assert b.launch_count() >= 6
@@ -579,17 +581,18 @@ def test_bank_v3_ragged_block_lengths(wro, geom, F):
 
 # ------------------------------------------------------------------ v4: streaming FIR over independent streams ----
 
-@pytest.mark.parametrize("warps_per_rx", [0, 2])
+@pytest.mark.parametrize("runs_per_rx", [0, 32, 41])
 @pytest.mark.parametrize("F,n1,d1,n2,d2,R", [(25600, 255, 50, 64, 1, 40), (20050, 255, 50, 64, 1, 7), (102400, 255, 50, 64, 1, 5),
                                              (12800, 127, 50, 64, 1, 9), (16000, 127, 40, 64, 5, 12), (21338, 127, 40, 64, 5, 3)])
-def test_bank_v4_streaming_fir(wro, monkeypatch, F, n1, d1, n2, d2, R, warps_per_rx):
+def test_bank_v4_streaming_fir(wro, monkeypatch, F, n1, d1, n2, d2, R, runs_per_rx):
     """The v4 channel kernel (one thread streams over a run of consecutive outputs, wr_kernels_v4.cuh) on
     independent streams: every receiver, every stage, three blocks -- so the gather prologue (outputs whose
     windows reach into the carried history), the runs' overlap, ragged ends (blocks that are not a multiple
-    of the decimation, lanes without outputs) and the epilogue's carried state are all exercised; with one
-    and with two warps per receiver."""
-    if warps_per_rx:
-        monkeypatch.setenv("WR_V4_G", str(warps_per_rx))
+    of the decimation, lanes without outputs) and the epilogue's carried state are all exercised; with the
+    cut the host picks for the grid, with one receiver per warp (32 runs) and with 41 runs per receiver
+    (warps that straddle two receivers, runs of two lengths)."""
+    if runs_per_rx:
+        monkeypatch.setenv("WR_V4_RUNS", str(runs_per_rx))
     fs = 2400000
     run_bank_vs_oracle(wro, 4, fs, F, R, synth.receiver_ifs(R, fs), [r % 4 for r in range(R)], n1, d1, n2, d2, 3, seed=F + R)
 
@@ -778,19 +781,21 @@ def test_bank_cfg3_full_size_float_one_launch(wro):
         assert len(picks) == 40
         orx = {r: wro.Rx(w["fs"], int(ifs[r]), t1, w["d1"], int(modes[r]), t2, w["d2"]) for r in picks}
         m2 = F // w["d1"] // w["d2"]
-        stream = torch.cuda.current_stream()
+        # torch works in the bank's own stream (torch's default stream is handle 0, which the C ABI reads as
+        # "the bank's stream" -- and that one does not synchronise with the legacy default stream)
+        stream = torch.cuda.ExternalStream(bank.stream())
         g = torch.Generator(device="cuda").manual_seed(34)
         for b in range(2):
-            # the RTL-SDR lattice (b - 128) / 128, generated on the device; only the picked streams come back
-            d_iq = (torch.randint(0, 256, (T, F, 2), device="cuda", generator=g, dtype=torch.int16).float() - 128.0) / 128.0
-            d_audio = torch.zeros(R, m2, device="cuda")
-            bank.process_device(d_iq.data_ptr(), F, F, d_audio.data_ptr(), m2, stream.cuda_stream)
-            bank.sync()
-            torch.cuda.synchronize()
-            audio = d_audio.cpu().numpy()
-            for r in picks:
-                assert_biteq(audio[r], orx[r].process(d_iq[r].cpu().numpy().ravel()), f"cfg3 float full rx{r} b{b}")
-            del d_iq, d_audio
+            with torch.cuda.stream(stream):
+                # the RTL-SDR lattice (b - 128) / 128, generated on the device; only the picked streams come back
+                d_iq = (torch.randint(0, 256, (T, F, 2), device="cuda", generator=g, dtype=torch.int16).float() - 128.0) / 128.0
+                d_audio = torch.full((R, m2), 7.0, device="cuda")
+                bank.process_device(d_iq.data_ptr(), F, F, d_audio.data_ptr(), m2, stream.cuda_stream)
+                audio = d_audio.cpu().numpy()
+                for r in picks:
+                    assert_biteq(audio[r], orx[r].process(d_iq[r].cpu().numpy().ravel()), f"cfg3 float full rx{r} b{b}")
+                assert not (audio == 7.0).any()
+                del d_iq, d_audio
         assert bank.variant_in_use() == 4
         assert bank.get_phase(5) == (capi.phase_step(int(ifs[5]), w["fs"]) * F * 2) & 0x7FFFFFFF
     finally:
