@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Measured error of the device spectrum (float32, spectrum_kernel_v3) against the oracle's float64
+transform, by bin level below the frame's peak -- the numbers behind the dB tolerance of the
+spectrum parity tests (VERDICT r01 "FFT dB tolerance").  Runs on the GPU box:
+    python scripts/fft_db_hist.py > profiles/r02_fft_db_error.txt
+Inputs: 8192-point frames, hop 4096 (BASELINE cfg4) of (a) the RTL-SDR lattice noise the bench uses
+(flat spectrum: every bin within ~15 dB of the peak) and (b) carriers 60 dB above a weak noise
+floor (a wide dynamic range: most bins 60-120 dB below the peak)."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import wro  # noqa: E402  (the checker; this script is measurement tooling, not product)
+from webradio_b200 import capi, synth  # noqa: E402
+
+N, HOP, F = 8192, 4096, 8192 * 12
+
+
+def report(name, iq):
+    sp = capi.Spectrum(N, hop=HOP, max_frames=F)
+    ref = wro.Spectrum(N, HOP)
+    try:
+        got = np.asarray(sp.process(iq[None])[0], np.float64)
+        want = np.asarray(ref.process(iq), np.float64)
+    finally:
+        sp.close()
+    n = min(len(got), len(want))
+    got, want = got[:n], want[:n]
+    mag_g, mag_w = 10 ** (got / 20), 10 ** (want / 20)
+    peak = mag_w.max(axis=1, keepdims=True)
+    rel = np.abs(mag_g - mag_w) / peak
+    below = 20 * np.log10(peak / np.maximum(mag_w, 1e-300))
+    ddb = np.abs(got - want)
+    print(f"== {name}: {n} frames of {N} points, hop {HOP}")
+    print(f"max |mag - mag_ref| / frame peak = {rel.max():.3e}   (tolerance asserted in tests: 1e-05)")
+    print("bins by level below the frame peak:   count     median |dB err|      99.9 %        max")
+    for lo in range(0, 140, 20):
+        m = (below >= lo) & (below < lo + 20)
+        if m.any():
+            e = ddb[m]
+            print(f"  {lo:3d} .. {lo + 20:3d} dB                  {m.sum():9d}      {np.median(e):.3e}    {np.quantile(e, 0.999):.3e}   {e.max():.3e}")
+    print()
+
+
+def main():
+    fs = 2400000
+    report("lattice noise (the bench's cfg4 input)", synth.lattice_noise(F, stream=4))
+    t = np.arange(F)
+    x = 0.4 * np.exp(2j * np.pi * 0.1037 * t) + 0.3 * np.exp(-2j * np.pi * 0.3171 * t) + 0.0004 * np.exp(2j * np.pi * 0.2203 * t)
+    rng = np.random.default_rng(9)
+    x = x + 2e-5 * (rng.standard_normal(F) + 1j * rng.standard_normal(F))
+    iq = np.empty(2 * F, np.float32)
+    iq[0::2], iq[1::2] = x.real, x.imag
+    report("two carriers + a -60 dB carrier over a -90 dB noise floor", iq)
+    print("A float32 transform of 8192 points carries ~1e-6 of the frame peak as rounding noise into every bin:")
+    print("bins within 40 dB of the peak agree to ~1e-3 dB, bins 100 dB down only to ~1 dB -- whatever the kernel.")
+
+
+if __name__ == "__main__":
+    main()
