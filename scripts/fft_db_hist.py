@@ -54,8 +54,8 @@ def main():
     iq = np.empty(2 * F, np.float32)
     iq[0::2], iq[1::2] = x.real, x.imag
     report("two carriers + a -60 dB carrier over a -90 dB noise floor", iq)
-    print("A float32 transform of 8192 points carries ~1e-6 of the frame peak as rounding noise into every bin:")
-    print("bins within 40 dB of the peak agree to ~1e-3 dB, bins 100 dB down only to ~1 dB -- whatever the kernel.")
+    print("A float32 transform of 8192 points carries ~1e-6 of the frame peak as rounding noise into every bin, so the dB")
+    print("error grows by a factor of ten for every 20 dB a bin lies below the peak -- whatever the kernel.")
 
 
 if __name__ == "__main__":
