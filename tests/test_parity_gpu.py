@@ -802,6 +802,39 @@ def test_bank_cfg3_full_size_float_one_launch(wro):
         bank.close()
 
 
+def test_bank_audio_fir_sliding_window_ragged(wro):
+    """The audio FIR's sliding-window path (large banks at the demodulator's own rate: tiles of 1024 outputs,
+    eight per thread) on a block whose last tile is ragged (1203 outputs = 1024 + 179), all four modes, two
+    blocks (carried audio history); 24 receivers against the oracle, raw bytes in."""
+    fs, R, F = 2400000, 600, 60163
+    rng = np.random.default_rng(77)
+    t1 = (rng.uniform(-1, 1, 127) / 127 * 4).astype(np.float32)
+    t2 = (rng.uniform(-1, 1, 64) / 64 * 4).astype(np.float32)
+    ifs = synth.receiver_ifs(R, fs)
+    bank = capi.Bank(R, R, F, 127, 50, 64, 1)
+    try:
+        for r in range(R):
+            bank.set_taps(r, 0, t1)
+            bank.set_taps(r, 1, t2)
+            bank.set_if(r, int(ifs[r]), fs)
+            bank.set_mode(r, r % 4)
+            bank.set_stream(r, r)
+        picks = list(range(0, R, 26)) + [R - 1]
+        orx = {r: wro.Rx(fs, int(ifs[r]), t1, 50, r % 4, t2, 1) for r in picks}
+        for b in range(2):
+            u8 = rng.integers(0, 256, (R, F, 2), dtype=np.uint8)
+            audio = bank.process_u8(u8)
+            assert audio.shape == (R, F // 50)
+            for r in picks:
+                want = orx[r].process(u8_to_iq(u8[r]).ravel())
+                if r % 4 == capi.FM:
+                    assert_fm(audio[r], want, f"sliding window rx{r} b{b}", audio=True)
+                else:
+                    assert_biteq(audio[r], want, f"sliding window rx{r} b{b}")
+    finally:
+        bank.close()
+
+
 def test_bank_cfg5_full_size(wro):
     """BASELINE config 5, one GPU's share at FULL size: 16 tuners x 64 mixed-mode receivers, 409600-frame
     blocks at 10 MSPS, 127 taps /40, 64 taps /5.  Two blocks; 12 receivers (all four modes, several

@@ -205,6 +205,7 @@ struct wr_bank {
 	int demodPerSM = -1;        // WR_DEMOD_PER_SM: > 0 = persistent demodulator grid of that many CTAs per SM, 0 = one CTA per tile, < 0 = by bank size
 	unsigned syncSplit = 0;     // WR_SYNC_SPLIT: pieces a synchronous wr_bank_process call is cut into (0 = by size)
 	int waitLate = 1;           // WR_WAIT_LATE: the channel kernel runs under the previous block's demodulator kernel
+	bool bigTiles = true;       // WR_DEMOD_BIG_TILES=0: never the 1024-output tiles of the sliding-window audio FIR
 	// the device address of a pinned output buffer (OUT_DIRECT): small cache of the runtime's answer
 	struct HostMap { const void *host; void *dev; size_t bytes; } hostMap[8] = {};
 	int hostMapNext = 0;
@@ -511,6 +512,12 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 		da.TK = (unsigned long long)b->R * ((M2 + 255) / 256) >= 16ull * (unsigned)b->numSMs ? 256 : 128;
 		while (da.TK > 16 && (unsigned long long)b->R * ((M2 + da.TK - 1) / da.TK) < 296ull)
 			da.TK /= 2;
+		// A large bank at the demodulator's own rate (cfg3): tiles of 1024 outputs, eight per thread
+		// through registers (demod_audio_kernel_v2's sliding-window path) -- a sixteenth of the
+		// samples is demodulated twice instead of a quarter, and the grid is one wave.
+		if (b->d2 == 1 && (b->n2 & 3u) == 0 && b->bigTiles && M2 >= 1024
+				&& (unsigned long long)b->R * ((M2 + 1023) / 1024) >= 8ull * (unsigned)b->numSMs)
+			da.TK = 1024;
 		da.ntiles = (M2 + da.TK - 1) / da.TK;
 		da.out_scale = b->outScale;
 		da.negzero = -0.0f;
@@ -775,6 +782,8 @@ wr_bank *wr_bank_create(int device, unsigned n_streams, unsigned n_receivers, un
 		b->demodPerSM = atoi(e);
 	if (const char *e = getenv("WR_WAIT_LATE"))
 		b->waitLate = atoi(e) != 0;
+	if (const char *e = getenv("WR_DEMOD_BIG_TILES"))
+		b->bigTiles = atoi(e) != 0;
 	if (const char *e = getenv("WR_SYNC_SPLIT"))
 		b->syncSplit = (unsigned)std::max(0, atoi(e));
 	if ((b->tracePath = getenv("WR_TRACE")) != nullptr) {

@@ -547,6 +547,49 @@ __global__ void __launch_bounds__(kThreads, 7) demod_audio_kernel_v2(const Demod
 	// each output's taps in the reference's order (lowpass.cxx:151-159), products and sums rounded
 	// separately (mul2_rn_exact), taps four per 128-bit load.
 	const float2 nz = make_float2(a.negzero, a.negzero);
+	if (d2 == 1 && (n2 & 3u) == 0 && a.TK >= 8u * 96u) {
+		// Large tiles at the demodulator's own rate (cfg3: 1024 receivers x 2048 samples): EIGHT
+		// consecutive outputs per thread over a window of samples that slides through registers --
+		// per four taps one 128-bit load of samples and one of taps serve 32 output-taps (the
+		// two-outputs path below: 2.25 loads per 2), each output in its own accumulator and the
+		// reference's order (taps ascending, products and sums rounded separately).  Outputs past
+		// the tile's end read the tap buffer behind the window and are not stored.
+		for (unsigned o = tid * 8u; o < nout; o += kThreads * 8u) {
+			const float *p = s + o;
+			float acc[8], w[12];
+			#pragma unroll
+			for (int i = 0; i < 8; i++)
+				acc[i] = 0.0f;
+			{
+				const float4 w0 = *reinterpret_cast<const float4*>(p), w1 = *reinterpret_cast<const float4*>(p + 4);
+				w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w;
+				w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+			}
+			#pragma unroll 4
+			for (unsigned j = 0; j < n2; j += 4) {
+				const float4 wn = *reinterpret_cast<const float4*>(p + j + 8);
+				const float4 c = *reinterpret_cast<const float4*>(rt + j);
+				w[8] = wn.x; w[9] = wn.y; w[10] = wn.z; w[11] = wn.w;
+				const float cc[4] = { c.x, c.y, c.z, c.w };
+				#pragma unroll
+				for (int t = 0; t < 4; t++) {
+					#pragma unroll
+					for (int i = 0; i < 8; i++)
+						acc[i] = __fadd_rn(acc[i], __fmul_rn(cc[t], w[i + t]));
+				}
+				#pragma unroll
+				for (int i = 0; i < 8; i++)
+					w[i] = w[i + 4];
+			}
+			float *dst = a.audio + (size_t)r * a.audio_stride + m0 + o;
+			#pragma unroll
+			for (int i = 0; i < 8; i++)
+				if (o + (unsigned)i < nout)
+					dst[i] = __fmul_rn(acc[i], a.out_scale);
+		}
+		__syncthreads();
+		continue;
+	}
 	const unsigned H = (nout + 1) / 2;
 	for (unsigned o = tid; o < H; o += kThreads) {
 		const bool two = o + H < nout;
