@@ -16,6 +16,7 @@
 #include <cstring>
 #include <ctime>
 #include <mutex>
+#include <cstdio>
 #include <vector>
 
 #ifndef M_PI
@@ -205,6 +206,7 @@ struct wr_bank {
 	int demodPerSM = -1;        // WR_DEMOD_PER_SM: > 0 = persistent demodulator grid of that many CTAs per SM, 0 = one CTA per tile, < 0 = by bank size
 	unsigned syncSplit = 0;     // WR_SYNC_SPLIT: pieces a synchronous wr_bank_process call is cut into (0 = by size)
 	int waitLate = 1;           // WR_WAIT_LATE: the channel kernel runs under the previous block's demodulator kernel
+	bool warnedSlow = false;    // the one-line notice about an un-instantiated geometry has been printed
 	bool bigTiles = true;       // WR_DEMOD_BIG_TILES=0: never the 1024-output tiles of the sliding-window audio FIR
 	// the device address of a pinned output buffer (OUT_DIRECT): small cache of the runtime's answer
 	struct HostMap { const void *host; void *dev; size_t bytes; } hostMap[8] = {};
@@ -412,6 +414,16 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 	if (b->variant == 2 && !wrd::v2_supported(b->v2)) {
 		wr::set_error("v2 kernels do not support this geometry (n1=%u d1=%u)", b->n1, b->d1);
 		return WR_EINVAL;
+	}
+	if (!useV4 && !useV3 && !b->v3.ok && !b->warnedSlow && b->variant == 0) {
+		// Say so ONCE when a geometry lands on the older kernel families: v3/v4 are instantiated for
+		// the BASELINE geometries only (profiles/README.md has the per-geometry throughput table).
+		// (v3.ok is also false for an NCO table the 16-bit compression cannot represent.)
+		b->warnedSlow = true;
+		if (!getenv("WEBRADIO_B200_QUIET"))
+			fprintf(stderr, "webradio_b200: channel filter of %u taps, decimation %u has no fused v3/v4 kernel: using the %s "
+					"kernels (1.8-5x slower; instantiated geometries: 64/10, 64/8, 127/50, 127/40, 255/50)\n",
+					b->n1, b->d1, useV2 ? "v2 (tiled)" : "v1 (generic)");
 	}
 	if (useV2 && !b->d_chan)
 		WR_CUDA(cudaMalloc(&b->d_chan, 2 * sizeof(float2) * (size_t)b->R * std::max(1u, b->maxM1)));
