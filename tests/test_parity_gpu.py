@@ -398,6 +398,35 @@ def test_spectrum_rows_vs_oracle(wro, n, hop, T):
             spectrum_close(sp.get(t), ors[t].get(), "getSpectrum")
 
 
+@pytest.mark.parametrize("hop", [4096, 8192])
+@pytest.mark.parametrize("family", ["v4", "v3", "v2"])
+def test_spectrum_8192_kernel_families(wro, monkeypatch, family, hop):
+    """The three kernels that serve 8192-point transforms -- v4 (two CTAs per SM, the 32 rows of the radix-32
+    pass in two halves, ring of the frame's own chunks), v3 (one CTA per SM, ring of hop + 1 chunks) and v2
+    (one transform per CTA) -- on runs of many rows, two blocks (a partial frame carried over), both hops."""
+    if family == "v3":
+        monkeypatch.setenv("WR_FFT_V4", "0")
+    if family == "v2":
+        monkeypatch.setenv("WR_FFT_V3", "0")
+    n, T = 8192, 2
+    F = 21 * 4096 + 1000
+    sp = capi.Spectrum(n, hop, T, max_frames=F)
+    ors = [wro.Spectrum(n, hop) for _ in range(T)]
+    try:
+        for b in range(2):
+            iq = np.stack([synth.structured(F, 2400000, [250000 + 3000 * t, -810000], [0, 1], start=b * F,
+                                            noise_db=-35.0, stream=t) for t in range(T)])
+            rows = sp.process(iq)
+            for t in range(T):
+                want = ors[t].process(iq[t])
+                assert rows.shape[1] == want.shape[0] and want.shape[0] >= 10
+                for m in range(want.shape[0]):
+                    spectrum_close(rows[t, m], want[m], f"{family} hop={hop} stream {t} block {b} row {m}")
+                spectrum_close(sp.get(t), ors[t].get(), "getSpectrum")
+    finally:
+        sp.close()
+
+
 def test_spectrum_before_first_frame():
     sp = capi.Spectrum(512)
     assert np.all(np.isneginf(sp.get(0)))  # reference: outbuf is zero before the first transform

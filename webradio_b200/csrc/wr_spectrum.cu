@@ -427,6 +427,160 @@ __global__ void __launch_bounds__(256) spectrum_kernel_v3(const SpecArgs3 g)
 	}
 }
 
+// ---- v4: 8192-point transforms, TWO CTAs per SM ------------------------------------------------
+// v3 keeps one CTA of eight warps per SM (64 KB work buffer + 96 KB ring): two warps per scheduler
+// that meet at four block-wide barriers per frame, the schedulers 73 % busy by the cost model of
+// DESIGN.md 5.0.  Here the 32 rows the radix-32 pass produces go through passes 2 and 3 in two halves
+// of 16 rows (they are independent 256-point transforms), so the work buffer is 33 KB, and the
+// ring holds just the frame's own chunks (the slot of the oldest chunk is handed to the copy for
+// the next frame as soon as pass 1 has read it; it lands under passes 2 and 3): 100 KB per CTA,
+// two CTAs per SM, four warps per scheduler -- one CTA computes while the other waits at a barrier
+// or for its chunk.  The second half's rows wait in registers; the window is re-read (L1/L2) per
+// frame instead of living in 32 registers.
+template <int C>     // C = N / hop: 1 or 2
+__global__ void __launch_bounds__(256, 2) spectrum_kernel_v4(const SpecArgs3 g)
+{
+	extern __shared__ __align__(16) float2 wr_fft_smem[];
+	const SpecArgs &a = g.a;
+	constexpr int R1 = 32, RH = 16;
+	constexpr unsigned N = R1 * 256, HOP = N / C, NSLOT = C;
+	float2 *sm = wr_fft_smem;                               // work buffer, RH rows of kRowPitch
+	float2 *tw2 = wr_fft_smem + RH * kRowPitch;             // pass-2 twiddles
+	float2 *ring = tw2 + 256;                               // NSLOT chunks of HOP samples
+	__shared__ __align__(8) unsigned long long wr_spec_bars4[NSLOT];
+	const unsigned tid = threadIdx.x;
+	const uint32_t bar32 = (uint32_t)__cvta_generic_to_shared(wr_spec_bars4);
+	const uint32_t ring32 = (uint32_t)__cvta_generic_to_shared(ring);
+	if (tid == 0) {
+		for (unsigned i = 0; i < NSLOT; i++)
+			spec_mbar_init(bar32 + 8u * i, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	tw2[tid] = __ldg(a.twiddle + ((((tid & 15) * (tid >> 4)) & 255) * R1));
+	const float2 w1 = __ldg(a.twiddle + tid);               // W_N^tid: row k1 of pass 1 is scaled by w1^k1
+	const float2 w1h = __ldg(a.twiddle + RH * tid);         // w1^16, where the second half begins
+	__syncthreads();
+
+	const unsigned nrows3 = a.nrows - g.row0;
+	const unsigned totalRuns = g.runsPerStream * g.nStreams;
+	unsigned phases = 0;                                    // bit s: parity of the next completion of slot s to wait for
+	for (unsigned run = blockIdx.x; run < totalRuns; run += gridDim.x) {
+		const unsigned t = run / g.runsPerStream;
+		const unsigned r0 = (run - t * g.runsPerStream) * g.rowsPerRun;
+		const unsigned nr = min(g.rowsPerRun, nrows3 - r0);
+		const unsigned mFirst = g.row0 + r0;
+		const float2 *src = a.in + (size_t)t * a.in_stride + ((size_t)mFirst * HOP - a.ncarry);
+		const unsigned nchunks = nr + C - 1;
+		if (tid == 0) {
+			for (unsigned c = 0; c < NSLOT && c < nchunks; c++)
+				spec_bulk_load(ring32 + c * HOP * 8u, src + (size_t)c * HOP, HOP * 8u, bar32 + 8u * c);
+		}
+		for (unsigned f = 0; f < nr; f++) {
+			const unsigned m = mFirst + f;
+			// ---- pass 1: window (fetched before the wait), the frame's chunks, radix-32 ----
+			float2 v[R1];
+			{
+				float win[R1];
+				#pragma unroll
+				for (int j = 0; j < R1; j++)
+					win[j] = __ldg(a.window + tid + 256u * j);
+				#pragma unroll
+				for (unsigned c = 0; c < (unsigned)C; c++) {
+					const unsigned slot = (f + c) % NSLOT;
+					if (c == (unsigned)C - 1 || f == 0) {
+						spec_mbar_wait(bar32 + 8u * slot, (phases >> slot) & 1u);
+						phases ^= 1u << slot;
+					}
+					const float2 *chunk = ring + slot * HOP;
+					#pragma unroll
+					for (int j = 0; j < R1 / C; j++)
+						v[c * (R1 / C) + j] = chunk[tid + 256u * j];
+				}
+				#pragma unroll
+				for (int j = 0; j < R1; j++) {
+					// inbuf[n] *= window[n] (spectrumsink.cxx:110-113): both components in one packed multiply
+					asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&v[j]))
+							: "l"(*reinterpret_cast<const unsigned long long*>(&v[j])), "l"(pack2(win[j], win[j])));
+				}
+			}
+			wrfft::RegDft<R1>::run(v);
+			// every thread is done with the previous frame's pass 3 (work buffer) and with this
+			// frame's oldest chunk (ring)
+			__syncthreads();
+			if (tid == 0 && f + NSLOT < nchunks) {
+				const unsigned c = f + NSLOT;               // the chunk that completes frame f + 1
+				spec_bulk_load(ring32 + (c % NSLOT) * HOP * 8u, src + (size_t)c * HOP, HOP * 8u, bar32 + 8u * (c % NSLOT));
+			}
+			float *rowout = a.rows + (size_t)t * a.row_stride + (size_t)m * N;
+			float *last = (m == a.nrows - 1) ? a.last + (size_t)t * N : nullptr;
+			#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				if (h)
+					__syncthreads();                        // the first half's pass 3 has read the work buffer
+				{
+					float2 cur = h ? w1h : w1;
+					#pragma unroll
+					for (int l = 0; l < RH; l++) {
+						const int k1 = h * RH + l;
+						if (k1 == 0) {
+							sm[tid] = v[0];
+						} else {
+							sm[l * kRowPitch + tid] = wrfft::cmul(v[k1], cur);
+							cur = wrfft::cmul(cur, w1);
+						}
+					}
+				}
+				__syncthreads();
+				// ---- pass 2: radix-16 over the stride-16 index of every 256-point row (one butterfly per thread) ----
+				{
+					float2 u[16];
+					const unsigned b = tid & 15, l = tid >> 4;
+					float2 *row = sm + l * kRowPitch + b;
+					#pragma unroll
+					for (int q = 0; q < 16; q++)
+						u[q] = row[16 * q];
+					wrfft::RegDft<16>::run(u);
+					#pragma unroll
+					for (int ka = 0; ka < 16; ka++)
+						row[16 * ka] = ka ? wrfft::cmul(u[ka], tw2[16 * ka + b]) : u[0];
+				}
+				__syncthreads();
+				// ---- pass 3: radix-16 over the contiguous index; dB + fft-shift fused into the store ----
+				{
+					float2 u[16];
+					const unsigned l = tid & (RH - 1), b2 = tid >> 4;
+					const float2 *row = sm + l * kRowPitch + 16 * b2;
+					#pragma unroll
+					for (int q = 0; q < 16; q++)
+						u[q] = row[q];
+					wrfft::RegDft<16>::run(u);
+					// bin k = k1 + 32 (b2 + 16 kb), k1 = 16 h + l; fft-shift: o = (k + N/2) mod N -- k < 512 + 512 kb,
+					// so the wrap is a compile-time matter of kb
+					const unsigned k0 = (unsigned)(h * RH) + l + R1 * b2;
+					float dbv[16];
+					#pragma unroll
+					for (int kb = 0; kb < 16; kb++) {
+						const float p = fmaf(u[kb].x, u[kb].x, u[kb].y * u[kb].y);
+						float l2;
+						asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(p));
+						dbv[kb] = fmaf(3.01029995663981195f, l2, -a.scaledb);
+					}
+					#pragma unroll
+					for (int kb = 0; kb < 16; kb++)
+						rowout[k0 + (kb < 8 ? N / 2 + 512 * kb : 512 * (kb - 8))] = dbv[kb];
+					if (last) {
+						#pragma unroll
+						for (int kb = 0; kb < 16; kb++)
+							last[k0 + (kb < 8 ? N / 2 + 512 * kb : 512 * (kb - 8))] = dbv[kb];
+					}
+				}
+			}
+		}
+		// the next run reuses ring and work buffer
+		__syncthreads();
+	}
+}
+
 // the browser's palette index for one row (wr_device.cuh: waterfall_index)
 __global__ void spectrum_palette_kernel(const float *__restrict__ db, unsigned char *__restrict__ out, unsigned n)
 {
@@ -462,6 +616,7 @@ struct wr_spectrum {
 	cudaStream_t lastStream = nullptr; // stream of the most recent launch
 	bool forceV1 = false;              // env WR_FFT_V1=1: radix-4 shared-memory kernel for every size
 	bool noV3 = false;                 // env WR_FFT_V3=0: never the persistent bulk-copy kernel
+	bool noV4 = false;                 // env WR_FFT_V4=0: 8192-point transforms stay with v3 (one CTA per SM)
 	int numSMs = 148;
 	unsigned long long launches = 0;
 };
@@ -528,17 +683,24 @@ long run(wr_spectrum *s, const float *iq_dev, size_t in_stride, unsigned nframes
 			g.row0 = row0;
 			const unsigned nrows3 = nrows - row0;
 			const unsigned long long total = (unsigned long long)nrows3 * s->T;
-			const unsigned want = (unsigned)std::max<unsigned long long>(4, (total + 7ull * s->numSMs - 1) / (7ull * s->numSMs));
+			const unsigned C = s->N / s->hop, R1 = s->N / 256;
+			// 8192-point transforms: the two-CTAs-per-SM kernel (half the work buffer, the frame's own chunks only)
+			const bool v4 = R1 == 32 && !s->noV4;
+			// about seven runs per CTA of the persistent grid
+			const unsigned long long ctas = (unsigned long long)s->numSMs * (v4 ? 2 : 1);
+			const unsigned want = (unsigned)std::max<unsigned long long>(4, (total + 7ull * ctas - 1) / (7ull * ctas));
 			g.rowsPerRun = std::min(want, nrows3);
 			g.runsPerStream = (nrows3 + g.rowsPerRun - 1) / g.rowsPerRun;
-			const unsigned C = s->N / s->hop, R1 = s->N / 256;
-			const size_t smem = sizeof(float2) * ((size_t)R1 * kRowPitch + 256 + (size_t)(C + 1) * s->hop);
+			const size_t smem = v4 ? sizeof(float2) * ((size_t)16 * kRowPitch + 256 + (size_t)C * s->hop)
+					: sizeof(float2) * ((size_t)R1 * kRowPitch + 256 + (size_t)(C + 1) * s->hop);
 			const unsigned long long runs = (unsigned long long)g.runsPerStream * s->T;
 			g.nStreams = s->T;
 			// persistent: one CTA per SM (two when two fit), each walking the run list with stride gridDim.x
 			const dim3 grid3((unsigned)std::min<unsigned long long>(runs, (unsigned long long)s->numSMs * (smem <= 100 * 1024 ? 2 : 1)));
 			void (*k3)(const SpecArgs3) = nullptr;
-			switch (R1 * 10 + C) {
+			switch (v4 ? 1000 + C : R1 * 10 + C) {
+			case 1001: k3 = spectrum_kernel_v4<1>; break;
+			case 1002: k3 = spectrum_kernel_v4<2>; break;
 			case 21: k3 = spectrum_kernel_v3<2, 1>; break;
 			case 22: k3 = spectrum_kernel_v3<2, 2>; break;
 			case 41: k3 = spectrum_kernel_v3<4, 1>; break;
@@ -656,6 +818,8 @@ wr_spectrum *wr_spectrum_create(int device, unsigned fft_size, unsigned hop, uns
 		s->forceV1 = atoi(e) != 0;
 	if (const char *e = getenv("WR_FFT_V3"))
 		s->noV3 = atoi(e) == 0;
+	if (const char *e = getenv("WR_FFT_V4"))
+		s->noV4 = atoi(e) == 0;
 	WR_SPEC_ALLOC(cudaDeviceGetAttribute(&s->numSMs, cudaDevAttrMultiProcessorCount, device));
 #undef WR_SPEC_ALLOC
 	return s;
