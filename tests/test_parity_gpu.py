@@ -626,6 +626,47 @@ def test_bank_v4_streaming_fir(wro, monkeypatch, F, n1, d1, n2, d2, R, runs_per_
     run_bank_vs_oracle(wro, 4, fs, F, R, synth.receiver_ifs(R, fs), [r % 4 for r in range(R)], n1, d1, n2, d2, 3, seed=F + R)
 
 
+def test_bank_v4_on_a_large_shared_tuner_bank(wro):
+    """cfg5's shape at a size the oracle can follow: 2 tuners x 64 mixed-mode receivers, 409600-frame blocks at
+    10 MSPS, 127 taps /40, 64 taps /5 -- enough outputs to fill every lane of the grid with long runs, so the
+    streaming kernel is selected although the receivers share their tuner streams.  Two blocks, every
+    receiver against the oracle."""
+    w = synth.WORKLOADS["cfg5"]
+    fs, F, T, R = w["fs"], w["frames"], 2, 128
+    rng = np.random.default_rng(55)
+    t1 = (rng.uniform(-1, 1, w["n1"]) / w["n1"] * 4).astype(np.float32)
+    t2 = (rng.uniform(-1, 1, w["n2"]) / w["n2"] * 4).astype(np.float32)
+    ifs = synth.receiver_ifs(R, fs)
+    bank = capi.Bank(T, R, F, w["n1"], w["d1"], w["n2"], w["d2"])
+    try:
+        for r in range(R):
+            bank.set_taps(r, 0, t1)
+            bank.set_taps(r, 1, t2)
+            bank.set_if(r, int(ifs[r]), fs)
+            bank.set_mode(r, r % 4)
+            bank.set_stream(r, r % T)
+        orx = [wro.Rx(fs, int(ifs[r]), t1, w["d1"], r % 4, t2, w["d2"]) for r in range(R)]
+        import torch
+        stream = torch.cuda.ExternalStream(bank.stream())
+        m2 = F // w["d1"] // w["d2"]
+        for b in range(2):
+            iq = np.stack([synth.lattice_noise(F, stream=70 + t, start=b * F) for t in range(T)])
+            with torch.cuda.stream(stream):
+                d_iq = torch.from_numpy(iq).cuda()
+                d_audio = torch.zeros(R, m2, device="cuda")
+                bank.process_device(d_iq.data_ptr(), F, F, d_audio.data_ptr(), m2, stream.cuda_stream)
+                audio = d_audio.cpu().numpy()
+            assert bank.variant_in_use() == 4
+            for r in range(R):
+                want = orx[r].process(iq[r % T])
+                if r % 4 == capi.FM:
+                    assert_fm(audio[r], want, f"shared tuner v4 rx{r} b{b}", audio=True)
+                else:
+                    assert_biteq(audio[r], want, f"shared tuner v4 rx{r} b{b}")
+    finally:
+        bank.close()
+
+
 def test_bank_v4_is_what_cfg3_runs(wro, monkeypatch):
     """Float blocks of independent streams select v4 on their own; raw bytes and shared tuners stay on v3."""
     monkeypatch.setenv("WR_SYNC_SPLIT", "1")      # (a block this short would otherwise be cut into pieces too short for v4)

@@ -44,8 +44,8 @@
 //     by an epilogue.  Both belong to the warp that owns the receiver's first run.  The steady state therefore
 //     has no special cases: frames outside the block read as zero (cp.async src-size).
 // Geometry: N1 odd (so that a run starts on a 16-byte boundary), D1 even and a multiple of the
-// stage length.  Shared-tuner banks (cfg2, cfg5) stay with v3, whose mixers share the raw
-// registers among the receivers of a stream.
+// stage length.  Small shared-tuner banks (cfg2) stay with v3, whose mixers share the raw
+// registers among the receivers of a stream; large ones (cfg5) are faster here (v4_shape).
 #pragma once
 
 #include "wr_kernels_v3.cuh"
@@ -673,9 +673,8 @@ inline bool v4_shape(const V4Plan &p, const V3Plan &v3, unsigned R, unsigned F, 
 {
 	if (!p.ok || !v3.ok)          // (v3.ok: the table survived the compression)
 		return false;
-	// independent streams only: a run re-reads its tuner stream from L2/HBM, which a bank of 64
-	// receivers per tuner cannot afford; runs must start on 16-byte boundaries
-	if ((p.maxPerStream > 2 && !forced) || ((uintptr_t)iq & 15u) || (stream_stride & 1u))
+	// runs must start on 16-byte boundaries
+	if (((uintptr_t)iq & 15u) || (stream_stride & 1u))
 		return false;
 	const unsigned M1 = F / p.d1;
 	if (F < p.n1 - 1 || M1 < 32u * 2u * p.kskip)
@@ -689,6 +688,13 @@ inline bool v4_shape(const V4Plan &p, const V3Plan &v3, unsigned R, unsigned F, 
 		return false;
 	// not enough work for a persistent grid of independent warps: a warp per SM at least
 	if ((unsigned long long)R * out->runsPerRx < 32ull * (unsigned)p.numSMs && !forced)
+		return false;
+	// Shared tuners (64 receivers per stream: cfg2, cfg5): every run re-reads its tuner stream -- from
+	// L2, the receivers of a stream walk it together -- where v3's mixers share the raw registers among
+	// the receivers of a stream.  v4 wins once the bank fills the WHOLE grid with long runs (cfg5:
+	// 1024 receivers x 10240 outputs, runs of 277, 0.84 -> 0.73 ms per block); a small bank (cfg2:
+	// 64 x 2048 outputs = 3.5 per lane) stays with v3.
+	if (p.maxPerStream > 2 && !forced && (out->grid < (unsigned)p.numSMs || out->runLen < 8u * p.ap))
 		return false;
 	return true;
 }
