@@ -441,6 +441,45 @@ __device__ __forceinline__ void demod_audio_done(const DemodAudioArgs &a, unsign
 	}
 }
 
+// Staging of a tile for the modes that need one channel-rate sample per output sample (AM, USB,
+// LSB -- the mode is the receiver's, i.e. uniform over the CTA, so it is a template parameter of the
+// loop instead of a switch per sample): four samples per thread and round, loads first.  The
+// general loop of the kernel spends ~70 instructions per sample on the mode switch, the FM
+// discriminator's second operand and its bounds; on cfg3 that was half of the kernel's instructions.
+template <int MODE, int kThreads>
+__device__ __forceinline__ void demod_stage_simple(const float2 *__restrict__ ch, float *__restrict__ xr, float *__restrict__ s,
+		unsigned tid, unsigned i0, unsigned L, unsigned nh)
+{
+	for (unsigned ib = tid; ib < L; ib += 4 * kThreads) {
+		float2 c[4];
+		float h[4];
+		#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			const unsigned il = ib + u * kThreads, i = i0 + il;
+			c[u] = make_float2(0.0f, 0.0f);
+			h[u] = 0.0f;
+			if (il < L) {
+				if (i < nh)
+					h[u] = xr[i];
+				else
+					c[u] = ch[i - nh];
+			}
+		}
+		#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			const unsigned il = ib + u * kThreads, i = i0 + il;
+			if (il < L) {
+				float v = h[u];
+				if (i >= nh) {
+					v = demod(MODE, c[u], c[u]);
+					xr[i] = v;
+				}
+				s[il] = v;
+			}
+		}
+	}
+}
+
 // This kernel runs under the NEXT block's channel kernel (programmatic dependent launch), whose
 // CTA needs almost a whole SM: it starts on an SM only when that SM's demodulator CTAs have
 // drained, so the life time of a CTA here is on the critical path of the block.  It is all
@@ -503,6 +542,19 @@ __global__ void __launch_bounds__(kThreads, 7) demod_audio_kernel_v2(const Demod
 	const unsigned L = nout * d2 + n2 - 1;
 	const unsigned i0 = m0 * d2;
 	const float tap0 = tid < n2 ? a.taps2[(size_t)r * n2 + tid] : 0.0f;
+	if (cf.mode != WR_MODE_FM && a.TK >= 8u * 96u) {
+		// large tiles, one-sample modes: the specialised staging loops
+		if (tid < n2)
+			rt[tid] = tap0;
+		for (unsigned i = tid + kThreads; i < n2; i += kThreads)
+			rt[i] = a.taps2[(size_t)r * n2 + i];
+		if (cf.mode == WR_MODE_AM)
+			demod_stage_simple<WR_MODE_AM, kThreads>(ch, xr, s, tid, i0, L, n2 - 1);
+		else if (cf.mode == WR_MODE_USB)
+			demod_stage_simple<WR_MODE_USB, kThreads>(ch, xr, s, tid, i0, L, n2 - 1);
+		else
+			demod_stage_simple<WR_MODE_LSB, kThreads>(ch, xr, s, tid, i0, L, n2 - 1);
+	} else
 	for (unsigned ib = tid; ib < L; ib += kDemodRounds * kThreads) {
 		// operands of up to kDemodRounds samples first: their loads are in flight together
 		float2 cur[kDemodRounds], prv[kDemodRounds];
