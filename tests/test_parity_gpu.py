@@ -626,6 +626,47 @@ def test_bank_v4_streaming_fir(wro, monkeypatch, F, n1, d1, n2, d2, R, runs_per_
     run_bank_vs_oracle(wro, 4, fs, F, R, synth.receiver_ifs(R, fs), [r % 4 for r in range(R)], n1, d1, n2, d2, 3, seed=F + R)
 
 
+def test_bank_v4_more_runs_than_lanes(wro):
+    """A bank with more receivers than one round of the grid holds at 32 runs each (1300 receivers x 42 runs
+    of 12/13 outputs = 54600 runs on 37888 lanes): the warps work through TWO rounds, the second one partly
+    empty.  Two blocks; 48 receivers against the oracle, the last ones of the bank among them."""
+    import torch
+    fs, R, F = 2400000, 1300, 25600
+    rng = np.random.default_rng(1300)
+    t1 = (rng.uniform(-1, 1, 255) / 255 * 4).astype(np.float32)
+    t2 = (rng.uniform(-1, 1, 64) / 64 * 4).astype(np.float32)
+    ifs = synth.receiver_ifs(R, fs)
+    bank = capi.Bank(R, R, F, 255, 50, 64, 1)
+    try:
+        for r in range(R):
+            bank.set_taps(r, 0, t1)
+            bank.set_taps(r, 1, t2)
+            bank.set_if(r, int(ifs[r]), fs)
+            bank.set_mode(r, r % 4)
+            bank.set_stream(r, r)
+        picks = sorted(set(list(range(0, R, 29)) + [R - 3, R - 2, R - 1]))
+        orx = {r: wro.Rx(fs, int(ifs[r]), t1, 50, r % 4, t2, 1) for r in picks}
+        m2 = F // 50
+        stream = torch.cuda.ExternalStream(bank.stream())
+        g = torch.Generator(device="cuda").manual_seed(13)
+        for b in range(2):
+            with torch.cuda.stream(stream):
+                d_iq = (torch.randint(0, 256, (R, F, 2), device="cuda", generator=g, dtype=torch.int16).float() - 128.0) / 128.0
+                d_audio = torch.full((R, m2), 7.0, device="cuda")
+                bank.process_device(d_iq.data_ptr(), F, F, d_audio.data_ptr(), m2, stream.cuda_stream)
+                audio = d_audio.cpu().numpy()
+                assert bank.variant_in_use() == 4
+                assert not (audio == 7.0).any()
+                for r in picks:
+                    want = orx[r].process(d_iq[r].cpu().numpy().ravel())
+                    if r % 4 == capi.FM:
+                        assert_fm(audio[r], want, f"two rounds rx{r} b{b}", audio=True)
+                    else:
+                        assert_biteq(audio[r], want, f"two rounds rx{r} b{b}")
+    finally:
+        bank.close()
+
+
 def test_bank_v4_on_a_large_shared_tuner_bank(wro):
     """cfg5's shape at a size the oracle can follow: 2 tuners x 64 mixed-mode receivers, 409600-frame blocks at
     10 MSPS, 127 taps /40, 64 taps /5 -- enough outputs to fill every lane of the grid with long runs, so the
