@@ -2,6 +2,9 @@
 #include "gpubank.h"
 
 #include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <ctime>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -13,6 +16,43 @@
 #include "lowpass.h"
 
 namespace wrhost {
+
+// ---- optional host-side profile of the plug-in path ----
+namespace {
+std::atomic<uint64_t> g_profNs[kProfSlots];
+std::atomic<uint64_t> g_profN[kProfSlots];
+void profDump()
+{
+	static const char *names[kProfSlots] = { "tuner block upload (begin)", "settings push", "bank process (kernels + audio copy-out)",
+			"audio slice copies (LowPass)", "spectrum process" };
+	for (int i = 0; i < kProfSlots; i++)
+		if (g_profN[i])
+			fprintf(stderr, "webradio_b200 profile: %-42s %10.1f us total  %9llu calls  %8.2f us per call\n", names[i],
+					g_profNs[i] / 1e3, (unsigned long long)g_profN[i], g_profNs[i] / 1e3 / (double)g_profN[i]);
+}
+}
+bool profOn()
+{
+	static const bool on = [] {
+		const char *e = getenv("WEBRADIO_B200_PROFILE");
+		const bool v = e && atoi(e) != 0;
+		if (v)
+			atexit(profDump);
+		return v;
+	}();
+	return on;
+}
+uint64_t profNow()
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+}
+void profAdd(int slot, uint64_t ns)
+{
+	g_profNs[slot] += ns;
+	g_profN[slot]++;
+}
 
 namespace {
 
@@ -325,11 +365,16 @@ bool FusedBank::ensureProcessed(uint64_t serial, const float *iq, unsigned nfram
 	// membership changed, or a block longer than the bank was sized for: a new bank, state carried
 	if ((!_bank || _dirty || nframes > _maxFrames) && !rebuild(nframes))
 		return false;
+	const bool prof = profOn();
+	uint64_t t0 = prof ? profNow() : 0;
 	wr_upload *up = uploadFor(_producer, owner, serial, iq, nframes);
 	if (!up)
 		return false;
+	if (prof) { const uint64_t t = profNow(); profAdd(kProfUpload, t - t0); t0 = t; }
 	pushSettings();
+	if (prof) { const uint64_t t = profNow(); profAdd(kProfSettings, t - t0); t0 = t; }
 	const int rc = wr_bank_process_upload(_bank, up, nframes, _audio, _audioStride);
+	if (prof) profAdd(kProfBank, profNow() - t0);
 	if (!_producer)
 		wr_upload_finish(up);   // nobody will call blockDone for a chain without a producer
 	if (rc != WR_OK) {

@@ -52,6 +52,12 @@ void blockDone(DspBlock *producer);
 // the producer stops or goes away: page-locking of its buffer is undone, the device copy freed
 void forget(const void *producerOrOwner);
 
+// WEBRADIO_B200_PROFILE=1: where the host thread spends a block (printed at exit; off: one branch per call)
+enum ProfSlot { kProfUpload, kProfSettings, kProfBank, kProfAudioCopy, kProfSpectrum, kProfSlots };
+bool profOn();
+uint64_t profNow();
+void profAdd(int slot, uint64_t ns);
+
 struct Chain {
 	DownConverter *dc;
 	LowPass *chan;

@@ -156,9 +156,12 @@ bool LowPass::process(const vector<sample_t> &inBuffer, vector<sample_t> &outBuf
 		if (!a)
 			return false;
 		const size_t want = outBuffer.size();
+		const uint64_t t0 = wrhost::profOn() ? wrhost::profNow() : 0;
 		memcpy(outBuffer.data(), a, sizeof(float) * std::min<size_t>(want, n));
 		if (want > n)
 			std::fill(outBuffer.begin() + n, outBuffer.end(), 0.0f);
+		if (t0)
+			wrhost::profAdd(wrhost::kProfAudioCopy, wrhost::profNow() - t0);
 		return true;
 	}
 

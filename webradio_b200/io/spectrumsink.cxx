@@ -86,8 +86,12 @@ bool SpectrumSink::process(const vector<sample_t> &inBuffer, vector<sample_t> &o
 		capacityFrames = nframes;
 	}
 	if (src) {
+		const uint64_t t0 = wrhost::profOn() ? wrhost::profNow() : 0;
 		wr_upload *up = wrhost::uploadFor(src, this, src->runSerial(), inBuffer.data(), nframes);
-		if (up && wr_spectrum_process_upload(spectrum, up, nframes) >= 0)
+		const bool ok = up && wr_spectrum_process_upload(spectrum, up, nframes) >= 0;
+		if (t0)
+			wrhost::profAdd(wrhost::kProfSpectrum, wrhost::profNow() - t0);
+		if (ok)
 			return true;
 		LOG_ERROR("SpectrumSink: %s\n", wr_last_error());
 		return false;
