@@ -50,6 +50,10 @@
 
 #include "wr_kernels_v3.cuh"
 
+#ifndef WR_V4_BODY_UNROLL
+#define WR_V4_BODY_UNROLL 1    // body stages per iteration of the period's loop (A/B knob)
+#endif
+
 namespace wrd {
 
 template <int N1, int D1>
@@ -115,14 +119,19 @@ __device__ __forceinline__ void v4_stage(uint32_t st32, f2_t (&acc)[V4Geo<N1, D1
 {
 	using G = V4Geo<N1, D1>;
 	constexpr int SFR = G::SFR, AP = G::AP, TS = G::TS, S = G::S;
-	constexpr int H = SFR / 2;
+	// the NCO of a whole stage is evaluated in one batch (ten independent chains; in two batches of five
+	// the same code ran 4 % slower on cfg3 and 6 % on cfg5, measured on one box: WR_V4_HB=2)
+#ifndef WR_V4_HB
+#define WR_V4_HB 1
+#endif
+	constexpr int H = SFR / WR_V4_HB;
 	f2_t raw[SFR];             // this lane's frames of the stage: its row of the ring slot
 	#pragma unroll
 	for (int i = 0; i < SFR; i += 2)
 		lds128p(st32 + 8u * (unsigned)i, raw[i], raw[i + 1]);
 	float4 t[G::ROWS];         // the taps of four consecutive frames, one 128-bit broadcast load per live row
 	#pragma unroll
-	for (int h = 0; h < 2; h++) {
+	for (int h = 0; h < WR_V4_HB; h++) {
 		uint32_t q[H];
 		float sn[H], cs[H];
 		#pragma unroll
@@ -267,7 +276,8 @@ __device__ __forceinline__ void v4_body(V4Run<N1, D1> &r, const Lo3Regs &lo, uin
 	using G = V4Geo<N1, D1>;
 	f2_t none = 0ull;
 	uint32_t t32 = taps32 + 4u * (unsigned)((G::SFIN + 1) * G::TS);
-	#pragma unroll 1
+	constexpr int kBodyUnroll = WR_V4_BODY_UNROLL;
+	#pragma unroll kBodyUnroll
 	for (int sb = G::SFIN + 1; sb < G::S; sb++) {
 		v4_step<N1, D1, NS, 0, false>(r, lo, t32, nz, none);
 		t32 += 4u * (unsigned)G::TS;
