@@ -542,8 +542,8 @@ __global__ void __launch_bounds__(kThreads, 7) demod_audio_kernel_v2(const Demod
 	const unsigned L = nout * d2 + n2 - 1;
 	const unsigned i0 = m0 * d2;
 	const float tap0 = tid < n2 ? a.taps2[(size_t)r * n2 + tid] : 0.0f;
-	if (cf.mode != WR_MODE_FM && a.TK >= 8u * 96u) {
-		// large tiles, one-sample modes: the specialised staging loops
+	if (cf.mode != WR_MODE_FM) {
+		// one-sample modes: the specialised staging loops
 		if (tid < n2)
 			rt[tid] = tap0;
 		for (unsigned i = tid + kThreads; i < n2; i += kThreads)
