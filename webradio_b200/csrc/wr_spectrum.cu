@@ -479,28 +479,26 @@ __global__ void __launch_bounds__(256, 2) spectrum_kernel_v4(const SpecArgs3 g)
 			const unsigned m = mFirst + f;
 			// ---- pass 1: window (fetched before the wait), the frame's chunks, radix-32 ----
 			float2 v[R1];
-			{
-				float win[R1];
+			#pragma unroll
+			for (unsigned c = 0; c < (unsigned)C; c++) {
+				// the window of this chunk's points is fetched before the wait for the chunk (a chunk at a
+				// time: all 32 window values at once cost a spill, 0.692 -> 0.678 ms on cfg4)
+				float win[R1 / C];
 				#pragma unroll
-				for (int j = 0; j < R1; j++)
-					win[j] = __ldg(a.window + tid + 256u * j);
-				#pragma unroll
-				for (unsigned c = 0; c < (unsigned)C; c++) {
-					const unsigned slot = (f + c) % NSLOT;
-					if (c == (unsigned)C - 1 || f == 0) {
-						spec_mbar_wait(bar32 + 8u * slot, (phases >> slot) & 1u);
-						phases ^= 1u << slot;
-					}
-					const float2 *chunk = ring + slot * HOP;
-					#pragma unroll
-					for (int j = 0; j < R1 / C; j++)
-						v[c * (R1 / C) + j] = chunk[tid + 256u * j];
+				for (int j = 0; j < R1 / C; j++)
+					win[j] = __ldg(a.window + tid + 256u * (c * (R1 / C) + j));
+				const unsigned slot = (f + c) % NSLOT;
+				if (c == (unsigned)C - 1 || f == 0) {
+					spec_mbar_wait(bar32 + 8u * slot, (phases >> slot) & 1u);
+					phases ^= 1u << slot;
 				}
+				const float2 *chunk = ring + slot * HOP;
 				#pragma unroll
-				for (int j = 0; j < R1; j++) {
+				for (int j = 0; j < R1 / C; j++) {
+					v[c * (R1 / C) + j] = chunk[tid + 256u * j];
 					// inbuf[n] *= window[n] (spectrumsink.cxx:110-113): both components in one packed multiply
-					asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&v[j]))
-							: "l"(*reinterpret_cast<const unsigned long long*>(&v[j])), "l"(pack2(win[j], win[j])));
+					asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&v[c * (R1 / C) + j]))
+							: "l"(*reinterpret_cast<const unsigned long long*>(&v[c * (R1 / C) + j])), "l"(pack2(win[j], win[j])));
 				}
 			}
 			wrfft::RegDft<R1>::run(v);
@@ -617,6 +615,7 @@ struct wr_spectrum {
 	bool forceV1 = false;              // env WR_FFT_V1=1: radix-4 shared-memory kernel for every size
 	bool noV3 = false;                 // env WR_FFT_V3=0: never the persistent bulk-copy kernel
 	bool noV4 = false;                 // env WR_FFT_V4=0: 8192-point transforms stay with v3 (one CTA per SM)
+	unsigned runsPerCta = 0;           // env WR_FFT_RUNS: runs of consecutive rows per CTA of the persistent grid (0 = 7)
 	int numSMs = 148;
 	unsigned long long launches = 0;
 };
@@ -688,7 +687,8 @@ long run(wr_spectrum *s, const float *iq_dev, size_t in_stride, unsigned nframes
 			const bool v4 = R1 == 32 && !s->noV4;
 			// about seven runs per CTA of the persistent grid
 			const unsigned long long ctas = (unsigned long long)s->numSMs * (v4 ? 2 : 1);
-			const unsigned want = (unsigned)std::max<unsigned long long>(4, (total + 7ull * ctas - 1) / (7ull * ctas));
+			const unsigned long long per = s->runsPerCta ? s->runsPerCta : 7ull;
+			const unsigned want = (unsigned)std::max<unsigned long long>(4, (total + per * ctas - 1) / (per * ctas));
 			g.rowsPerRun = std::min(want, nrows3);
 			g.runsPerStream = (nrows3 + g.rowsPerRun - 1) / g.rowsPerRun;
 			const size_t smem = v4 ? sizeof(float2) * ((size_t)16 * kRowPitch + 256 + (size_t)C * s->hop)
@@ -820,6 +820,8 @@ wr_spectrum *wr_spectrum_create(int device, unsigned fft_size, unsigned hop, uns
 		s->noV3 = atoi(e) == 0;
 	if (const char *e = getenv("WR_FFT_V4"))
 		s->noV4 = atoi(e) == 0;
+	if (const char *e = getenv("WR_FFT_RUNS"))
+		s->runsPerCta = (unsigned)std::max(0, atoi(e));
 	WR_SPEC_ALLOC(cudaDeviceGetAttribute(&s->numSMs, cudaDevAttrMultiProcessorCount, device));
 #undef WR_SPEC_ALLOC
 	return s;
