@@ -135,7 +135,7 @@ def test_bank_golden_chain(wro, name, variant):
 
 
 def run_bank_vs_oracle(wro, variant, fs, F, n_streams, ifs, modes, n1, d1, n2, d2, blocks, seed=0,
-                       structured=False, check_rx=None):
+                       structured=False, check_rx=None, u8=False):
     R = len(ifs)
     rng = np.random.default_rng(seed)
     taps1 = [(rng.uniform(-1, 1, n1) / n1 * 4).astype(np.float32) for _ in range(R)]
@@ -162,7 +162,8 @@ def run_bank_vs_oracle(wro, variant, fs, F, n_streams, ifs, modes, n1, d1, n2, d
             else:
                 iq = np.stack([synth.lattice_noise(F, stream=t + 100 * seed, start=b * F) for t in range(n_streams)])
             try:
-                audio = bank.process(iq)
+                # (the lattice is exactly what the tuner's conversion makes of bytes: b = iq * 128 + 128)
+                audio = bank.process_u8((iq * 128 + 128).astype(np.uint8)) if u8 else bank.process(iq)
             except capi.WrError as e:
                 if (variant in (2, 3) and "do not support" in str(e)) or (variant == 4 and "do not serve" in str(e)):
                     pytest.skip(str(e))
@@ -626,6 +627,18 @@ def test_bank_v4_streaming_fir(wro, monkeypatch, F, n1, d1, n2, d2, R, runs_per_
     run_bank_vs_oracle(wro, 4, fs, F, R, synth.receiver_ifs(R, fs), [r % 4 for r in range(R)], n1, d1, n2, d2, 3, seed=F + R)
 
 
+@pytest.mark.parametrize("runs_per_rx", [0, 41])
+@pytest.mark.parametrize("F,n1,d1,n2,d2,R", [(25600, 255, 50, 64, 1, 40), (20050, 255, 50, 64, 1, 7), (12800, 127, 50, 64, 1, 9),
+                                             (21338, 127, 40, 64, 5, 3)])
+def test_bank_v4_streaming_fir_raw_bytes(wro, monkeypatch, F, n1, d1, n2, d2, R, runs_per_rx):
+    """The same kernel fed raw RTL-SDR bytes (20-byte rows by 4-byte copies, the tuner's conversion in the stage's
+    load): every receiver, every stage, three blocks, against the reference chain fed the tuner's floats."""
+    if runs_per_rx:
+        monkeypatch.setenv("WR_V4_RUNS", str(runs_per_rx))
+    fs = 2400000
+    run_bank_vs_oracle(wro, 4, fs, F, R, synth.receiver_ifs(R, fs), [r % 4 for r in range(R)], n1, d1, n2, d2, 3, seed=F + R + 1, u8=True)
+
+
 def test_bank_v4_more_runs_than_lanes(wro):
     """A bank with more receivers than one round of the grid holds at 32 runs each (1300 receivers x 42 runs
     of 12/13 outputs = 54600 runs on 37888 lanes): the warps work through TWO rounds, the second one partly
@@ -709,7 +722,7 @@ def test_bank_v4_on_a_large_shared_tuner_bank(wro):
 
 
 def test_bank_v4_is_what_cfg3_runs(wro, monkeypatch):
-    """Float blocks of independent streams select v4 on their own; raw bytes and shared tuners stay on v3."""
+    """Blocks of independent streams select v4 on their own, float or raw bytes."""
     monkeypatch.setenv("WR_SYNC_SPLIT", "1")      # (a block this short would otherwise be cut into pieces too short for v4)
     w = synth.WORKLOADS["cfg3"]
     R = 160
@@ -727,8 +740,8 @@ def test_bank_v4_is_what_cfg3_runs(wro, monkeypatch):
             assert_biteq(audio[r], wro.Rx(w["fs"], 1000 * r - 70000, t1, w["d1"], 0, t2, w["d2"]).process(iq[r]), f"rx{r}")
         u8 = (iq * 128 + 128).astype(np.uint8)
         audio8 = bank.process_u8(u8)
-        assert bank.variant_in_use() == 3
-        assert audio8.shape == audio.shape
+        assert bank.variant_in_use() == 4
+        assert audio8.shape == audio.shape      # (a second block: parity of raw bytes is test_bank_v4_streaming_fir_raw_bytes)
 
 
 # ------------------------------------------------------------------ shared upload, state hand-over ----
@@ -872,7 +885,7 @@ def test_bank_cfg3_full_size(wro):
             for r in picks:
                 assert_biteq(audio[r], orx[r].process(u8_to_iq(u8[r]).ravel()), f"cfg3 full rx{r} b{b}")
             del u8, half
-        assert bank.variant_in_use() == 3
+        assert bank.variant_in_use() == 4
     finally:
         bank.close()
 
@@ -946,6 +959,40 @@ def test_bank_audio_fir_sliding_window_ragged(wro):
         bank.close()
 
 
+def test_bank_cfg5_full_size_float_one_launch(wro):
+    """BASELINE config 5, one GPU's share at FULL size as bench.py runs it: float IQ resident in HBM, one launch
+    per block of the streaming channel kernel on SHARED tuners (16 tuners x 64 mixed-mode receivers, runs of
+    277 outputs).  Two blocks; 24 receivers (all four modes, several tuners) against the oracle."""
+    import torch
+    w = synth.WORKLOADS["cfg5"]
+    R, T, F = w["n_rx"], w["n_streams"], w["frames"]
+    bank, t1, t2, ifs, modes = _full_size_bank(w, 53)
+    try:
+        picks = sorted(set([0, 1, 2, 3, 17, 130, 515, 516, 777, 1021, 1022, 1023] + list(range(40, R, 83))))[:24]
+        orx = {r: wro.Rx(w["fs"], int(ifs[r]), t1, w["d1"], int(modes[r]), t2, w["d2"]) for r in picks}
+        m2 = F // w["d1"] // w["d2"]
+        stream = torch.cuda.ExternalStream(bank.stream())
+        for b in range(2):
+            iq = np.stack([synth.lattice_noise(F, stream=500 + t, start=b * F) for t in range(T)])
+            with torch.cuda.stream(stream):
+                d_iq = torch.from_numpy(iq).cuda()
+                d_audio = torch.full((R, m2), 7.0, device="cuda")
+                bank.process_device(d_iq.data_ptr(), F, F, d_audio.data_ptr(), m2, stream.cuda_stream)
+                audio = d_audio.cpu().numpy()
+            assert bank.variant_in_use() == 4
+            assert not (audio == 7.0).any()
+            for r in picks:
+                want = orx[r].process(iq[r % T])
+                if int(modes[r]) == capi.FM:
+                    assert_fm(audio[r], want, f"cfg5 float full rx{r} b{b}", audio=True)
+                else:
+                    assert_biteq(audio[r], want, f"cfg5 float full rx{r} b{b}")
+        for r in range(0, R, 37):
+            assert bank.get_phase(r) == (capi.phase_step(int(ifs[r]), w["fs"]) * F * 2) & 0x7FFFFFFF
+    finally:
+        bank.close()
+
+
 def test_bank_cfg5_full_size(wro):
     """BASELINE config 5, one GPU's share at FULL size: 16 tuners x 64 mixed-mode receivers, 409600-frame
     blocks at 10 MSPS, 127 taps /40, 64 taps /5.  Two blocks; 12 receivers (all four modes, several
@@ -968,7 +1015,7 @@ def test_bank_cfg5_full_size(wro):
                     assert_biteq(audio[r], want, f"cfg5 full rx{r} b{b}")
         for r in range(0, R, 37):
             assert bank.get_phase(r) == (capi.phase_step(int(ifs[r]), w["fs"]) * F * 2) & 0x7FFFFFFF
-        assert bank.variant_in_use() == 3
+        assert bank.variant_in_use() == 4      # (the streaming kernel: the bank fills the grid with long runs)
     finally:
         bank.close()
 

@@ -365,12 +365,12 @@ void *device_view(wr_bank *b, const void *host, size_t bytes)
 	return m.dev;
 }
 
-// can this block go through the v4 channel kernel (streaming FIR; float blocks of independent streams)?
+// can this block go through the v4 channel kernel (streaming FIR; banks that fill the grid with long runs)?
 bool block_uses_v4(const wr_bank *b, unsigned F, bool u8, const void *iq, size_t stream_stride, wrd::V4Launch *shape)
 {
 	wrd::V4Launch tmp;
-	return (b->variant == 4 || b->variant == 0) && !u8
-			&& wrd::v4_shape(b->v4, b->v3, b->R, F, iq, stream_stride, b->variant == 4, shape ? shape : &tmp);
+	return (b->variant == 4 || b->variant == 0)
+			&& wrd::v4_shape(b->v4, b->v3, b->R, F, iq, u8, stream_stride, b->variant == 4, shape ? shape : &tmp);
 }
 
 // can this block go through the v3 channel kernel?  (v3 and v4 know the flag hand-over of the
@@ -428,7 +428,7 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 	if (useV2 && !b->d_chan)
 		WR_CUDA(cudaMalloc(&b->d_chan, 2 * sizeof(float2) * (size_t)b->R * std::max(1u, b->maxM1)));
 	float2 *const chanBuf = b->d_chan ? b->d_chan + (size_t)cur * b->R * std::max(1u, b->maxM1) : nullptr;
-	if (u8 && !useV3) {     // (useV4 implies float input)
+	if (u8 && !useV3 && !useV4) {
 		// the older kernel families read float blocks: convert once into a scratch block
 		if (!b->d_iqf)
 			WR_CUDA(cudaMalloc(&b->d_iqf, sizeof(float) * 2 * (size_t)b->T * b->maxF));
@@ -473,7 +473,7 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 	ca.poll_ns = b->pollNs;
 
 	if (useV4) {
-		rc = wrd::v4_launch_chan(b->v4, b->v3, shape4, ca, b->R, st, &b->launches);
+		rc = wrd::v4_launch_chan(b->v4, b->v3, shape4, ca, b->R, u8, st, &b->launches);
 		if (rc != WR_OK)
 			return rc;
 	} else if (useV3) {

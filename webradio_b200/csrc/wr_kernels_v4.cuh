@@ -22,6 +22,9 @@
 //     so the 32 consecutive runs of a warp belong to at most TWO receivers: both tap sets are
 //     staged, a lane reads the one of its receiver.  Warps are independent of each other: no
 //     block-wide barrier after start-up, no slot hand-over, no spinning.
+//   * (Raw RTL-SDR bytes -- template parameter U8 -- take the same road: a stage's row is 20 bytes,
+//     fetched by 4-byte copies, five lanes to a row as well; a lane reads its row with five 32-bit
+//     loads and converts two frames per word, (2^23 + b) * 2^-7 - 65537 = (b - 128) / 128 exactly.)
 //   * Raw IQ: each warp keeps an NS-deep ring of stages in shared memory, a stage = SFR frames of
 //     each of the warp's 32 runs (32 rows of 80 bytes).  The rows are 25.6 KB apart in HBM, so
 //     the stage is fetched by 16-byte cp.async copies, 8-byte granules apart within a row being
@@ -56,7 +59,7 @@
 
 namespace wrd {
 
-template <int N1, int D1>
+template <int N1, int D1, bool U8 = false>
 struct V4Geo {
 	static constexpr int SFR = 10;                          // frames per run and stage
 	static constexpr int S = D1 / SFR;                      // stages per period
@@ -67,15 +70,23 @@ struct V4Geo {
 	static constexpr int SFIN = REM / SFR;                  // stage in which the oldest output completes
 	static constexpr int CFIN = REM % SFR + 1;              // ... after this many of its frames
 	static constexpr int KSKIP = (N1 - 1 + D1 - 1) / D1;    // outputs whose windows reach into the history
-	static constexpr unsigned kRowBytes = SFR * 8;          // a run's frames of one stage
+	static constexpr unsigned FB = U8 ? 2 : 8;              // bytes per frame: raw RTL-SDR bytes or float IQ
+	static constexpr unsigned CH = U8 ? 4 : 16;             // bytes per cp.async copy (two frames)
+	static constexpr unsigned kRowBytes = SFR * FB;         // a run's frames of one stage
 	static constexpr unsigned kStageBytes = 32 * kRowBytes;
 	static constexpr unsigned kTapBytes = (unsigned)ROWS * S * TS * 4;
 	static constexpr unsigned kScratchFrames = (unsigned)(KSKIP - 1) * D1 + N1;   // [history | first frames] of the prologue
 	static_assert(D1 % SFR == 0, "a period must be a whole number of stages");
 	static_assert(N1 % 2 == 1 && D1 % 2 == 0, "v4 needs an odd tap count and an even decimation (16-byte aligned runs)");
-	static_assert((kRowBytes / 16) % 2 == 1, "a row must be an odd number of 16-byte chunks (bank spread)");
+	static_assert((kRowBytes / CH) % 2 == 1, "a row must be an odd number of chunks (bank spread)");
 	static_assert(AP >= 1, "the window must span more than one period");
 };
+
+// bytes of a warp's ring region: the ring, or the prologue's scratch where that is larger (16-byte multiple)
+__host__ __device__ constexpr unsigned v4_ring_region(unsigned ring, unsigned scratch)
+{
+	return ring >= scratch ? ring : ((scratch + 15u) & ~15u);
+}
 
 struct V4Args {
 	const int16_t *delta;     // padded corrections (wr_lo3.h), staged to shared memory per CTA
@@ -99,6 +110,43 @@ __device__ __forceinline__ void cp_async16z(uint32_t dst, const void *src, unsig
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(srcBytes) : "memory");
 }
 
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ void cp_async4z(uint32_t dst, const void *src, unsigned srcBytes)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(src), "r"(srcBytes) : "memory");
+}
+
+// Two frames of raw RTL-SDR bytes (i0 q0 i1 q1 in one word) as float IQ: (2^23 + b) * 2^-7 - 65537 =
+// (b - 128) / 128 exactly, rtlsdrtuner.cxx:106 (RawIO<true>::cvt of the v3 kernel, for both halves)
+__device__ __forceinline__ void v4_cvt_bytes(uint32_t w, uint32_t hi, f2_t &a, f2_t &b)
+{
+	uint32_t i0, q0, i1, q1;
+	asm("prmt.b32 %0, %1, %2, 0x5440;" : "=r"(i0) : "r"(w), "r"(hi));
+	asm("prmt.b32 %0, %1, %2, 0x5441;" : "=r"(q0) : "r"(w), "r"(hi));
+	asm("prmt.b32 %0, %1, %2, 0x5442;" : "=r"(i1) : "r"(w), "r"(hi));
+	asm("prmt.b32 %0, %1, %2, 0x5443;" : "=r"(q1) : "r"(w), "r"(hi));
+	const f2_t k = f2_pack(0.0078125f, 0.0078125f), m = f2_pack(-65537.0f, -65537.0f);
+	a = f2_fma(f2_pack(__uint_as_float(i0), __uint_as_float(q0)), k, m);
+	b = f2_fma(f2_pack(__uint_as_float(i1), __uint_as_float(q1)), k, m);
+}
+
+// frame f of a tuner stream as float IQ (the prologue's and the epilogue's gathers)
+template <bool U8>
+__device__ __forceinline__ float2 v4_load_frame(const char *src, long long f, uint32_t hi)
+{
+	if constexpr (U8) {
+		float2 x;
+		f2_unpack(RawIO<true>::cvt(RawIO<true>::load(src + f * 2), hi), x.x, x.y);
+		return x;
+	} else {
+		return __ldg(reinterpret_cast<const float2*>(src) + f);
+	}
+}
+
 __device__ __forceinline__ void cp_async_commit()
 {
 	asm volatile("cp.async.commit_group;" ::: "memory");
@@ -113,7 +161,7 @@ __device__ __forceinline__ void cp_async_wait()
 // One stage of a run: SFR frames mixed and applied to the live outputs.  CX = how many of the
 // stage's leading frames still carry the OLDEST output (tap row AP); FIN = that output completes
 // in this stage (after frame CX-1), and `fin` receives it.
-template <int N1, int D1, int CX, bool FIN>
+template <int N1, int D1, int CX, bool FIN, bool U8 = false>
 __device__ __forceinline__ void v4_stage(uint32_t st32, f2_t (&acc)[V4Geo<N1, D1>::ROWS],
 		uint32_t q0, uint32_t qs, const Lo3Regs &lo, uint32_t tap32, f2_t nz, f2_t &fin)
 {
@@ -126,9 +174,19 @@ __device__ __forceinline__ void v4_stage(uint32_t st32, f2_t (&acc)[V4Geo<N1, D1
 #endif
 	constexpr int H = SFR / WR_V4_HB;
 	f2_t raw[SFR];             // this lane's frames of the stage: its row of the ring slot
-	#pragma unroll
-	for (int i = 0; i < SFR; i += 2)
-		lds128p(st32 + 8u * (unsigned)i, raw[i], raw[i + 1]);
+	if constexpr (U8) {
+		uint32_t w[SFR / 2];
+		#pragma unroll
+		for (int i = 0; i < SFR / 2; i++)
+			asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[i]) : "r"(st32 + 4u * (unsigned)i));
+		#pragma unroll
+		for (int i = 0; i < SFR / 2; i++)
+			v4_cvt_bytes(w[i], lo.hi, raw[2 * i], raw[2 * i + 1]);
+	} else {
+		#pragma unroll
+		for (int i = 0; i < SFR; i += 2)
+			lds128p(st32 + 8u * (unsigned)i, raw[i], raw[i + 1]);
+	}
 	float4 t[G::ROWS];         // the taps of four consecutive frames, one 128-bit broadcast load per live row
 	#pragma unroll
 	for (int h = 0; h < WR_V4_HB; h++) {
@@ -171,10 +229,10 @@ __device__ __forceinline__ void v4_stage(uint32_t st32, f2_t (&acc)[V4Geo<N1, D1
 }
 
 // What a run carries from stage to stage (registers once everything is inlined).
-template <int N1, int D1>
+template <int N1, int D1, bool U8 = false>
 struct V4Run {
-	using G = V4Geo<N1, D1>;
-	static constexpr int NCH = (int)(G::kRowBytes / 16);    // 16-byte chunks a lane copies per stage (32 rows * chunks per row / 32 lanes)
+	using G = V4Geo<N1, D1, U8>;
+	static constexpr int NCH = (int)(G::kRowBytes / G::CH); // chunks a lane copies per stage (32 rows * chunks per row / 32 lanes)
 	f2_t acc[G::ROWS];         // live outputs by age
 	uint32_t q;                // biased doubled phase of the next frame
 	uint32_t qs;               // ... and its step per frame
@@ -186,43 +244,51 @@ struct V4Run {
 	long long cf0[NCH];        // first frame of those chunks in stage 0 of the run
 	const char *src;           // the stream
 	unsigned F;
-	unsigned laneOff;          // 16 * lane - lane * kRowBytes: from st32 to this lane's first chunk of the slot
+	unsigned laneOff;          // CH * lane - lane * kRowBytes: from st32 to this lane's first chunk of the slot
 };
 
 // The rare stage that reaches outside the block (history in front of it, nothing behind it):
 // frames outside read as zero through the copies' source size.
-template <int N1, int D1>
+template <int N1, int D1, bool U8 = false>
 __device__ __noinline__ void v4_fetch_edge(uint32_t dst, const char *c0, const char *c1, const char *c2, const char *c3, const char *c4,
 		long long f0, long long f1, long long f2, long long f3, long long f4, long long F, const char *src)
 {
+	using G = V4Geo<N1, D1, U8>;
 	const char *c[5] = { c0, c1, c2, c3, c4 };
 	const long long f[5] = { f0, f1, f2, f3, f4 };
 	#pragma unroll
-	for (int i = 0; i < V4Run<N1, D1>::NCH; i++) {
+	for (int i = 0; i < V4Run<N1, D1, U8>::NCH; i++) {
 		const long long left = F - f[i];                     // (a chunk starts on an even frame: it never straddles frame 0)
-		const unsigned nb = (f[i] < 0 || left <= 0) ? 0u : (left >= 2 ? 16u : 8u);
-		cp_async16z(dst + 512u * (unsigned)i, nb ? c[i] : src, nb);
+		const unsigned nb = (f[i] < 0 || left <= 0) ? 0u : (left >= 2 ? G::CH : G::CH / 2);
+		if constexpr (U8)
+			cp_async4z(dst + 32u * G::CH * (unsigned)i, nb ? c[i] : src, nb);
+		else
+			cp_async16z(dst + 32u * G::CH * (unsigned)i, nb ? c[i] : src, nb);
 	}
 }
 
 // Copies stage (current + NS - 1) of every run of the warp into the ring slot the stage before the
 // current one has just left.  SOFF = that stage's position counted from the stage cptr points at
 // (the one being computed; the ring fill: stage 0), so its source is an immediate offset.
-template <int N1, int D1, int SOFF>
-__device__ __forceinline__ void v4_fetch(V4Run<N1, D1> &r, uint32_t slot32)
+template <int N1, int D1, int SOFF, bool U8 = false>
+__device__ __forceinline__ void v4_fetch(V4Run<N1, D1, U8> &r, uint32_t slot32)
 {
-	using G = V4Geo<N1, D1>;
-	constexpr int NCH = V4Run<N1, D1>::NCH;
+	using G = V4Geo<N1, D1, U8>;
+	constexpr int NCH = V4Run<N1, D1, U8>::NCH;
 	static_assert(NCH == 5, "v4_fetch_edge takes five chunks");
 	if (r.nf < r.nStages) {
 		const uint32_t dst = slot32 + r.laneOff;
 		if (r.nf >= r.nLo && r.nf < r.nHi) {
 			#pragma unroll
-			for (int i = 0; i < NCH; i++)
-				cp_async16(dst + 512u * (unsigned)i, r.cptr[i] + SOFF * (int)G::kRowBytes);
+			for (int i = 0; i < NCH; i++) {
+				if constexpr (U8)
+					cp_async4(dst + 32u * G::CH * (unsigned)i, r.cptr[i] + SOFF * (int)G::kRowBytes);
+				else
+					cp_async16(dst + 32u * G::CH * (unsigned)i, r.cptr[i] + SOFF * (int)G::kRowBytes);
+			}
 		} else {
 			const long long adv = (long long)r.nf * G::SFR;
-			v4_fetch_edge<N1, D1>(dst, r.cptr[0] + SOFF * (int)G::kRowBytes, r.cptr[1] + SOFF * (int)G::kRowBytes,
+			v4_fetch_edge<N1, D1, U8>(dst, r.cptr[0] + SOFF * (int)G::kRowBytes, r.cptr[1] + SOFF * (int)G::kRowBytes,
 					r.cptr[2] + SOFF * (int)G::kRowBytes, r.cptr[3] + SOFF * (int)G::kRowBytes, r.cptr[4] + SOFF * (int)G::kRowBytes,
 					r.cf0[0] + adv, r.cf0[1] + adv, r.cf0[2] + adv, r.cf0[3] + adv, r.cf0[4] + adv, (long long)r.F, r.src);
 		}
@@ -234,61 +300,61 @@ __device__ __forceinline__ void v4_fetch(V4Run<N1, D1> &r, uint32_t slot32)
 // One stage of the steady state: stage n has landed, the slot of stage n-1 is handed to the copy of
 // stage n + NS - 1, the stage's frames are mixed and applied.  The copies' sources advance with the
 // stages (cptr points at the stage being computed), so the offset of the fetch is the constant NS - 1.
-template <int N1, int D1, int NS, int CX, bool FIN>
-__device__ __forceinline__ void v4_step(V4Run<N1, D1> &r, const Lo3Regs &lo, uint32_t tapsStage32, f2_t nz, f2_t &fin)
+template <int N1, int D1, int NS, int CX, bool FIN, bool U8 = false>
+__device__ __forceinline__ void v4_step(V4Run<N1, D1, U8> &r, const Lo3Regs &lo, uint32_t tapsStage32, f2_t nz, f2_t &fin)
 {
-	using G = V4Geo<N1, D1>;
+	using G = V4Geo<N1, D1, U8>;
 	// stage n has landed (all but the NS-2 youngest groups are complete) ...
 	cp_async_wait<NS - 2>();
 	__syncwarp();
 	// ... and the slot of stage n-1 is free: every lane is past its reads of it
 	const uint32_t prev32 = (r.st32 == r.stEnd - r.ringBytes + 0u) ? r.stEnd - G::kStageBytes : r.st32 - G::kStageBytes;
-	v4_fetch<N1, D1, NS - 1>(r, prev32);
-	v4_stage<N1, D1, CX, FIN>(r.st32, r.acc, r.q, r.qs, lo, tapsStage32, nz, fin);
+	v4_fetch<N1, D1, NS - 1, U8>(r, prev32);
+	v4_stage<N1, D1, CX, FIN, U8>(r.st32, r.acc, r.q, r.qs, lo, tapsStage32, nz, fin);
 	r.q += (uint32_t)G::SFR * r.qs;
 	r.st32 += G::kStageBytes;
 	if (r.st32 == r.stEnd)
 		r.st32 -= r.ringBytes;
 	#pragma unroll
-	for (int i = 0; i < V4Run<N1, D1>::NCH; i++)
+	for (int i = 0; i < V4Run<N1, D1, U8>::NCH; i++)
 		r.cptr[i] += G::kRowBytes;
 }
 
 // The HEAD of a period: stages [SB, SFIN], in which the oldest output still collects taps (and, in
 // stage SFIN, completes).  Unrolled: which frames carry the oldest output is a compile-time matter.
-template <int N1, int D1, int NS, int SB>
-__device__ __forceinline__ void v4_head(V4Run<N1, D1> &r, const Lo3Regs &lo, uint32_t taps32, f2_t nz, f2_t &fin)
+template <int N1, int D1, int NS, int SB, bool U8 = false>
+__device__ __forceinline__ void v4_head(V4Run<N1, D1, U8> &r, const Lo3Regs &lo, uint32_t taps32, f2_t nz, f2_t &fin)
 {
-	using G = V4Geo<N1, D1>;
+	using G = V4Geo<N1, D1, U8>;
 	if constexpr (SB <= G::SFIN) {
 		constexpr int CX = (G::REM + 1 - SB * G::SFR) > G::SFR ? G::SFR : (G::REM + 1 - SB * G::SFR);
-		v4_step<N1, D1, NS, CX, SB == G::SFIN>(r, lo, taps32 + 4u * (unsigned)(SB * G::TS), nz, fin);
-		v4_head<N1, D1, NS, SB + 1>(r, lo, taps32, nz, fin);
+		v4_step<N1, D1, NS, CX, SB == G::SFIN, U8>(r, lo, taps32 + 4u * (unsigned)(SB * G::TS), nz, fin);
+		v4_head<N1, D1, NS, SB + 1, U8>(r, lo, taps32, nz, fin);
 	}
 }
 
 // The BODY of a period: stages (SFIN, S), all alike but for their taps -- ONE copy of the stage's
 // code in a loop (the fully unrolled period was 34 KB of instructions; rolled it is 14 KB at the same
 // speed, measured on one box against the unrolled build: 256.6 vs 256.3 us per cfg3 step).
-template <int N1, int D1, int NS>
-__device__ __forceinline__ void v4_body(V4Run<N1, D1> &r, const Lo3Regs &lo, uint32_t taps32, f2_t nz)
+template <int N1, int D1, int NS, bool U8 = false>
+__device__ __forceinline__ void v4_body(V4Run<N1, D1, U8> &r, const Lo3Regs &lo, uint32_t taps32, f2_t nz)
 {
-	using G = V4Geo<N1, D1>;
+	using G = V4Geo<N1, D1, U8>;
 	f2_t none = 0ull;
 	uint32_t t32 = taps32 + 4u * (unsigned)((G::SFIN + 1) * G::TS);
 	constexpr int kBodyUnroll = WR_V4_BODY_UNROLL;
 	#pragma unroll kBodyUnroll
 	for (int sb = G::SFIN + 1; sb < G::S; sb++) {
-		v4_step<N1, D1, NS, 0, false>(r, lo, t32, nz, none);
+		v4_step<N1, D1, NS, 0, false, U8>(r, lo, t32, nz, none);
 		t32 += 4u * (unsigned)G::TS;
 	}
 }
 
-template <int N1, int D1, int WMAX, int NS>
+template <int N1, int D1, int WMAX, int NS, bool U8 = false>
 __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a, const V4Args v)
 {
-	using G = V4Geo<N1, D1>;
-	using Run = V4Run<N1, D1>;
+	using G = V4Geo<N1, D1, U8>;
+	using Run = V4Run<N1, D1, U8>;
 	constexpr int SFR = G::SFR, S = G::S, AP = G::AP, ROWS = G::ROWS, TS = G::TS, NCH = Run::NCH;
 	extern __shared__ __align__(16) unsigned char wr_smem_v4[];
 	const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nWarps = blockDim.x >> 5;
@@ -342,10 +408,11 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 	const Lo3Regs lo = lo3_regs(v.eps, smem32 + kV3MidOffset, v.prmtHi);
 	const f2_t nz = f2_pack(v.negzero, v.negzero);
 	// per warp: [ring: NS stages (also the prologue's scratch, before it is filled) | taps of two receivers]
-	static_assert(NS * G::kStageBytes >= G::kScratchFrames * 8u, "the ring must hold the prologue's [history | first frames]");
-	const unsigned perWarp = NS * G::kStageBytes + 2u * G::kTapBytes;
+	// (raw bytes: the ring proper is a quarter of the size, the region is as large as the scratch needs)
+	constexpr unsigned kRingRegion = v4_ring_region(NS * G::kStageBytes, G::kScratchFrames * 8u);
+	const unsigned perWarp = kRingRegion + 2u * G::kTapBytes;
 	const uint32_t ring32 = smem32 + kV3TableBytes + warp * perWarp;
-	const uint32_t tapsA32 = ring32 + NS * G::kStageBytes;
+	const uint32_t tapsA32 = ring32 + kRingRegion;
 	bool tableReady = false;
 	const unsigned Kmax = v.runLen + (v.longRuns ? 1u : 0u);
 
@@ -367,7 +434,7 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 		const RxConf cf = a.conf[rx];
 		const uint32_t ph0 = a.st_in[rx].phase;
 		const int32_t step = cf.step;
-		const char *__restrict__ src = reinterpret_cast<const char*>(a.iq) + (size_t)cf.stream * a.stream_stride * 8u;
+		const char *__restrict__ src = reinterpret_cast<const char*>(a.iq) + (size_t)cf.stream * a.stream_stride * G::FB;
 		const uint32_t taps32 = tapsA32 + (rx - rxA) * G::kTapBytes;
 		__syncwarp();
 
@@ -393,13 +460,13 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 			const long long f0r = __shfl_sync(0xFFFFFFFFu, f0, c / NCH);
 			const char *srcr = reinterpret_cast<const char*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)(uintptr_t)src, c / NCH));
 			r.cf0[i] = f0r + 2 * (long long)(c % NCH);
-			r.cptr[i] = srcr + r.cf0[i] * 8;
+			r.cptr[i] = srcr + r.cf0[i] * (long long)G::FB;
 		}
 		r.nf = 0;
 		r.ringBytes = NS * G::kStageBytes;
 		r.st32 = ring32 + lane * G::kRowBytes;
 		r.stEnd = r.st32 + r.ringBytes;
-		r.laneOff = 16u * lane - lane * G::kRowBytes;
+		r.laneOff = G::CH * lane - lane * G::kRowBytes;
 
 		// ---- the taps of the warp's receiver(s), rows of one period: row a, stage s, frame i <- tap a*D1 + s*SFR + i ----
 		#pragma unroll 1
@@ -431,7 +498,7 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 			const uint32_t tapsP32 = tapsA32 + x * G::kTapBytes;
 			const uint32_t php = a.st_in[rxp].phase;
 			const RxConf cfp = a.conf[rxp];
-			const char *__restrict__ srcp = reinterpret_cast<const char*>(a.iq) + (size_t)cfp.stream * a.stream_stride * 8u;
+			const char *__restrict__ srcp = reinterpret_cast<const char*>(a.iq) + (size_t)cfp.stream * a.stream_stride * G::FB;
 			// [history (N1-1) | mixed frames 0 ...], float2 each; four entries per lane and round, loads first
 			for (unsigned c0 = 0; c0 < G::kScratchFrames; c0 += 128) {
 				float2 xx[4];
@@ -441,7 +508,7 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 					if (c < (unsigned)(N1 - 1))
 						xx[u] = a.hist_in[(size_t)rxp * (N1 - 1) + c];
 					else if (c < G::kScratchFrames && c - (unsigned)(N1 - 1) < a.F)
-						xx[u] = __ldg(reinterpret_cast<const float2*>(srcp) + (c - (unsigned)(N1 - 1)));
+						xx[u] = v4_load_frame<U8>(srcp, (long long)(c - (unsigned)(N1 - 1)), lo.hi);
 					else
 						xx[u] = make_float2(0.0f, 0.0f);
 				}
@@ -482,9 +549,9 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 		}
 		// ---- fill the ring: stages 0 .. NS-2 of period 0 (v4_fetch takes its sources relative to the
 		// period being computed, SOFF = 0 .. NS-2 is exactly where cptr points) ----
-		v4_fetch<N1, D1, 0>(r, ring32 + lane * G::kRowBytes);
-		if (NS > 2) v4_fetch<N1, D1, 1>(r, ring32 + G::kStageBytes + lane * G::kRowBytes);
-		if (NS > 3) v4_fetch<N1, D1, 2>(r, ring32 + 2 * G::kStageBytes + lane * G::kRowBytes);
+		v4_fetch<N1, D1, 0, U8>(r, ring32 + lane * G::kRowBytes);
+		if (NS > 2) v4_fetch<N1, D1, 1, U8>(r, ring32 + G::kStageBytes + lane * G::kRowBytes);
+		if (NS > 3) v4_fetch<N1, D1, 2, U8>(r, ring32 + 2 * G::kStageBytes + lane * G::kRowBytes);
 
 		#pragma unroll
 		for (int i = 0; i < ROWS; i++)
@@ -500,9 +567,9 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 				r.acc[i] = r.acc[i - 1];
 			r.acc[0] = 0ull;
 			f2_t fin = 0ull;
-			v4_head<N1, D1, NS, 0>(r, lo, taps32, nz, fin);
+			v4_head<N1, D1, NS, 0, U8>(r, lo, taps32, nz, fin);
 			if (p + 1 < nPeriods)
-				v4_body<N1, D1, NS>(r, lo, taps32, nz);
+				v4_body<N1, D1, NS, U8>(r, lo, taps32, nz);
 			// the output that began AP periods ago is complete (the first KSKIP of a receiver are the prologue's)
 			if (kdone - k0 < Kl && kdone >= (unsigned)G::KSKIP) {
 				float2 y;
@@ -518,7 +585,7 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 			const unsigned rxp = rxA + x;
 			const uint32_t php = a.st_in[rxp].phase;
 			const RxConf cfp = a.conf[rxp];
-			const char *__restrict__ srcp = reinterpret_cast<const char*>(a.iq) + (size_t)cfp.stream * a.stream_stride * 8u;
+			const char *__restrict__ srcp = reinterpret_cast<const char*>(a.iq) + (size_t)cfp.stream * a.stream_stride * G::FB;
 			for (unsigned i0 = 0; i0 < (unsigned)(N1 - 1); i0 += 64) {
 				// the last N1-1 mixed frames of [history | block]
 				float2 xx[2];
@@ -531,7 +598,7 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 					else if (f < 0)
 						xx[u] = a.hist_in[(size_t)rxp * (N1 - 1) + (unsigned)(f + (N1 - 1))];
 					else
-						xx[u] = __ldg(reinterpret_cast<const float2*>(srcp) + f);
+						xx[u] = v4_load_frame<U8>(srcp, f, lo.hi);
 				}
 				#pragma unroll
 				for (int u = 0; u < 2; u++) {
@@ -573,7 +640,8 @@ struct V4Plan {
 	unsigned n1 = 0, d1 = 0;
 	unsigned kskip = 0;          // outputs the prologue computes
 	unsigned ap = 0;             // periods a run spends beyond its own outputs
-	unsigned stageBytes = 0, tapBytes = 0;
+	V4Kernel kernelU8 = nullptr; // the same kernel fed raw RTL-SDR bytes
+	unsigned ringBytes = 0, ringBytesU8 = 0, tapBytes = 0;   // a warp's ring region (float / bytes), one tap set
 	size_t smemMax = 0;
 	unsigned maxPerStream = 1;   // most receivers that share one tuner stream (v4_set_groups)
 	unsigned runs = 0;           // WR_V4_RUNS: runs per receiver (0 = fill the grid; 32 = one receiver per warp)
@@ -586,9 +654,11 @@ inline void v4_fill(V4Plan &p)
 {
 	using G = V4Geo<N1, D1>;
 	p.kernel = chan_kernel_v4<N1, D1, kV4Warps, 3>;
+	p.kernelU8 = chan_kernel_v4<N1, D1, kV4Warps, 3, true>;
 	p.kskip = G::KSKIP;
 	p.ap = G::AP;
-	p.stageBytes = G::kStageBytes;
+	p.ringBytes = v4_ring_region(3 * G::kStageBytes, G::kScratchFrames * 8u);
+	p.ringBytesU8 = v4_ring_region(3 * V4Geo<N1, D1, true>::kStageBytes, G::kScratchFrames * 8u);
 	p.tapBytes = G::kTapBytes;
 }
 
@@ -625,6 +695,7 @@ inline int v4_init(V4Plan &p, const V3Plan &v3, int device, unsigned n1, unsigne
 	// the opt-in limit covers static and dynamic shared memory together (the kernel's mbarrier is static)
 	p.smemMax = prop.sharedMemPerBlockOptin - ((fa.sharedSizeBytes + 255) & ~(size_t)255);
 	WR_CUDA(cudaFuncSetAttribute(p.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemMax));
+	WR_CUDA(cudaFuncSetAttribute(p.kernelU8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemMax));
 	p.ok = true;
 	return WR_OK;
 }
@@ -679,19 +750,19 @@ inline bool v4_cut(const V4Plan &p, unsigned R, unsigned M1, unsigned warps, V4L
 }
 
 // How a block of F frames would be launched; false if v4 does not serve it.
-inline bool v4_shape(const V4Plan &p, const V3Plan &v3, unsigned R, unsigned F, const void *iq, size_t stream_stride, bool forced, V4Launch *out)
+inline bool v4_shape(const V4Plan &p, const V3Plan &v3, unsigned R, unsigned F, const void *iq, bool u8, size_t stream_stride, bool forced, V4Launch *out)
 {
 	if (!p.ok || !v3.ok)          // (v3.ok: the table survived the compression)
 		return false;
-	// runs must start on 16-byte boundaries
-	if (((uintptr_t)iq & 15u) || (stream_stride & 1u))
+	// runs must start on the copies' boundaries: 16 bytes (two float frames), 4 bytes (two frames of raw bytes)
+	if (((uintptr_t)iq & (u8 ? 3u : 15u)) || (stream_stride & 1u))
 		return false;
 	const unsigned M1 = F / p.d1;
 	if (F < p.n1 - 1 || M1 < 32u * 2u * p.kskip)
 		return false;
 	unsigned warps = kV4Warps;
 	const size_t avail = p.smemMax - kV3TableBytes;
-	const size_t perWarp = (size_t)3 * p.stageBytes + 2 * (size_t)p.tapBytes;
+	const size_t perWarp = (size_t)(u8 ? p.ringBytesU8 : p.ringBytes) + 2 * (size_t)p.tapBytes;
 	while (warps > 1 && perWarp * warps > avail)
 		warps--;
 	if (perWarp * warps > avail || !v4_cut(p, R, M1, warps, out))
@@ -709,7 +780,7 @@ inline bool v4_shape(const V4Plan &p, const V3Plan &v3, unsigned R, unsigned F, 
 	return true;
 }
 
-inline int v4_launch_chan(V4Plan &p, const V3Plan &v3, const V4Launch &L, ChanArgs &ca, unsigned R, cudaStream_t st, unsigned long long *launches)
+inline int v4_launch_chan(V4Plan &p, const V3Plan &v3, const V4Launch &L, ChanArgs &ca, unsigned R, bool u8, cudaStream_t st, unsigned long long *launches)
 {
 	V4Args v;
 	v.delta = v3.d_delta;
@@ -721,7 +792,7 @@ inline int v4_launch_chan(V4Plan &p, const V3Plan &v3, const V4Launch &L, ChanAr
 	v.longRuns = L.longRuns;
 	v.totalRuns = R * L.runsPerRx;
 	v.R = R;
-	const size_t smem = kV3TableBytes + (size_t)L.warps * ((size_t)3 * p.stageBytes + 2 * (size_t)p.tapBytes);
+	const size_t smem = kV3TableBytes + (size_t)L.warps * ((size_t)(u8 ? p.ringBytesU8 : p.ringBytes) + 2 * (size_t)p.tapBytes);
 	cudaLaunchConfig_t cfg = {};
 	cudaLaunchAttribute attr[1];
 	cfg.gridDim = dim3(L.grid);
@@ -732,7 +803,7 @@ inline int v4_launch_chan(V4Plan &p, const V3Plan &v3, const V4Launch &L, ChanAr
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = p.pdl ? 1 : 0;
-	cudaError_t e = cudaLaunchKernelEx(&cfg, p.kernel, (const ChanArgs)ca, (const V4Args)v);
+	cudaError_t e = cudaLaunchKernelEx(&cfg, u8 ? p.kernelU8 : p.kernel, (const ChanArgs)ca, (const V4Args)v);
 	(*launches)++;
 	if (e == cudaSuccess)
 		e = cudaGetLastError();
