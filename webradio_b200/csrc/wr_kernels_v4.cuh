@@ -630,6 +630,10 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 
 typedef void (*V4Kernel)(const ChanArgs, const V4Args);
 
+#ifndef WR_V4_NS
+#define WR_V4_NS 3
+#endif
+constexpr int kV4Stages = WR_V4_NS;   // depth of a warp's ring of stages: the copies run kV4Stages - 1 stages ahead
 constexpr int kV4Warps = 8;           // warps per CTA: two per scheduler (up to 255 registers per thread), ring of three stages
 
 struct V4Plan {
@@ -653,12 +657,12 @@ template <int N1, int D1>
 inline void v4_fill(V4Plan &p)
 {
 	using G = V4Geo<N1, D1>;
-	p.kernel = chan_kernel_v4<N1, D1, kV4Warps, 3>;
-	p.kernelU8 = chan_kernel_v4<N1, D1, kV4Warps, 3, true>;
+	p.kernel = chan_kernel_v4<N1, D1, kV4Warps, kV4Stages>;
+	p.kernelU8 = chan_kernel_v4<N1, D1, kV4Warps, kV4Stages, true>;
 	p.kskip = G::KSKIP;
 	p.ap = G::AP;
-	p.ringBytes = v4_ring_region(3 * G::kStageBytes, G::kScratchFrames * 8u);
-	p.ringBytesU8 = v4_ring_region(3 * V4Geo<N1, D1, true>::kStageBytes, G::kScratchFrames * 8u);
+	p.ringBytes = v4_ring_region(kV4Stages * G::kStageBytes, G::kScratchFrames * 8u);
+	p.ringBytesU8 = v4_ring_region(kV4Stages * V4Geo<N1, D1, true>::kStageBytes, G::kScratchFrames * 8u);
 	p.tapBytes = G::kTapBytes;
 }
 
