@@ -639,6 +639,35 @@ def test_bank_v4_streaming_fir_raw_bytes(wro, monkeypatch, F, n1, d1, n2, d2, R,
     run_bank_vs_oracle(wro, 4, fs, F, R, synth.receiver_ifs(R, fs), [r % 4 for r in range(R)], n1, d1, n2, d2, 3, seed=F + R + 1, u8=True)
 
 
+def _v4_random_case(seed):
+    rng = np.random.default_rng(4000 + seed)
+    n1, d1, n2, d2 = [(255, 50, 64, 1), (127, 50, 64, 1), (127, 40, 64, 5)][int(rng.integers(0, 3))]
+    R = int(rng.choice([1, 2, 3, 5, 17, 33, 64, 150, 301]))
+    shared = bool(rng.integers(0, 2)) and R >= 4
+    T = max(1, R // int(rng.choice([2, 3, 7]))) if shared else R
+    kmin = 2 * ((n1 - 1) // d1 + 1)
+    # a block long enough for 32 runs per receiver, ragged against the decimation more often than not
+    m1 = int(rng.integers(32 * kmin, 32 * kmin + 900))
+    F = m1 * d1 + int(rng.integers(0, d1)) * int(rng.integers(0, 2))
+    runs = int(rng.choice([0, 0, 32, 33, 37, 45]))
+    return n1, d1, n2, d2, R, T, F, runs, bool(rng.integers(0, 2))
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_bank_v4_random_cuts(wro, monkeypatch, seed):
+    """Seeded random banks through the streaming kernel: geometry, receivers (1 .. 301; independent or shared
+    tuner streams), block length (ragged against the decimation), runs per receiver (the host's choice or forced),
+    float or raw bytes, all four modes; two blocks, up to 24 receivers against the oracle (the first and last
+    of the bank always)."""
+    n1, d1, n2, d2, R, T, F, runs, u8 = _v4_random_case(seed)
+    if runs:
+        monkeypatch.setenv("WR_V4_RUNS", str(runs))
+    fs = 2400000
+    picks = sorted(set([0, R - 1] + list(range(0, R, max(1, R // 22)))))[:24]
+    run_bank_vs_oracle(wro, 4, fs, F, T, synth.receiver_ifs(R, fs), [(r + seed) % 4 for r in range(R)], n1, d1, n2, d2, 2,
+                       seed=seed + 7, check_rx=picks, u8=u8)
+
+
 def test_bank_v4_more_runs_than_lanes(wro):
     """A bank with more receivers than one round of the grid holds at 32 runs each (1300 receivers x 42 runs
     of 12/13 outputs = 54600 runs on 37888 lanes): the warps work through TWO rounds, the second one partly

@@ -157,6 +157,8 @@ struct wr_bank {
 	int device = 0;
 	int numSMs = 148;
 	unsigned T = 0, R = 0, maxF = 0, n1 = 0, d1 = 0, n2 = 0, d2 = 0;
+	unsigned pitchF = 0;        // frames between the streams of the bank's own device blocks: maxF rounded up to even, so
+	                            // that every stream starts on the copies' boundary of the streaming channel kernel
 	unsigned maxM1 = 0, maxM2 = 0;
 	size_t dstride = 0;
 	cudaStream_t compute = nullptr, h2d = nullptr, d2h = nullptr;
@@ -431,14 +433,14 @@ int launch_block(wr_bank *b, const void *iq_dev, bool u8, size_t stream_stride, 
 	if (u8 && !useV3 && !useV4) {
 		// the older kernel families read float blocks: convert once into a scratch block
 		if (!b->d_iqf)
-			WR_CUDA(cudaMalloc(&b->d_iqf, sizeof(float) * 2 * (size_t)b->T * b->maxF));
+			WR_CUDA(cudaMalloc(&b->d_iqf, sizeof(float) * 2 * (size_t)b->T * b->pitchF));
 		dim3 grid(std::max(1u, std::min(64u, (2 * F + 1023) / 1024)), b->T);
 		u8_to_f32_kernel<<<grid, 256, 0, st>>>(static_cast<const unsigned char*>(iq_dev), b->d_iqf,
-				2 * stream_stride, 2 * (size_t)b->maxF, 2 * F);
+				2 * stream_stride, 2 * (size_t)b->pitchF, 2 * F);
 		b->launches++;
 		WR_CUDA(cudaGetLastError());
 		iq_dev = b->d_iqf;
-		stream_stride = b->maxF;
+		stream_stride = b->pitchF;
 		u8 = false;
 	}
 
@@ -753,6 +755,7 @@ wr_bank *wr_bank_create(int device, unsigned n_streams, unsigned n_receivers, un
 	wr_bank *b = new wr_bank();
 	b->device = device;
 	b->T = n_streams; b->R = n_receivers; b->maxF = max_frames;
+	b->pitchF = (max_frames + 1u) & ~1u;
 	b->n1 = n1; b->d1 = d1; b->n2 = n2; b->d2 = d2;
 	b->maxM1 = max_frames / d1;
 	b->maxM2 = b->maxM1 / d2;
@@ -1066,7 +1069,7 @@ static int submit_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframes
 	const unsigned long long t_enter = b->d_ts ? host_ns() : 0;
 	Slot &s = b->slot[b->head];
 	if (!s.d_iq && !iq_dev)
-		WR_CUDA(cudaMalloc(&s.d_iq, sizeof(float) * 2 * (size_t)b->T * b->maxF));
+		WR_CUDA(cudaMalloc(&s.d_iq, sizeof(float) * 2 * (size_t)b->T * b->pitchF));
 	if (!s.d_audio)
 		WR_CUDA(cudaMalloc(&s.d_audio, sizeof(float) * (size_t)b->R * std::max(1u, b->maxM2)));
 	const unsigned M2 = nframes / b->d1 / b->d2;
@@ -1084,7 +1087,7 @@ static int submit_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframes
 	//        its last CTA raises a counter in mapped host memory that wr_bank_wait polls -- or it
 	//        raises a counter in HBM that the copy-out stream waits for.
 	// Hand-over by events (other kernel families): events between the three streams.
-	const bool v3 = block_uses_v4(b, nframes, u8, iq_dev ? (const void*)iq_dev : (const void*)s.d_iq, b->maxF, nullptr) || block_uses_v3(b, nframes);
+	const bool v3 = block_uses_v4(b, nframes, u8, iq_dev ? (const void*)iq_dev : (const void*)s.d_iq, b->pitchF, nullptr) || block_uses_v3(b, nframes);
 	int handIn = (v3 && !iq_dev) ? b->handIn : IN_EVENT, handOut = v3 ? b->handOut : OUT_EVENT;
 	float *audio_dev = s.d_audio;
 	size_t audio_dev_stride = maxM2;
@@ -1101,10 +1104,10 @@ static int submit_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframes
 	if (iq_dev) {
 		if (dev_ready)
 			WR_CUDA(cudaStreamWaitEvent(b->compute, dev_ready, 0));
-	} else if (b->T == 1 || (nframes == b->maxF && host_pitch == nframes))
+	} else if (b->T == 1 || (nframes == b->pitchF && host_pitch == nframes))
 		WR_CUDA(cudaMemcpyAsync(s.d_iq, iq_host, fb * (size_t)nframes * b->T, cudaMemcpyHostToDevice, b->h2d));
 	else
-		WR_CUDA(cudaMemcpy2DAsync(s.d_iq, fb * (size_t)b->maxF, iq_host, fb * host_pitch,
+		WR_CUDA(cudaMemcpy2DAsync(s.d_iq, fb * (size_t)b->pitchF, iq_host, fb * host_pitch,
 				fb * (size_t)nframes, b->T, cudaMemcpyHostToDevice, b->h2d));
 	if (iq_dev) {
 		// (ordered by the event above)
@@ -1121,7 +1124,7 @@ static int submit_any(wr_bank *b, const void *iq_host, bool u8, unsigned nframes
 		WR_CUDA(cudaEventRecord(s.in_ready, b->h2d));
 		WR_CUDA(cudaStreamWaitEvent(b->compute, s.in_ready, 0));
 	}
-	int rc = launch_block(b, iq_dev ? (const void*)iq_dev : (const void*)s.d_iq, u8, b->maxF, nframes, audio_dev, audio_dev_stride,
+	int rc = launch_block(b, iq_dev ? (const void*)iq_dev : (const void*)s.d_iq, u8, b->pitchF, nframes, audio_dev, audio_dev_stride,
 			b->compute, seq, handIn, handOut);
 	if (rc != WR_OK)
 		return rc;
