@@ -274,7 +274,7 @@ int wr_bank_set_audio_format(wr_bank *b, int format);
  * the block length), 1 = v1 generic kernels (NCO table read from L2), 2 = v2 kernels (NCO table
  * resident in shared memory, tile per work item), 3 = v3 kernels (streaming ring of mixed
  * slots, packed NCO arithmetic), 4 = v4 kernels (streaming FIR, one thread per run of outputs:
- * float blocks of independent streams).  For tests and profiling. */
+ * banks large enough to fill the GPU with long runs, float or raw bytes).  For tests and profiling. */
 int wr_bank_set_variant(wr_bank *b, int variant);
 /* Which family ran the last block: 1 ... 4 (0 before the first block). */
 int wr_bank_variant_in_use(const wr_bank *b);
