@@ -498,22 +498,26 @@ def chain_record(ctx, wname, w, steps, warmup, full_cpu=True, plugin=False):
     # the job finishes when its slowest rank does: MAX over ranks of the device time
     ms = ctx.max_over_ranks([ev0.elapsed_time(ev1)])[0]
     value = shard.job_throughput(R * F * steps, ctx.world, ms) / 1e6
+    # ---- per-kernel device time (CUDA events around each kernel, same inputs, K more steps), straight behind
+    # the timed region so that it sees the same clocks (on a power-capped box the clocks sag under the
+    # sustained load below: a pass taken after it once read a kernel LONGER than the step that contains it).
+    # Three passes; the line reports the fastest pass's mean and lists all three.
+    ksteps = min(max(steps, 20), 2000)
+    kpasses = []
+    for _ in range(3):
+        bank.set_timing(True)
+        run_steps(0, ksteps)
+        chan_ms, audio_ms, nb = bank.kernel_times()
+        bank.set_timing(False)
+        kpasses.append((chan_ms / max(nb, 1), audio_ms / max(nb, 1)))
+    chan_ms_avg, audio_ms_avg = min(kpasses)
+    variant_used = bank.variant_in_use()
     # keep the load on long enough for the sampler to see it (a 20-step region of a small bank is 0.5 ms)
     t_end = time.perf_counter() + 0.4
     while time.perf_counter() < t_end:
         run_steps(0, max(steps, 50))
         bank.sync()
     clk = clocks.stop()
-
-    # ---- per-kernel device time (CUDA events around each kernel, same inputs, K more steps) ----
-    bank.set_timing(True)
-    ksteps = min(max(steps, 20), 2000)
-    run_steps(0, ksteps)
-    chan_ms, audio_ms, nb = bank.kernel_times()
-    bank.set_timing(False)
-    chan_ms_avg = chan_ms / max(nb, 1)
-    audio_ms_avg = audio_ms / max(nb, 1)
-    variant_used = bank.variant_in_use()
 
     # ---- host path: the C ABI with HOST buffers, H2D + kernels + D2H inside the timed region ----
     e2e = None
@@ -548,6 +552,7 @@ def chain_record(ctx, wname, w, steps, warmup, full_cpu=True, plugin=False):
         "algorithmic_bytes_formula": "SURVEY.md 8d: 8*F*T + 4*R*F/(D1*D2)" if fb == 8 else "SURVEY.md 8d with 2-byte frames: 2*F*T + 4*R*F/(D1*D2)",
         "kernel_own_bytes_per_launch": own, "kernel_own_gbs": own / (chan_ms_avg * 1e-3) / 1e9 if chan_ms_avg > 0 else 0.0,
         "kernel_ms": chan_ms_avg, "audio_kernel_ms": audio_ms_avg,
+        "kernel_ms_passes": [round(c, 6) for c, _ in kpasses],
         # serialised kernel times (CUDA events around each kernel); in the timed region the next block's
         # channel kernel starts under this block's demodulator kernel, so ms_per_step < their sum
         "kernel_share_of_step": chan_ms_avg / max(chan_ms_avg + audio_ms_avg, 1e-12),
