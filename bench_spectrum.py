@@ -138,13 +138,16 @@ def record(ctx, steps=None, warmup=3):
         esteps = 3
         h_in = inputs[0].cpu().pin_memory()
         h_rows = torch.empty(STREAMS, ROWS + 1, N).pin_memory()
-        hs = [fresh() for _ in range(esteps + 1)]
+        # ONE handle, warmed by a first call: a handle allocates its device blocks (2 GiB here) on first use, which
+        # is not part of a step (a fresh handle per step had put the allocation inside the timed region: 1.2-3.3 k
+        # MS/s from run to run).  A reused handle carries half a frame over, so a step yields ROWS or ROWS + 1 rows.
+        hs = [fresh()]
         hs[0].L.wr_spectrum_process(hs[0].h, h_in.data_ptr(), FRAMES, h_rows.data_ptr(), (ROWS + 1) * N)
         ctx.barrier()
         t0 = time.perf_counter()
         for i in range(esteps):
-            n = hs[i + 1].L.wr_spectrum_process(hs[i + 1].h, h_in.data_ptr(), FRAMES, h_rows.data_ptr(), (ROWS + 1) * N)
-            assert n == ROWS
+            n = hs[0].L.wr_spectrum_process(hs[0].h, h_in.data_ptr(), FRAMES, h_rows.data_ptr(), (ROWS + 1) * N)
+            assert n in (ROWS, ROWS + 1)
         torch.cuda.synchronize()
         e2e_s = ctx.max_over_ranks([time.perf_counter() - t0])[0]
         e2e = {"value": ctx.world * STREAMS * FRAMES * esteps / e2e_s / 1e6, "unit": "MSamples/s",
