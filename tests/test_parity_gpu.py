@@ -428,6 +428,35 @@ def test_spectrum_8192_kernel_families(wro, monkeypatch, family, hop):
         sp.close()
 
 
+def test_spectrum_host_path_pipelined_by_stream_groups(wro, monkeypatch):
+    """wr_spectrum_process on a large multi-stream block (16 streams x 262144 frames = 33.5 MB in): the streams go
+    through copy-in / transforms / copy-out in eight groups.  Two blocks (a partial frame carried over per stream);
+    every row of every stream bit-identical to the unpipelined call, four streams against the oracle."""
+    n, hop, T, F = 8192, 4096, 16, 262144 + 777
+    x = [np.stack([synth.structured(F, 2400000, [200000 + 5000 * t, -600000], [0, 1], start=b * F, noise_db=-35.0, stream=t)
+                   for t in range(T)]) for b in range(2)]
+    rows = {}
+    for pipe in ("1", "0"):
+        monkeypatch.setenv("WR_FFT_PIPE", pipe)
+        sp = capi.Spectrum(n, hop, T, max_frames=F)
+        try:
+            rows[pipe] = [sp.process(x[b]).copy() for b in range(2)]
+            last = np.stack([sp.get(t) for t in range(T)])
+        finally:
+            sp.close()
+        rows[pipe].append(last)
+    for b in range(3):
+        assert rows["1"][b].shape == rows["0"][b].shape
+        assert np.array_equal(rows["1"][b].view(np.uint32), rows["0"][b].view(np.uint32)), f"pipelined vs plain, block {b}"
+    for t in (1, 6, 9, 15):
+        o = wro.Spectrum(n, hop)
+        for b in range(2):
+            want = o.process(x[b][t])
+            assert rows["1"][b].shape[1] == want.shape[0]
+            for m in range(0, want.shape[0], 7):
+                spectrum_close(rows["1"][b][t, m], want[m], f"stream {t} block {b} row {m}")
+
+
 def test_spectrum_before_first_frame():
     sp = capi.Spectrum(512)
     assert np.all(np.isneginf(sp.get(0)))  # reference: outbuf is zero before the first transform

@@ -612,6 +612,11 @@ struct wr_spectrum {
 	unsigned char *d_palette = nullptr;   // [N] scratch of wr_spectrum_get_palette
 	bool haveLast = false;
 	cudaStream_t lastStream = nullptr; // stream of the most recent launch
+	// host path of large multi-stream blocks: groups of streams go through copy-in / transforms / copy-out pipelined
+	static constexpr int kGroups = 8;
+	cudaStream_t h2d = nullptr, d2h = nullptr;
+	cudaEvent_t inReady[kGroups] = {}, rowsReady[kGroups] = {}, outDone = nullptr;
+	bool noPipe = false;               // env WR_FFT_PIPE=0: one copy in, the kernels, one copy out
 	bool forceV1 = false;              // env WR_FFT_V1=1: radix-4 shared-memory kernel for every size
 	bool noV3 = false;                 // env WR_FFT_V3=0: never the persistent bulk-copy kernel
 	bool noV4 = false;                 // env WR_FFT_V4=0: 8192-point transforms stay with v3 (one CTA per SM)
@@ -639,17 +644,29 @@ void free_spectrum(wr_spectrum *s)
 	cudaFree(s->d_palette);
 	if (s->st)
 		cudaStreamDestroy(s->st);
+	if (s->h2d)
+		cudaStreamDestroy(s->h2d);
+	if (s->d2h)
+		cudaStreamDestroy(s->d2h);
+	for (int i = 0; i < wr_spectrum::kGroups; i++) {
+		if (s->inReady[i]) cudaEventDestroy(s->inReady[i]);
+		if (s->rowsReady[i]) cudaEventDestroy(s->rowsReady[i]);
+	}
+	if (s->outDone)
+		cudaEventDestroy(s->outDone);
 	cudaGetLastError();
 	delete s;
 }
 
-long run(wr_spectrum *s, const float *iq_dev, size_t in_stride, unsigned nframes,
+// The kernels of one call for streams [t0, t0 + nT): iq_dev and rows_dev point at stream t0.  The
+// handle's state (carry side, carried frames) is advanced by the caller once every stream is through.
+long run_part(wr_spectrum *s, unsigned t0, unsigned nT, const float *iq_dev, size_t in_stride, unsigned nframes,
 		float *rows_dev, size_t row_stride, cudaStream_t st)
 {
 	const size_t avail = (size_t)s->ncarry + nframes;
 	const unsigned nrows = avail >= s->N ? (unsigned)((avail - s->N) / s->hop + 1) : 0;
 	SpecArgs a;
-	a.carry = s->d_carry[s->cur];
+	a.carry = s->d_carry[s->cur] + (size_t)t0 * s->N;
 	a.carry_stride = s->N;
 	a.ncarry = s->ncarry;
 	a.in = reinterpret_cast<const float2*>(iq_dev);
@@ -658,7 +675,7 @@ long run(wr_spectrum *s, const float *iq_dev, size_t in_stride, unsigned nframes
 	a.twiddle = s->d_twiddle;
 	a.rows = rows_dev;
 	a.row_stride = row_stride;
-	a.last = s->d_last;
+	a.last = s->d_last + (size_t)t0 * s->N;
 	a.N = s->N;
 	a.logN = s->logN;
 	a.hop = s->hop;
@@ -681,7 +698,7 @@ long run(wr_spectrum *s, const float *iq_dev, size_t in_stride, unsigned nframes
 			g.a = a;
 			g.row0 = row0;
 			const unsigned nrows3 = nrows - row0;
-			const unsigned long long total = (unsigned long long)nrows3 * s->T;
+			const unsigned long long total = (unsigned long long)nrows3 * nT;
 			const unsigned C = s->N / s->hop, R1 = s->N / 256;
 			// 8192-point transforms: the two-CTAs-per-SM kernel (half the work buffer, the frame's own chunks only)
 			const bool v4 = R1 == 32 && !s->noV4;
@@ -693,8 +710,8 @@ long run(wr_spectrum *s, const float *iq_dev, size_t in_stride, unsigned nframes
 			g.runsPerStream = (nrows3 + g.rowsPerRun - 1) / g.rowsPerRun;
 			const size_t smem = v4 ? sizeof(float2) * ((size_t)16 * kRowPitch + 256 + (size_t)C * s->hop)
 					: sizeof(float2) * ((size_t)R1 * kRowPitch + 256 + (size_t)(C + 1) * s->hop);
-			const unsigned long long runs = (unsigned long long)g.runsPerStream * s->T;
-			g.nStreams = s->T;
+			const unsigned long long runs = (unsigned long long)g.runsPerStream * nT;
+			g.nStreams = nT;
 			// persistent: one CTA per SM (two when two fit), each walking the run list with stride gridDim.x
 			const dim3 grid3((unsigned)std::min<unsigned long long>(runs, (unsigned long long)s->numSMs * (smem <= 100 * 1024 ? 2 : 1)));
 			void (*k3)(const SpecArgs3) = nullptr;
@@ -718,7 +735,7 @@ long run(wr_spectrum *s, const float *iq_dev, size_t in_stride, unsigned nframes
 			WR_CUDA(cudaGetLastError());
 			nrows2 = row0;                          // what is left for the kernels below
 		}
-		dim3 grid(nrows2, s->T);
+		dim3 grid(nrows2, nT);
 		if (nrows2 == 0) {
 			// nothing left
 		} else if (s->N >= 512 && !s->forceV1) {
@@ -745,14 +762,29 @@ long run(wr_spectrum *s, const float *iq_dev, size_t in_stride, unsigned nframes
 	const size_t consumed = (size_t)nrows * s->hop;
 	const unsigned left = (unsigned)(avail - consumed);
 	if (left) {
-		dim3 grid(std::max(1u, std::min(8u, (left + 255) / 256)), s->T);
-		spectrum_carry_kernel<<<grid, 256, 0, st>>>(a, s->d_carry[s->cur ^ 1], consumed, left);
+		dim3 grid(std::max(1u, std::min(8u, (left + 255) / 256)), nT);
+		spectrum_carry_kernel<<<grid, 256, 0, st>>>(a, s->d_carry[s->cur ^ 1] + (size_t)t0 * s->N, consumed, left);
 		s->launches++;
 		WR_CUDA(cudaGetLastError());
 	}
-	s->cur ^= 1;
-	s->ncarry = left;
 	return (long)nrows;
+}
+
+// every stream went through run_part: the carried frames are on the other side now
+void advance(wr_spectrum *s, unsigned nframes, long nrows)
+{
+	const size_t avail = (size_t)s->ncarry + nframes;
+	s->cur ^= 1;
+	s->ncarry = (unsigned)(avail - (size_t)nrows * s->hop);
+}
+
+long run(wr_spectrum *s, const float *iq_dev, size_t in_stride, unsigned nframes,
+		float *rows_dev, size_t row_stride, cudaStream_t st)
+{
+	const long nrows = run_part(s, 0, s->T, iq_dev, in_stride, nframes, rows_dev, row_stride, st);
+	if (nrows >= 0)
+		advance(s, nframes, nrows);
+	return nrows;
 }
 
 } // namespace
@@ -820,6 +852,8 @@ wr_spectrum *wr_spectrum_create(int device, unsigned fft_size, unsigned hop, uns
 		s->noV3 = atoi(e) == 0;
 	if (const char *e = getenv("WR_FFT_V4"))
 		s->noV4 = atoi(e) == 0;
+	if (const char *e = getenv("WR_FFT_PIPE"))
+		s->noPipe = atoi(e) == 0;
 	if (const char *e = getenv("WR_FFT_RUNS"))
 		s->runsPerCta = (unsigned)std::max(0, atoi(e));
 	WR_SPEC_ALLOC(cudaDeviceGetAttribute(&s->numSMs, cudaDevAttrMultiProcessorCount, device));
@@ -849,6 +883,46 @@ long wr_spectrum_process(wr_spectrum *s, const float *iq_host, unsigned nframes,
 		WR_CUDA(cudaMalloc(&s->d_in, sizeof(float) * 2 * (size_t)s->T * s->maxF));
 	if (rows_host && !s->d_rows)
 		WR_CUDA(cudaMalloc(&s->d_rows, sizeof(float) * (size_t)s->T * s->maxRows * s->N));
+	// Large multi-stream blocks with a row buffer (a waterfall of many tuners: BASELINE config 4 moves 1 GiB in
+	// and 1 GiB out per call): the streams go through in groups, so that a group's copy-in runs under the
+	// transforms of the group before it and under the copy-out of the one before that (the link is full duplex).
+	if (rows_host && nframes && !s->noPipe && s->T >= 2 * wr_spectrum::kGroups
+			&& sizeof(float) * 2 * (size_t)nframes * s->T >= ((size_t)32 << 20)) {
+		constexpr int G = wr_spectrum::kGroups;
+		if (!s->h2d) {
+			WR_CUDA(cudaStreamCreateWithFlags(&s->h2d, cudaStreamNonBlocking));
+			WR_CUDA(cudaStreamCreateWithFlags(&s->d2h, cudaStreamNonBlocking));
+			for (int i = 0; i < G; i++) {
+				WR_CUDA(cudaEventCreateWithFlags(&s->inReady[i], cudaEventDisableTiming));
+				WR_CUDA(cudaEventCreateWithFlags(&s->rowsReady[i], cudaEventDisableTiming));
+			}
+			WR_CUDA(cudaEventCreateWithFlags(&s->outDone, cudaEventDisableTiming));
+		}
+		long nrows = 0;
+		for (int gi = 0; gi < G; gi++) {
+			const unsigned t0 = (unsigned)((unsigned long long)s->T * gi / G), t1 = (unsigned)((unsigned long long)s->T * (gi + 1) / G);
+			const unsigned nT = t1 - t0;
+			float *din = s->d_in + (size_t)t0 * 2 * s->maxF;
+			float *drows = s->d_rows + (size_t)t0 * s->maxRows * s->N;
+			WR_CUDA(cudaMemcpy2DAsync(din, sizeof(float) * 2 * (size_t)s->maxF, iq_host + (size_t)t0 * 2 * nframes,
+					sizeof(float) * 2 * (size_t)nframes, sizeof(float) * 2 * (size_t)nframes, nT, cudaMemcpyHostToDevice, s->h2d));
+			WR_CUDA(cudaEventRecord(s->inReady[gi], s->h2d));
+			WR_CUDA(cudaStreamWaitEvent(s->st, s->inReady[gi], 0));
+			nrows = run_part(s, t0, nT, din, s->maxF, nframes, drows, (size_t)s->maxRows * s->N, s->st);
+			if (nrows < 0)
+				return nrows;
+			WR_CUDA(cudaEventRecord(s->rowsReady[gi], s->st));
+			if (nrows > 0) {
+				WR_CUDA(cudaStreamWaitEvent(s->d2h, s->rowsReady[gi], 0));
+				WR_CUDA(cudaMemcpy2DAsync(rows_host + (size_t)t0 * row_stride, sizeof(float) * row_stride, drows,
+						sizeof(float) * (size_t)s->maxRows * s->N, sizeof(float) * (size_t)nrows * s->N, nT, cudaMemcpyDeviceToHost, s->d2h));
+			}
+		}
+		advance(s, nframes, nrows);
+		WR_CUDA(cudaStreamSynchronize(s->st));
+		WR_CUDA(cudaStreamSynchronize(s->d2h));
+		return nrows;
+	}
 	if (nframes)
 		WR_CUDA(cudaMemcpy2DAsync(s->d_in, sizeof(float) * 2 * (size_t)s->maxF, iq_host, sizeof(float) * 2 * (size_t)nframes,
 				sizeof(float) * 2 * (size_t)nframes, s->T, cudaMemcpyHostToDevice, s->st));
