@@ -17,8 +17,8 @@ run smoke memcheck python -c "import __graft_entry__ as g; g.smoke()"
 run parity memcheck python -m pytest tests/test_parity_gpu.py -q -x --timeout=250 -k "ragged or golden_chain or u8_ingest or pipelined or v3_ragged"
 # round 2: the streaming channel kernel (cuts with one / two receivers per warp, ragged ends), the sliding-window
 # audio FIR, the spectrum kernels (v4 / v3 / v2, both hops), the shared upload
-run v4 memcheck python -m pytest tests/test_parity_gpu.py -q -x --timeout=270 -k "v4_streaming or v4_is_what or sliding_window"
-run spectrum memcheck python -m pytest tests/test_parity_gpu.py -q -x --timeout=270 -k "spectrum_8192 or spectrum_rows or share_one_upload"
+run v4 memcheck python -m pytest tests/test_parity_gpu.py -q -x --timeout=270 -k "v4_streaming or v4_is_what or sliding_window or random_cuts or shared_tuner"
+run spectrum memcheck python -m pytest tests/test_parity_gpu.py -q -x --timeout=270 -k "spectrum_8192 or spectrum_rows or share_one_upload or pipelined_by_stream"
 run v4 synccheck python -m pytest tests/test_parity_gpu.py -q -x --timeout=270 -k "v4_is_what"
 run smoke synccheck python -c "import __graft_entry__ as g; g.smoke()"
 run smoke racecheck python -c "import __graft_entry__ as g; g.smoke()"
