@@ -919,20 +919,28 @@ def _full_size_bank(w, taps_seed):
     return bank, t1, t2, ifs, modes
 
 
+def _oracle_every_receiver(orx, block_of):
+    """The oracle chain of every receiver of a bank over one block, one receiver per host thread at a time
+    (the oracle's entry points are plain C calls: ctypes drops the interpreter lock around them)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max(1, os.cpu_count() or 1)) as pool:
+        return list(pool.map(lambda r: orx[r].process(block_of(r)), range(len(orx))))
+
+
 def test_bank_cfg3_full_size(wro):
     """BASELINE config 3 at FULL size: 1024 independent AM streams x 102400 frames, 255 taps, decim 50,
     fed as raw bytes (210 MB per block on the host instead of 839 MB).  Two blocks.  Size-independent
     property: streams 512..1023 repeat streams 0..511 and the receivers on them share IF and taps, so
-    their audio must be bit-identical; 32 receivers spread over the bank are checked against the oracle."""
+    their audio must be bit-identical; every receiver of the first half (and so, by the twin property, all
+    1024) is checked against the oracle."""
     w = synth.WORKLOADS["cfg3"]
     R, T, F = w["n_rx"], w["n_streams"], w["frames"]
     bank, t1, t2, ifs, modes = _full_size_bank(w, 31)
     try:
         for r in range(R // 2, R):
             bank.set_if(r, int(ifs[r - R // 2]), w["fs"])
-        picks = sorted(set([0, 1, 255, 511, 512, 700, 1022, 1023] + list(range(17, R, 41))))[:32]
-        assert len(picks) == 32
-        orx = {r: wro.Rx(w["fs"], int(ifs[r % (R // 2)]), t1, w["d1"], int(modes[r]), t2, w["d2"]) for r in picks}
+        orx = [wro.Rx(w["fs"], int(ifs[r]), t1, w["d1"], int(modes[r]), t2, w["d2"]) for r in range(R // 2)]
         rng = np.random.default_rng(32)
         for b in range(2):
             half = rng.integers(0, 256, (T // 2, F, 2), dtype=np.uint8)
@@ -940,9 +948,10 @@ def test_bank_cfg3_full_size(wro):
             audio = bank.process_u8(u8)
             assert audio.shape == (R, F // w["d1"] // w["d2"])
             assert_biteq(audio[:R // 2], audio[R // 2:], f"twin streams, block {b}")
-            for r in picks:
-                assert_biteq(audio[r], orx[r].process(u8_to_iq(u8[r]).ravel()), f"cfg3 full rx{r} b{b}")
-            del u8, half
+            want = _oracle_every_receiver(orx, lambda r: u8_to_iq(half[r]).ravel())
+            for r in range(R // 2):
+                assert_biteq(audio[r], want[r], f"cfg3 full rx{r} b{b}")
+            del u8, half, want
         assert bank.variant_in_use() == 4
     finally:
         bank.close()
@@ -951,17 +960,14 @@ def test_bank_cfg3_full_size(wro):
 def test_bank_cfg3_full_size_float_one_launch(wro):
     """BASELINE config 3 at FULL size as bench.py runs it: float IQ resident in HBM, ONE launch per block of
     the streaming channel kernel (v4: every receiver cut into 37 runs of 55/56 outputs, a warp's 32 runs
-    straddling two receivers).  Two blocks (carried NCO phase and both FIR histories); 40 receivers
-    against the oracle -- the first and last of the bank, both sides of warp boundaries (run 32 s falls
-    into receiver (32 s) // 37), and a spread over the rest."""
+    straddling two receivers).  Two blocks (carried NCO phase and both FIR histories); EVERY ONE of the 1024
+    receivers against the oracle, all 2048 audio samples of both blocks bit for bit."""
     import torch
     w = synth.WORKLOADS["cfg3"]
     R, T, F = w["n_rx"], w["n_streams"], w["frames"]
     bank, t1, t2, ifs, modes = _full_size_bank(w, 33)
     try:
-        picks = sorted(set([0, 1, 2, 6, 7, 36, 37, 863, 864, 865, 1021, 1022, 1023] + list(range(11, R, 37))))[:40]
-        assert len(picks) == 40
-        orx = {r: wro.Rx(w["fs"], int(ifs[r]), t1, w["d1"], int(modes[r]), t2, w["d2"]) for r in picks}
+        orx = [wro.Rx(w["fs"], int(ifs[r]), t1, w["d1"], int(modes[r]), t2, w["d2"]) for r in range(R)]
         m2 = F // w["d1"] // w["d2"]
         # torch works in the bank's own stream (torch's default stream is handle 0, which the C ABI reads as
         # "the bank's stream" -- and that one does not synchronise with the legacy default stream)
@@ -969,15 +975,18 @@ def test_bank_cfg3_full_size_float_one_launch(wro):
         g = torch.Generator(device="cuda").manual_seed(34)
         for b in range(2):
             with torch.cuda.stream(stream):
-                # the RTL-SDR lattice (b - 128) / 128, generated on the device; only the picked streams come back
+                # the RTL-SDR lattice (b - 128) / 128, generated on the device
                 d_iq = (torch.randint(0, 256, (T, F, 2), device="cuda", generator=g, dtype=torch.int16).float() - 128.0) / 128.0
                 d_audio = torch.full((R, m2), 7.0, device="cuda")
                 bank.process_device(d_iq.data_ptr(), F, F, d_audio.data_ptr(), m2, stream.cuda_stream)
                 audio = d_audio.cpu().numpy()
-                for r in picks:
-                    assert_biteq(audio[r], orx[r].process(d_iq[r].cpu().numpy().ravel()), f"cfg3 float full rx{r} b{b}")
-                assert not (audio == 7.0).any()
+                iq = d_iq.cpu().numpy().reshape(T, 2 * F)
                 del d_iq, d_audio
+            assert not (audio == 7.0).any()
+            want = _oracle_every_receiver(orx, lambda r: iq[r % T])
+            for r in range(R):
+                assert_biteq(audio[r], want[r], f"cfg3 float full rx{r} b{b}")
+            del iq, want
         assert bank.variant_in_use() == 4
         assert bank.get_phase(5) == (capi.phase_step(int(ifs[5]), w["fs"]) * F * 2) & 0x7FFFFFFF
     finally:
@@ -1020,14 +1029,13 @@ def test_bank_audio_fir_sliding_window_ragged(wro):
 def test_bank_cfg5_full_size_float_one_launch(wro):
     """BASELINE config 5, one GPU's share at FULL size as bench.py runs it: float IQ resident in HBM, one launch
     per block of the streaming channel kernel on SHARED tuners (16 tuners x 64 mixed-mode receivers, runs of
-    277 outputs).  Two blocks; 24 receivers (all four modes, several tuners) against the oracle."""
+    277 outputs).  Two blocks; EVERY ONE of the 1024 receivers (all four modes) against the oracle."""
     import torch
     w = synth.WORKLOADS["cfg5"]
     R, T, F = w["n_rx"], w["n_streams"], w["frames"]
     bank, t1, t2, ifs, modes = _full_size_bank(w, 53)
     try:
-        picks = sorted(set([0, 1, 2, 3, 17, 130, 515, 516, 777, 1021, 1022, 1023] + list(range(40, R, 83))))[:24]
-        orx = {r: wro.Rx(w["fs"], int(ifs[r]), t1, w["d1"], int(modes[r]), t2, w["d2"]) for r in picks}
+        orx = [wro.Rx(w["fs"], int(ifs[r]), t1, w["d1"], int(modes[r]), t2, w["d2"]) for r in range(R)]
         m2 = F // w["d1"] // w["d2"]
         stream = torch.cuda.ExternalStream(bank.stream())
         for b in range(2):
@@ -1039,12 +1047,12 @@ def test_bank_cfg5_full_size_float_one_launch(wro):
                 audio = d_audio.cpu().numpy()
             assert bank.variant_in_use() == 4
             assert not (audio == 7.0).any()
-            for r in picks:
-                want = orx[r].process(iq[r % T])
+            want = _oracle_every_receiver(orx, lambda r: iq[r % T])
+            for r in range(R):
                 if int(modes[r]) == capi.FM:
-                    assert_fm(audio[r], want, f"cfg5 float full rx{r} b{b}", audio=True)
+                    assert_fm(audio[r], want[r], f"cfg5 float full rx{r} b{b}", audio=True)
                 else:
-                    assert_biteq(audio[r], want, f"cfg5 float full rx{r} b{b}")
+                    assert_biteq(audio[r], want[r], f"cfg5 float full rx{r} b{b}")
         for r in range(0, R, 37):
             assert bank.get_phase(r) == (capi.phase_step(int(ifs[r]), w["fs"]) * F * 2) & 0x7FFFFFFF
     finally:
@@ -1053,24 +1061,24 @@ def test_bank_cfg5_full_size_float_one_launch(wro):
 
 def test_bank_cfg5_full_size(wro):
     """BASELINE config 5, one GPU's share at FULL size: 16 tuners x 64 mixed-mode receivers, 409600-frame
-    blocks at 10 MSPS, 127 taps /40, 64 taps /5.  Two blocks; 12 receivers (all four modes, several
-    tuners) against the oracle, and the phase accumulators of all 1024 against the closed form."""
+    blocks at 10 MSPS, 127 taps /40, 64 taps /5, fed as raw bytes.  Two blocks; every one of the 1024 receivers
+    (all four modes) against the oracle, and phase accumulators against the closed form."""
     w = synth.WORKLOADS["cfg5"]
     R, T, F = w["n_rx"], w["n_streams"], w["frames"]
     bank, t1, t2, ifs, modes = _full_size_bank(w, 51)
     try:
-        picks = [0, 1, 2, 3, 17, 130, 515, 516, 777, 1021, 1022, 1023]
-        orx = {r: wro.Rx(w["fs"], int(ifs[r]), t1, w["d1"], int(modes[r]), t2, w["d2"]) for r in picks}
+        orx = [wro.Rx(w["fs"], int(ifs[r]), t1, w["d1"], int(modes[r]), t2, w["d2"]) for r in range(R)]
         rng = np.random.default_rng(52)
         for b in range(2):
             u8 = rng.integers(0, 256, (T, F, 2), dtype=np.uint8)
             audio = bank.process_u8(u8)
-            for r in picks:
-                want = orx[r].process(u8_to_iq(u8[r % T]).ravel())
+            iq = [u8_to_iq(u8[t]).ravel() for t in range(T)]
+            want = _oracle_every_receiver(orx, lambda r: iq[r % T])
+            for r in range(R):
                 if int(modes[r]) == capi.FM:
-                    assert_fm(audio[r], want, f"cfg5 full rx{r} b{b}", audio=True)
+                    assert_fm(audio[r], want[r], f"cfg5 full rx{r} b{b}", audio=True)
                 else:
-                    assert_biteq(audio[r], want, f"cfg5 full rx{r} b{b}")
+                    assert_biteq(audio[r], want[r], f"cfg5 full rx{r} b{b}")
         for r in range(0, R, 37):
             assert bank.get_phase(r) == (capi.phase_step(int(ifs[r]), w["fs"]) * F * 2) & 0x7FFFFFFF
         assert bank.variant_in_use() == 4      # (the streaming kernel: the bank fills the grid with long runs)
@@ -1080,25 +1088,27 @@ def test_bank_cfg5_full_size(wro):
 
 def test_spectrum_cfg4_full_size(wro):
     """BASELINE config 4 at FULL size: 8192-point transforms at hop 4096 over 256 streams of 528384 frames
-    (128 rows per stream, 32768 transforms, 1 GiB in, 1 GiB out).  Size-independent property: the 256
-    streams carry the same samples, so every stream's rows must be bit-identical to stream 0's; the first,
-    a middle and the last row of stream 0 are compared with the oracle at the north_star tolerance."""
-    n, hop, T = 8192, 4096, 256
+    (128 rows per stream, 32768 transforms, 1 GiB in, 1 GiB out).  Stream t carries the base signal from hop
+    (t mod 8) on, so eight different signals are in the bank: ALL 128 rows of streams 0..7 are compared with
+    the oracle at the north_star tolerance (row m of stream s is the oracle's row m + s of the long signal),
+    and -- size-independent property -- every other stream must be bit-identical to the stream of 0..7 that
+    carries the same samples."""
+    n, hop, T, S = 8192, 4096, 256, 8
     F = hop * 129
-    base = synth.structured(F, 2400000, [300000, -700000, 15000], [0, 1, 2], noise_db=-40.0)
+    base = synth.structured(F + (S - 1) * hop, 2400000, [300000, -700000, 15000], [0, 1, 2], noise_db=-40.0).reshape(-1, 2)
     sp = capi.Spectrum(n, hop, T, max_frames=F)
     try:
-        iq = np.ascontiguousarray(np.broadcast_to(base.reshape(1, F, 2), (T, F, 2)))
+        iq = np.stack([base[(t % S) * hop:(t % S) * hop + F] for t in range(T)])
         rows = sp.process(iq)
         del iq
         assert rows.shape == (T, 128, n)
-        ref0 = rows[0].view(np.uint32)
-        for t in range(1, T):
-            assert np.array_equal(rows[t].view(np.uint32), ref0), f"stream {t} differs from stream 0"
-        want = wro.Spectrum(n, hop).process(base)
-        assert want.shape[0] == 128
-        for m in (0, 63, 127):
-            spectrum_close(rows[0, m], want[m], f"cfg4 full row {m}")
-        spectrum_close(sp.get(T - 1), want[127], "getSpectrum of the last stream")
+        for t in range(S, T):
+            assert np.array_equal(rows[t].view(np.uint32), rows[t % S].view(np.uint32)), f"stream {t} differs from stream {t % S}"
+        want = wro.Spectrum(n, hop).process(base.ravel())
+        assert want.shape[0] == 128 + S - 1
+        for s_ in range(S):
+            for m in range(128):
+                spectrum_close(rows[s_, m], want[m + s_], f"cfg4 full stream {s_} row {m}")
+        spectrum_close(sp.get(T - 1), want[127 + (T - 1) % S], "getSpectrum of the last stream")
     finally:
         sp.close()
