@@ -68,8 +68,8 @@ def parity_check(rows_dev, first_stream):
     from oracle import wro
     worst = 0.0
     checked = 0
-    for s in (0, STREAMS // 2, STREAMS - 1):
-        x = synth.lattice_noise(HOP * 5, stream=first_stream + s)       # the first four transforms of the stream
+    for s in sorted({int(v) for v in np.linspace(0, STREAMS - 1, 8)}):
+        x = synth.lattice_noise(FRAMES, stream=first_stream + s)        # every transform of eight streams
         want = wro.Spectrum(N, HOP).process(x, rows=True).astype(np.float64)
         got = rows_dev[s, :want.shape[0]].cpu().numpy().astype(np.float64)
         mg, mw = 10 ** (got / 20), 10 ** (want / 20)
