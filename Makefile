@@ -129,10 +129,13 @@ check: lib harness harness-mock oracle
 	python -m pytest tests -q -m "not gpu"
 
 # stand-alone micro-benchmarks (run on the GPU box; build/ travels with gpurun)
-tools: build/ubench_copy
+tools: build/ubench_copy build/ubench_dsmem
 build/ubench_copy: tools/ubench_copy.cu
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O2 -o $@ $<
+build/ubench_dsmem: tools/ubench_dsmem.cu
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -o $@ $<
 
 clean:
 	rm -rf build $(LIB) $(HARNESS) $(HARNESS_MOCK)
