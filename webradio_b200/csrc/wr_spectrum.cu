@@ -898,25 +898,36 @@ long wr_spectrum_process(wr_spectrum *s, const float *iq_host, unsigned nframes,
 			}
 			WR_CUDA(cudaEventCreateWithFlags(&s->outDone, cudaEventDisableTiming));
 		}
-		long nrows = 0;
-		for (int gi = 0; gi < G; gi++) {
-			const unsigned t0 = (unsigned)((unsigned long long)s->T * gi / G), t1 = (unsigned)((unsigned long long)s->T * (gi + 1) / G);
-			const unsigned nT = t1 - t0;
-			float *din = s->d_in + (size_t)t0 * 2 * s->maxF;
-			float *drows = s->d_rows + (size_t)t0 * s->maxRows * s->N;
-			WR_CUDA(cudaMemcpy2DAsync(din, sizeof(float) * 2 * (size_t)s->maxF, iq_host + (size_t)t0 * 2 * nframes,
-					sizeof(float) * 2 * (size_t)nframes, sizeof(float) * 2 * (size_t)nframes, nT, cudaMemcpyHostToDevice, s->h2d));
-			WR_CUDA(cudaEventRecord(s->inReady[gi], s->h2d));
-			WR_CUDA(cudaStreamWaitEvent(s->st, s->inReady[gi], 0));
-			nrows = run_part(s, t0, nT, din, s->maxF, nframes, drows, (size_t)s->maxRows * s->N, s->st);
-			if (nrows < 0)
-				return nrows;
-			WR_CUDA(cudaEventRecord(s->rowsReady[gi], s->st));
-			if (nrows > 0) {
-				WR_CUDA(cudaStreamWaitEvent(s->d2h, s->rowsReady[gi], 0));
-				WR_CUDA(cudaMemcpy2DAsync(rows_host + (size_t)t0 * row_stride, sizeof(float) * row_stride, drows,
-						sizeof(float) * (size_t)s->maxRows * s->N, sizeof(float) * (size_t)nrows * s->N, nT, cudaMemcpyDeviceToHost, s->d2h));
+		// (a failure half-way must not leave copies in flight on the caller's buffers)
+		auto groups = [&]() -> long {
+			long nrows = 0;
+			for (int gi = 0; gi < G; gi++) {
+				const unsigned t0 = (unsigned)((unsigned long long)s->T * gi / G), t1 = (unsigned)((unsigned long long)s->T * (gi + 1) / G);
+				const unsigned nT = t1 - t0;
+				float *din = s->d_in + (size_t)t0 * 2 * s->maxF;
+				float *drows = s->d_rows + (size_t)t0 * s->maxRows * s->N;
+				WR_CUDA(cudaMemcpy2DAsync(din, sizeof(float) * 2 * (size_t)s->maxF, iq_host + (size_t)t0 * 2 * nframes,
+						sizeof(float) * 2 * (size_t)nframes, sizeof(float) * 2 * (size_t)nframes, nT, cudaMemcpyHostToDevice, s->h2d));
+				WR_CUDA(cudaEventRecord(s->inReady[gi], s->h2d));
+				WR_CUDA(cudaStreamWaitEvent(s->st, s->inReady[gi], 0));
+				nrows = run_part(s, t0, nT, din, s->maxF, nframes, drows, (size_t)s->maxRows * s->N, s->st);
+				if (nrows < 0)
+					return nrows;
+				WR_CUDA(cudaEventRecord(s->rowsReady[gi], s->st));
+				if (nrows > 0) {
+					WR_CUDA(cudaStreamWaitEvent(s->d2h, s->rowsReady[gi], 0));
+					WR_CUDA(cudaMemcpy2DAsync(rows_host + (size_t)t0 * row_stride, sizeof(float) * row_stride, drows,
+							sizeof(float) * (size_t)s->maxRows * s->N, sizeof(float) * (size_t)nrows * s->N, nT, cudaMemcpyDeviceToHost, s->d2h));
+				}
 			}
+			return nrows;
+		};
+		const long nrows = groups();
+		if (nrows < 0) {
+			cudaStreamSynchronize(s->h2d);
+			cudaStreamSynchronize(s->st);
+			cudaStreamSynchronize(s->d2h);
+			return nrows;
 		}
 		advance(s, nframes, nrows);
 		WR_CUDA(cudaStreamSynchronize(s->st));
