@@ -84,3 +84,26 @@ def test_gpu_and_reference_arm_name_the_same_config():
     # SURVEY.md 8d algorithmic bytes
     assert bench.algorithmic_bytes(bench.synth.WORKLOADS["cfg3"]) == 8 * 102400 * 1024 + 4 * 1024 * 2048
     assert bench.algorithmic_bytes(bench.synth.WORKLOADS["cfg2"]) == 819200 + 524288
+
+
+def test_in_run_parity_check_covers_every_receiver_and_refuses_a_wrong_block(wro):
+    """bench.parity_check: the whole bank's block 0 against the oracle, spread over the host threads; a single
+    wrong audio sample anywhere means no number is reported."""
+    import numpy as np
+    import pytest
+    sys.path.insert(0, ROOT)
+    import bench
+    from webradio_b200 import synth
+    w = synth.WORKLOADS["cfg2"]
+    R, F = w["n_rx"], w["frames"]
+    rng = np.random.default_rng(3)
+    t1 = (rng.uniform(-1, 1, w["n1"]) / w["n1"]).astype(np.float32)
+    t2 = (rng.uniform(-1, 1, w["n2"]) / w["n2"]).astype(np.float32)
+    ifs, modes = synth.workload_ifs(w), synth.workload_modes(w)
+    block = synth.lattice_noise(F, stream=11)
+    audio = np.stack([wro.Rx(w["fs"], int(ifs[r]), t1, w["d1"], int(modes[r]), t2, w["d2"]).process(block) for r in range(R)])
+    rec = bench.parity_check(w, audio, np.arange(R), 11, t1, t2)
+    assert rec["receivers_checked"] == R == rec["receivers_in_bank"] and rec["bit_exact"] and rec["receivers_differing"] == 0
+    audio[R - 1, 17] += np.float32(1e-3)
+    with pytest.raises(SystemExit):
+        bench.parity_check(w, audio, np.arange(R), 11, t1, t2)
