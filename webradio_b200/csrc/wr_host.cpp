@@ -109,8 +109,12 @@ static inline float lo3_F(int s)
 
 static inline float lo3_poly(float y)
 {
+#if WR_LO3_DEGREE == 3
 	float p = fmaf(y, WR_LO3_C3, WR_LO3_C2);
 	p = fmaf(y, p, WR_LO3_C1);
+#else
+	const float p = fmaf(y, WR_LO3_C2, WR_LO3_C1);
+#endif
 	return fmaf(y, p, WR_LO3_C0);
 }
 

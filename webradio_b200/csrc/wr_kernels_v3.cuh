@@ -207,7 +207,10 @@ __device__ __forceinline__ void mbar_wait_fir(uint32_t bar, unsigned parity) { m
 
 // Packed constants of the table reconstruction, built once per thread.
 struct Lo3Regs {
-	f2_t tscale, tbias, slotk, slotm, eps, c0, c1, c2, c3;
+	f2_t tscale, tbias, slotk, slotm, eps, c0, c1, c2;
+#if WR_LO3_DEGREE == 3
+	f2_t c3;
+#endif
 	uint32_t cbase;   // shared-space address of slot 0 minus 2 * WR_LO3_SLOTBITS (mod 2^32)
 	uint32_t hi;      // 0x4B00: exponent bytes of the float index
 };
@@ -223,7 +226,9 @@ __device__ __forceinline__ Lo3Regs lo3_regs(float eps, uint32_t dmid32, uint32_t
 	k.c0 = f2_pack(WR_LO3_C0, WR_LO3_C0);
 	k.c1 = f2_pack(WR_LO3_C1, WR_LO3_C1);
 	k.c2 = f2_pack(WR_LO3_C2, WR_LO3_C2);
+#if WR_LO3_DEGREE == 3
 	k.c3 = f2_pack(WR_LO3_C3, WR_LO3_C3);
+#endif
 	k.cbase = dmid32 - 2u * (uint32_t)WR_LO3_SLOTBITS;
 	k.hi = hi;
 	return k;
@@ -244,8 +249,12 @@ __device__ __forceinline__ void lo3_sincos(uint32_t qb, const Lo3Regs &k, float 
 	const f2_t Y = f2_mul(T, T);
 	const f2_t Z = f2_fma(f2_neg(Y), T, T);        // t - t^3
 	const f2_t U = f2_fma(T, k.eps, Z);
+#if WR_LO3_DEGREE == 3
 	f2_t P = f2_fma(Y, k.c3, k.c2);
 	P = f2_fma(Y, P, k.c1);
+#else
+	f2_t P = f2_fma(Y, k.c2, k.c1);
+#endif
 	P = f2_fma(Y, P, k.c0);
 	const f2_t B = f2_mul(U, P);
 	float sls, slc, bs, bc;
@@ -293,6 +302,7 @@ __device__ __forceinline__ void lo3_sincos_n(const uint32_t (&qb)[J], const Lo3R
 	#pragma unroll
 	for (int j = 0; j < J; j++)
 		Y[j] = f2_mul(T[j], T[j]);
+#if WR_LO3_DEGREE == 3
 	#pragma unroll
 	for (int j = 0; j < J; j++) {
 		W[j] = f2_fma(f2_neg(Y[j]), T[j], T[j]);
@@ -306,6 +316,93 @@ __device__ __forceinline__ void lo3_sincos_n(const uint32_t (&qb)[J], const Lo3R
 	#pragma unroll
 	for (int j = 0; j < J; j++)
 		P[j] = f2_fma(Y[j], P[j], k.c0);
+#else
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		W[j] = f2_fma(f2_neg(Y[j]), T[j], T[j]);
+		P[j] = f2_fma(Y[j], k.c2, k.c1);
+	}
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		W[j] = f2_fma(T[j], k.eps, W[j]);
+		P[j] = f2_fma(Y[j], P[j], k.c0);
+	}
+#endif
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		float bs, bc;
+		f2_unpack(f2_mul(W[j], P[j]), bs, bc);
+		sn[j] = __int_as_float(__float_as_int(bs) + ds[j]);
+		cs[j] = __int_as_float(__float_as_int(bc) + dc[j]);
+	}
+}
+
+// lo3_sincos_n in two halves, for a caller that puts other work between them: the table lookups are
+// random 16-bit gathers (two per frame, ~2.6 cycles of the SM's one shared-memory pipe each), and with
+// eight warps gathering they queue -- issued a whole FIR phase ahead of their use, nobody waits for them.
+template <int J>
+__device__ __forceinline__ void lo3_issue_n(const uint32_t (&qb)[J], const Lo3Regs &k, f2_t (&F)[J], int (&ds)[J], int (&dc)[J])
+{
+	uint32_t as[J], ac[J];
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		uint32_t fs, fc;
+		const uint32_t qc = qb[j] + 0x40000000u;      // + a quarter turn
+		asm("prmt.b32 %0, %1, %2, 0x5432;" : "=r"(fs) : "r"(qb[j]), "r"(k.hi));
+		asm("prmt.b32 %0, %1, %2, 0x5432;" : "=r"(fc) : "r"(qc), "r"(k.hi));
+		F[j] = f2_pack(__uint_as_float(fs), __uint_as_float(fc));
+	}
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		float sls, slc;
+		f2_unpack(f2_fma(F[j], k.slotk, k.slotm), sls, slc);
+		as[j] = k.cbase + 2u * __float_as_uint(sls);
+		ac[j] = k.cbase + 2u * __float_as_uint(slc);
+	}
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		asm volatile("ld.shared.s16 %0, [%1];" : "=r"(ds[j]) : "r"(as[j]));
+		asm volatile("ld.shared.s16 %0, [%1];" : "=r"(dc[j]) : "r"(ac[j]));
+	}
+}
+
+template <int J>
+__device__ __forceinline__ void lo3_finish_n(const f2_t (&F)[J], const int (&ds)[J], const int (&dc)[J], const Lo3Regs &k,
+		float (&sn)[J], float (&cs)[J])
+{
+	f2_t T[J], Y[J], W[J], P[J];
+	#pragma unroll
+	for (int j = 0; j < J; j++)
+		T[j] = f2_fma(F[j], k.tscale, k.tbias);
+	#pragma unroll
+	for (int j = 0; j < J; j++)
+		Y[j] = f2_mul(T[j], T[j]);
+#if WR_LO3_DEGREE == 3
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		W[j] = f2_fma(f2_neg(Y[j]), T[j], T[j]);
+		P[j] = f2_fma(Y[j], k.c3, k.c2);
+	}
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		W[j] = f2_fma(T[j], k.eps, W[j]);
+		P[j] = f2_fma(Y[j], P[j], k.c1);
+	}
+	#pragma unroll
+	for (int j = 0; j < J; j++)
+		P[j] = f2_fma(Y[j], P[j], k.c0);
+#else
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		W[j] = f2_fma(f2_neg(Y[j]), T[j], T[j]);
+		P[j] = f2_fma(Y[j], k.c2, k.c1);
+	}
+	#pragma unroll
+	for (int j = 0; j < J; j++) {
+		W[j] = f2_fma(T[j], k.eps, W[j]);
+		P[j] = f2_fma(Y[j], P[j], k.c0);
+	}
+#endif
 	#pragma unroll
 	for (int j = 0; j < J; j++) {
 		float bs, bc;

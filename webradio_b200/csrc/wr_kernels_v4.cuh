@@ -161,9 +161,13 @@ __device__ __forceinline__ void cp_async_wait()
 // One stage of a run: SFR frames mixed and applied to the live outputs.  CX = how many of the
 // stage's leading frames still carry the OLDEST output (tap row AP); FIN = that output completes
 // in this stage (after frame CX-1), and `fin` receives it.
+#ifndef WR_V4_AHEAD
+#define WR_V4_AHEAD 0          // 1: the NCO of stage n+1 is computed during stage n, its table gathers issued in front of the FIR
+#endif
 template <int N1, int D1, int CX, bool FIN, bool U8 = false>
 __device__ __forceinline__ void v4_stage(uint32_t st32, f2_t (&acc)[V4Geo<N1, D1>::ROWS],
-		uint32_t q0, uint32_t qs, const Lo3Regs &lo, uint32_t tap32, f2_t nz, f2_t &fin)
+		uint32_t q0, uint32_t qs, const Lo3Regs &lo, uint32_t tap32, f2_t nz, f2_t &fin,
+		float (&snc)[V4Geo<N1, D1>::SFR], float (&csc)[V4Geo<N1, D1>::SFR])
 {
 	using G = V4Geo<N1, D1>;
 	constexpr int SFR = G::SFR, AP = G::AP, TS = G::TS, S = G::S;
@@ -188,14 +192,32 @@ __device__ __forceinline__ void v4_stage(uint32_t st32, f2_t (&acc)[V4Geo<N1, D1
 			lds128p(st32 + 8u * (unsigned)i, raw[i], raw[i + 1]);
 	}
 	float4 t[G::ROWS];         // the taps of four consecutive frames, one 128-bit broadcast load per live row
+#if WR_V4_AHEAD
+	static_assert(WR_V4_HB == 1, "WR_V4_AHEAD works on whole stages");
+	// the NEXT stage's table gathers go out now; its polynomial follows this stage's FIR
+	f2_t Fn[SFR];
+	int dsn[SFR], dcn[SFR];
+	{
+		uint32_t q[SFR];
+		#pragma unroll
+		for (int i = 0; i < SFR; i++)
+			q[i] = q0 + (uint32_t)(SFR + i) * qs;
+		lo3_issue_n<SFR>(q, lo, Fn, dsn, dcn);
+	}
+#endif
 	#pragma unroll
 	for (int h = 0; h < WR_V4_HB; h++) {
+#if WR_V4_AHEAD
+		float (&sn)[SFR] = snc;
+		float (&cs)[SFR] = csc;
+#else
 		uint32_t q[H];
 		float sn[H], cs[H];
 		#pragma unroll
 		for (int i = 0; i < H; i++)
 			q[i] = q0 + (uint32_t)(h * H + i) * qs;
 		lo3_sincos_n<H>(q, lo, sn, cs);
+#endif
 		#pragma unroll
 		for (int i = 0; i < H; i++) {
 			const int fi = h * H + i;
@@ -226,6 +248,9 @@ __device__ __forceinline__ void v4_stage(uint32_t st32, f2_t (&acc)[V4Geo<N1, D1
 			}
 		}
 	}
+#if WR_V4_AHEAD
+	lo3_finish_n<SFR>(Fn, dsn, dcn, lo, snc, csc);
+#endif
 }
 
 // What a run carries from stage to stage (registers once everything is inlined).
@@ -234,6 +259,7 @@ struct V4Run {
 	using G = V4Geo<N1, D1, U8>;
 	static constexpr int NCH = (int)(G::kRowBytes / G::CH); // chunks a lane copies per stage (32 rows * chunks per row / 32 lanes)
 	f2_t acc[G::ROWS];         // live outputs by age
+	float sn[G::SFR], cs[G::SFR];   // (WR_V4_AHEAD) the NCO of the stage about to be computed
 	uint32_t q;                // biased doubled phase of the next frame
 	uint32_t qs;               // ... and its step per frame
 	uint32_t st32;             // this lane's row in the ring slot of the stage being computed
@@ -310,7 +336,7 @@ __device__ __forceinline__ void v4_step(V4Run<N1, D1, U8> &r, const Lo3Regs &lo,
 	// ... and the slot of stage n-1 is free: every lane is past its reads of it
 	const uint32_t prev32 = (r.st32 == r.stEnd - r.ringBytes + 0u) ? r.stEnd - G::kStageBytes : r.st32 - G::kStageBytes;
 	v4_fetch<N1, D1, NS - 1, U8>(r, prev32);
-	v4_stage<N1, D1, CX, FIN, U8>(r.st32, r.acc, r.q, r.qs, lo, tapsStage32, nz, fin);
+	v4_stage<N1, D1, CX, FIN, U8>(r.st32, r.acc, r.q, r.qs, lo, tapsStage32, nz, fin, r.sn, r.cs);
 	r.q += (uint32_t)G::SFR * r.qs;
 	r.st32 += G::kStageBytes;
 	if (r.st32 == r.stEnd)
@@ -558,6 +584,15 @@ __global__ void __launch_bounds__(WMAX * 32, 1) chan_kernel_v4(const ChanArgs a,
 			r.acc[i] = 0ull;
 		r.q = ((ph0 + (uint32_t)(int32_t)f0 * (uint32_t)step) << 1) + 0x80000000u;
 		r.qs = 2u * (uint32_t)step;
+#if WR_V4_AHEAD
+		{
+			uint32_t q[SFR];
+			#pragma unroll
+			for (int i = 0; i < SFR; i++)
+				q[i] = r.q + (uint32_t)i * r.qs;
+			lo3_sincos_n<SFR>(q, lo, r.sn, r.cs);
+		}
+#endif
 		float2 *out = a.chan + (size_t)rx * a.chan_stride;
 		unsigned kdone = k0 - (unsigned)AP;                     // the output that completes in the current period (wraps below zero at first)
 		for (unsigned p = 0; p < nPeriods; p++) {

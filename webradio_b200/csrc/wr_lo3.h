@@ -9,7 +9,7 @@
 //     t    = fma(F, 2^-15, -257)                = s / 32768, exact           (angle = pi t)
 //     y    = t * t
 //     u    = fma(t, eps, fma(-y, t, t))         (t - t^3: zero crossings at t = 0, +-1; eps: see below)
-//     base = u * (c0 + y (c1 + y (c2 + y c3)))              minimax fit of sin(pi t) / (t (1 - t^2))
+//     base = u * (c0 + y (c1 + y (c2 + y c3)))              fit of sin(pi t) / (t (1 - t^2)); or a quadratic, below
 //     table[index] == int_as_float(float_as_int(base) + delta[index])        BIT-EXACT
 //
 // and the padded position of an entry in shared memory comes out of the same register pair:
@@ -25,10 +25,28 @@
 
 #include <stdint.h>
 
+// WR_LO3_DEGREE: degree of the base polynomial in y.
+// 3 (default): the minimax cubic, corrections up to 28 019 ULP.
+// 2: a QUADRATIC in y is enough for 16-bit corrections -- if it is the right one.  The entries that
+// need the largest corrections are not the polynomial's fault: the reference's table is sinf of an
+// angle ROUNDED TO FLOAT, so just below the zero crossings (index 32767, 65531...) the entries carry
+// half an ULP of pi or 2 pi of absolute error, up to 28 000 ULP of their own tiny values.  The plain
+// minimax quadratic (8.7e-4 relative, 7 300 ULP) adds to that at t -> 1 and index 32767 would need 17
+// bits; pinning P(1) = pi/2 (1 - 3.4e-4) and minimising the rest leaves 1.1e-3 (18 500 ULP) in the bulk
+// and 23 801 ULP at worst, for one packed fma per frame less.  (Measured: DESIGN.md 5.1a.)
+#ifndef WR_LO3_DEGREE
+#define WR_LO3_DEGREE 3
+#endif
+#if WR_LO3_DEGREE == 3
 #define WR_LO3_C0     3.141528367996216f
 #define WR_LO3_C1    (-2.024317979812622f)
 #define WR_LO3_C2     0.5156225562095642f
 #define WR_LO3_C3    (-0.06206892058253288f)
+#else
+#define WR_LO3_C0     3.1380698680877686f
+#define WR_LO3_C1    (-1.9768874645233154f)
+#define WR_LO3_C2     0.4090798795223236f
+#endif
 #define WR_LO3_TSCALE 3.0517578125e-05f      /* 2^-15 */
 #define WR_LO3_TBIAS  (-257.0f)
 #define WR_LO3_SLOTK  1.0322265625f          /* 1057/1024 */
