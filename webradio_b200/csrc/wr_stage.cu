@@ -253,11 +253,13 @@ int wr_stage_fir(wr_stage *s, const float *in_host, unsigned nframes, unsigned d
 		WR_CUDA(cudaMemcpyAsync(blk + hist, in_host, sizeof(float) * ch * nframes, cudaMemcpyHostToDevice, s->st));
 	if (nout) {
 		const unsigned threads = 128;
+		// (whole 16-byte groups: the compiler fetches the last one to three taps with one 128-bit load)
+		const size_t tapBytes = sizeof(float) * ((s->ntaps + 3u) & ~3u);
 		if (ch == 2)
-			stage_fir_kernel<2><<<grid_for(nout, threads), threads, sizeof(float) * s->ntaps, s->st>>>(
+			stage_fir_kernel<2><<<grid_for(nout, threads), threads, tapBytes, s->st>>>(
 					blk, s->d_taps, s->d_out, nout, s->ntaps, decim);
 		else
-			stage_fir_kernel<1><<<grid_for(nout, threads), threads, sizeof(float) * s->ntaps, s->st>>>(
+			stage_fir_kernel<1><<<grid_for(nout, threads), threads, tapBytes, s->st>>>(
 					blk, s->d_taps, s->d_out, nout, s->ntaps, decim);
 		s->launches++;
 		WR_CUDA(cudaGetLastError());
